@@ -1,0 +1,206 @@
+"""Synthetic input surfaces for the ACVD clustering path.
+
+Every generator returns ``(points float32 [V,3], triangles int32 [F,3])`` with
+outward (counter-clockwise) orientation, fixed seeds, and closed topology.
+Points are float32 because the reference stores mesh points in a default
+``vtkPoints`` (float32) and widens to double on read
+(reference Common/vtkSurfaceBase.cxx:1389-1391).
+
+Workloads of BASELINE.json map to:
+  C1  geodesic_icosphere(128)                       V = 163 842
+  C2  noisy_torus(2000, 1300)                       V = 2 600 000
+  C3  ridged_ellipsoid(316)                         V = 998 562
+  C4  displaced_sphere(2000)                        V = 40 000 002
+  C5  thin_torus(16000, 10000)                      V = 160 000 000
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_T = (1.0 + 5.0 ** 0.5) / 2.0
+_ICO_V = np.array(
+    [[-1, _T, 0], [1, _T, 0], [-1, -_T, 0], [1, -_T, 0],
+     [0, -1, _T], [0, 1, _T], [0, -1, -_T], [0, 1, -_T],
+     [_T, 0, -1], [_T, 0, 1], [-_T, 0, -1], [-_T, 0, 1]], dtype=np.float64)
+_ICO_F = np.array(
+    [[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11],
+     [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+     [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9],
+     [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+
+
+def geodesic_icosphere(n: int, dtype=np.float32):
+    """Class-I geodesic subdivision of the icosahedron with frequency ``n``.
+
+    V = 10 n^2 + 2, F = 20 n^2, E = 30 n^2.  ``n = 2**L`` gives the same vertex
+    count as L rounds of 1->4 subdivision (reference Common/vtkSurface.cxx:605).
+    Vertex ids: 12 corners, then 30 x (n-1) edge points, then per-face interior
+    points row by row, so a face's interior is contiguous in memory.
+    """
+    assert n >= 1
+    corners = _ICO_V / np.linalg.norm(_ICO_V[0])
+    edges = {}
+    for f in _ICO_F:
+        for a, b in ((f[0], f[1]), (f[1], f[2]), (f[2], f[0])):
+            key = (min(a, b), max(a, b))
+            if key not in edges:
+                edges[key] = len(edges)
+    n_edge_pts = n - 1
+    n_int = (n - 1) * (n - 2) // 2
+    V = 12 + 30 * n_edge_pts + 20 * n_int
+    pts = np.empty((V, 3), dtype=np.float64)
+    pts[:12] = corners
+    k = np.arange(1, n, dtype=np.float64)[:, None]
+    for (a, b), e in edges.items():
+        base = 12 + e * n_edge_pts
+        pts[base:base + n_edge_pts] = (corners[a] * (n - k) + corners[b] * k) / n
+    tris = np.empty((20 * n * n, 3), dtype=np.int64)
+    ii, jj = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    tpos = 0
+    for fi, (A, B, C) in enumerate(_ICO_F):
+        T = np.full((n + 1, n + 1), -1, dtype=np.int64)
+        T[0, 0], T[n, 0], T[0, n] = A, B, C
+        if n > 1:
+            kk = np.arange(1, n)
+
+            def edge_ids(a, b):
+                e = edges[(min(a, b), max(a, b))]
+                base = 12 + e * n_edge_pts
+                return base + (kk - 1) if a < b else base + (n - kk - 1)
+
+            T[kk, 0] = edge_ids(A, B)          # j = 0, i = k along A->B
+            T[0, kk] = edge_ids(A, C)          # i = 0, j = k along A->C
+            T[n - kk, kk] = edge_ids(B, C)     # i + j = n, j = k along B->C
+        if n_int > 0:
+            m = (ii >= 1) & (jj >= 1) & (ii + jj <= n - 1)
+            i_in, j_in = ii[m], jj[m]
+            # rows j = 1..n-2 hold (n-1-j) interior points each
+            row_off = (j_in - 1) * (n - 1) - (j_in - 1) * j_in // 2
+            ids = 12 + 30 * n_edge_pts + fi * n_int + row_off + (i_in - 1)
+            T[i_in, j_in] = ids
+            w = (corners[A][None, :] * (n - i_in - j_in)[:, None]
+                 + corners[B][None, :] * i_in[:, None]
+                 + corners[C][None, :] * j_in[:, None]) / n
+            pts[ids] = w
+        up = (ii + jj <= n - 1)
+        iu, ju = ii[up], jj[up]
+        nu = iu.size
+        tris[tpos:tpos + nu, 0] = T[iu, ju]
+        tris[tpos:tpos + nu, 1] = T[iu + 1, ju]
+        tris[tpos:tpos + nu, 2] = T[iu, ju + 1]
+        tpos += nu
+        dn = (ii + jj <= n - 2)
+        idn, jdn = ii[dn], jj[dn]
+        nd = idn.size
+        tris[tpos:tpos + nd, 0] = T[idn + 1, jdn]
+        tris[tpos:tpos + nd, 1] = T[idn + 1, jdn + 1]
+        tris[tpos:tpos + nd, 2] = T[idn, jdn + 1]
+        tpos += nd
+    assert tpos == tris.shape[0]
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    return pts.astype(dtype), tris.astype(np.int32)
+
+
+def torus_grid(nu: int, nv: int, R: float = 1.0, r: float = 0.35, noise: float = 0.0,
+               seed: int = 1, dtype=np.float32, return_uv: bool = False):
+    """Closed torus on an ``nu`` (major) x ``nv`` (minor) grid, quads split on a fixed
+    diagonal; V = nu*nv, F = 2V, E = 3V.  ``noise`` is the sigma of a radial
+    (tube-normal) Gaussian perturbation."""
+    u = (np.arange(nu, dtype=np.float64) * (2 * np.pi / nu))[:, None]
+    v = (np.arange(nv, dtype=np.float64) * (2 * np.pi / nv))[None, :]
+    rr = np.full((nu, nv), r, dtype=np.float64)
+    if noise > 0:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        rr = rr + rng.normal(0.0, noise, size=(nu, nv))
+    x = (R + rr * np.cos(v)) * np.cos(u)
+    y = (R + rr * np.cos(v)) * np.sin(u)
+    z = rr * np.sin(v) + 0 * u
+    pts = np.stack([x, y, z], axis=-1).reshape(-1, 3).astype(dtype)
+    i = np.arange(nu, dtype=np.int64)[:, None]
+    j = np.arange(nv, dtype=np.int64)[None, :]
+    i1 = (i + 1) % nu
+    j1 = (j + 1) % nv
+    a = (i * nv + j).ravel()
+    b = (i1 * nv + j).ravel()
+    c = (i1 * nv + j1).ravel()
+    d = (i * nv + j1).ravel()
+    tris = np.empty((2 * nu * nv, 3), dtype=np.int32)
+    tris[0::2, 0], tris[0::2, 1], tris[0::2, 2] = a, b, c
+    tris[1::2, 0], tris[1::2, 1], tris[1::2, 2] = a, c, d
+    if return_uv:
+        uu = np.broadcast_to(u, (nu, nv)).ravel()
+        vv = np.broadcast_to(v, (nu, nv)).ravel()
+        return pts, tris, uu, vv
+    return pts, tris
+
+
+def torus_curvature_indicator(nu: int, nv: int, R: float = 1.0, r: float = 0.35):
+    """Analytic curvature indicator sqrt(k1^2 + k2^2) of the *smooth* torus on the same grid
+    (k1 = 1/r, k2 = cos v / (R + r cos v)).  Stands in for vtkCurvatureMeasure
+    (reference DiscreteRemeshing/vtkDiscreteRemeshing.h:640-653) until §8f-2 is built;
+    runs that use it are labelled "analytic-curvature"."""
+    v = (np.arange(nv, dtype=np.float64) * (2 * np.pi / nv))[None, :]
+    k1 = 1.0 / r
+    k2 = np.cos(v) / (R + r * np.cos(v))
+    ind = np.sqrt(k1 * k1 + k2 * k2)
+    return np.broadcast_to(ind, (nu, nv)).ravel().copy()
+
+
+def noisy_torus(nu: int = 2000, nv: int = 1300, dtype=np.float32):
+    """C2: R=1, r=0.35, radial Gaussian noise sigma=0.002, seed 1."""
+    return torus_grid(nu, nv, 1.0, 0.35, noise=0.002, seed=1, dtype=dtype)
+
+
+def thin_torus(nu: int = 16000, nv: int = 10000, dtype=np.float32):
+    """C5: R=1, r=0.078125 -> 8:1 elongated cells along the major circle."""
+    return torus_grid(nu, nv, 1.0, 0.078125, dtype=dtype)
+
+
+def displaced_sphere(n: int = 2000, amp: float = 0.05, seed: int = 2, dtype=np.float32):
+    """C4: geodesic icosphere radially displaced by amp * sum_k a_k sin(f_k d_k.p + phi_k)."""
+    pts, tris = geodesic_icosphere(n, dtype=np.float64)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nk = 6
+    d = rng.normal(size=(nk, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    f = rng.uniform(2.0, 12.0, size=nk)
+    phi = rng.uniform(0, 2 * np.pi, size=nk)
+    a = rng.uniform(0.5, 1.0, size=nk)
+    a /= a.sum()
+    disp = np.zeros(pts.shape[0], dtype=np.float64)
+    for k in range(nk):
+        disp += a[k] * np.sin(f[k] * (pts @ d[k]) + phi[k])
+    pts *= (1.0 + amp * disp)[:, None]
+    return pts.astype(dtype), tris
+
+
+def ridged_ellipsoid(n: int = 316, axes=(1.0, 0.6, 0.4), ridge: float = 0.03, freq: int = 24,
+                     dtype=np.float32):
+    """C3: geodesic icosphere mapped to an ellipsoid with sinusoidal ridges r(1 + ridge sin(freq theta))."""
+    pts, tris = geodesic_icosphere(n, dtype=np.float64)
+    theta = np.arctan2(pts[:, 1], pts[:, 0])
+    rad = 1.0 + ridge * np.sin(freq * theta)
+    pts = pts * np.asarray(axes, dtype=np.float64)[None, :] * rad[:, None]
+    return pts.astype(dtype), tris
+
+
+def workload(name: str):
+    """Named workloads used by bench.py and the tests."""
+    if name == "C1":
+        p, t = geodesic_icosphere(128)
+        return dict(points=p, triangles=t, K=3000, metric="iso", gradation=0.0, indicator=None)
+    if name == "C2":
+        p, t = noisy_torus()
+        return dict(points=p, triangles=t, K=100000, metric="qem", gradation=1.5,
+                    indicator=torus_curvature_indicator(2000, 1300))
+    if name == "C2s":  # 1/16-size C2 for CPU-side tests
+        p, t = torus_grid(500, 325, noise=0.002, seed=1)
+        return dict(points=p, triangles=t, K=6250, metric="qem", gradation=1.5,
+                    indicator=torus_curvature_indicator(500, 325))
+    if name == "C4":
+        p, t = displaced_sphere(2000)
+        return dict(points=p, triangles=t, K=400000, metric="qem", gradation=0.0, indicator=None)
+    if name == "C4s":  # 1/100-size C4
+        p, t = displaced_sphere(200)
+        return dict(points=p, triangles=t, K=4000, metric="qem", gradation=0.0, indicator=None)
+    raise KeyError(name)
