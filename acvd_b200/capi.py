@@ -1,0 +1,288 @@
+"""ctypes binding of the C ABI in include/acvd_b200.h.
+
+This is plumbing only: every call goes straight into ``libacvd_b200.so``.  There is no CPU
+fallback — if the library is missing or no CUDA device is present the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacvd_b200.so")
+
+ISO, QEM, ANISO, ANISOQ = 0, 1, 2, 3
+METRICS = {"iso": ISO, "qem": QEM, "aniso": ANISO, "anisoq": ANISOQ}
+NCCL_ID_BYTES = 128
+
+
+class AcvdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"acvd_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("unconstrained_init", C.c_int32), ("quadrics_level", C.c_int32), ("connexity", C.c_int32),
+        ("max_loops", C.c_int32), ("max_convergences", C.c_int32), ("early_stop_div", C.c_int32),
+        ("log_energy", C.c_int32), ("rounds_per_sync", C.c_int32), ("sv_threshold", C.c_double),
+    ]
+
+
+class Report(C.Structure):
+    _fields_ = [
+        ("rounds", C.c_int64), ("convergences", C.c_int64), ("tests", C.c_int64), ("modifications", C.c_int64),
+        ("proposals", C.c_int64), ("disconnected", C.c_int64), ("energy", C.c_double), ("ms_total", C.c_double),
+        ("ms_propose", C.c_double), ("ms_commit", C.c_double), ("ms_clean", C.c_double),
+        ("propose_launches", C.c_int64), ("propose_bytes", C.c_int64),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/acvd_b200.h declares: (name, restype, argtypes)
+_vp, _i32, _i64, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+SYMBOLS = [
+    ("acvd_payload_size", C.c_int, [C.c_int]),
+    ("acvd_create", C.c_int, [C.POINTER(_vp), C.c_int]),
+    ("acvd_destroy", C.c_int, [_vp]),
+    ("acvd_last_error", C.c_char_p, [_vp]),
+    ("acvd_abi_version", C.c_int, []),
+    ("acvd_set_mesh", C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    ("acvd_get_num_edges", C.c_int, [_vp, C.POINTER(_i64)]),
+    ("acvd_get_csr", C.c_int, [_vp, _vp, _vp]),
+    ("acvd_build_items", C.c_int, [_vp, C.c_int, _d, _vp, _vp]),
+    ("acvd_set_items", C.c_int, [_vp, C.c_int, _vp]),
+    ("acvd_get_items", C.c_int, [_vp, _vp]),
+    ("acvd_get_vertex_areas", C.c_int, [_vp, _vp]),
+    ("acvd_set_num_clusters", C.c_int, [_vp, _i32]),
+    ("acvd_set_clustering", C.c_int, [_vp, _vp]),
+    ("acvd_get_clustering", C.c_int, [_vp, _vp]),
+    ("acvd_set_frozen", C.c_int, [_vp, _vp]),
+    ("acvd_set_fixed_clusters", C.c_int, [_vp, _vp, _i32]),
+    ("acvd_initial_sampling", C.c_int, [_vp]),
+    ("acvd_minimize", C.c_int, [_vp, C.POINTER(Params), C.POINTER(Report)]),
+    ("acvd_recompute_statistics", C.c_int, [_vp, C.c_int, C.c_int]),
+    ("acvd_clean_clustering", C.c_int, [_vp, C.POINTER(_i32)]),
+    ("acvd_fill_holes", C.c_int, [_vp]),
+    ("acvd_reassign_round", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    ("acvd_get_cluster_stats", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    ("acvd_global_energy", C.c_int, [_vp, C.POINTER(_d)]),
+    ("acvd_get_energy_log", C.c_int, [_vp, _vp, _i32, C.POINTER(_i32)]),
+    ("acvd_representative_points", C.c_int, [_vp, _i32, _vp, _vp, _i32, _d, _vp]),
+    ("acvd_boundary_flags", C.c_int, [_vp, _vp]),
+    ("acvd_cluster_adjacency", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    ("acvd_dual_triangles", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    ("acvd_dist_unique_id", C.c_int, [_vp]),
+    ("acvd_dist_init", C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+]
+
+_LIB = None
+
+
+def load_library():
+    """Load libacvd_b200.so (built in-tree by acvd_b200.build).  Raises if it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise AcvdError(-2, f"{LIB_PATH} not built: run `python -m acvd_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One clustering context on one CUDA device (acvd_ctx)."""
+
+    def __init__(self, device: int = -1):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.acvd_create(C.byref(h), device)
+        if rc != 0:
+            raise AcvdError(rc, self.L.acvd_last_error(None).decode())
+        self.h = h
+        self.V = self.F = self.K = 0
+        self.metric = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.acvd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AcvdError(rc, self.L.acvd_last_error(self.h).decode())
+
+    # ---- mesh / items
+    def set_mesh(self, points, triangles):
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        t = np.ascontiguousarray(triangles, dtype=np.int32)
+        self.V, self.F = p.shape[0], t.shape[0]
+        self._ck(self.L.acvd_set_mesh(self.h, self.V, self.F, _p(p), _p(t)))
+
+    def num_edges(self):
+        e = C.c_int64()
+        self._ck(self.L.acvd_get_num_edges(self.h, C.byref(e)))
+        return e.value
+
+    def csr(self):
+        E = self.num_edges()
+        rp = np.zeros(self.V + 1, dtype=np.int32)
+        col = np.zeros(2 * E, dtype=np.int32)
+        self._ck(self.L.acvd_get_csr(self.h, _p(rp), _p(col)))
+        return rp, col
+
+    def build_items(self, metric="iso", gradation=0.0, custom_weights=None, principal_dirs=None):
+        m = METRICS[metric] if isinstance(metric, str) else int(metric)
+        cw = None if custom_weights is None else np.ascontiguousarray(custom_weights, dtype=np.float64)
+        pd = None if principal_dirs is None else np.ascontiguousarray(principal_dirs, dtype=np.float32)
+        self._ck(self.L.acvd_build_items(self.h, m, float(gradation), _p(cw), _p(pd)))
+        self.metric = m
+
+    def set_items(self, metric, payload):
+        m = METRICS[metric] if isinstance(metric, str) else int(metric)
+        a = np.ascontiguousarray(payload, dtype=np.float64)
+        assert a.shape == (self.V, self.L.acvd_payload_size(m))
+        self._ck(self.L.acvd_set_items(self.h, m, _p(a)))
+        self.metric = m
+
+    def items(self):
+        out = np.zeros((self.V, self.L.acvd_payload_size(self.metric)))
+        self._ck(self.L.acvd_get_items(self.h, _p(out)))
+        return out
+
+    def vertex_areas(self):
+        out = np.zeros(self.V)
+        self._ck(self.L.acvd_get_vertex_areas(self.h, _p(out)))
+        return out
+
+    # ---- clusters
+    def set_num_clusters(self, K):
+        self._ck(self.L.acvd_set_num_clusters(self.h, int(K)))
+        self.K = int(K)
+
+    def set_clustering(self, cl):
+        a = np.ascontiguousarray(cl, dtype=np.int32)
+        assert a.size == self.V
+        self._ck(self.L.acvd_set_clustering(self.h, _p(a)))
+
+    def clustering(self, out=None):
+        if out is None:
+            out = np.zeros(self.V, dtype=np.int32)
+        self._ck(self.L.acvd_get_clustering(self.h, _p(out)))
+        return out
+
+    def set_frozen(self, flags):
+        a = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        self._ck(self.L.acvd_set_frozen(self.h, _p(a)))
+
+    def set_fixed_clusters(self, items):
+        a = np.ascontiguousarray(items, dtype=np.int64)
+        self._ck(self.L.acvd_set_fixed_clusters(self.h, _p(a), a.size))
+
+    def initial_sampling(self):
+        self._ck(self.L.acvd_initial_sampling(self.h))
+
+    # ---- hot path
+    def minimize(self, **kw) -> dict:
+        p = Params()
+        p.quadrics_level = 3
+        for k, v in kw.items():
+            setattr(p, k, v)
+        r = Report()
+        self._ck(self.L.acvd_minimize(self.h, C.byref(p), C.byref(r)))
+        return r.asdict()
+
+    def recompute_statistics(self, constrained=1, quadrics_level=3):
+        self._ck(self.L.acvd_recompute_statistics(self.h, int(constrained), int(quadrics_level)))
+
+    def clean_clustering(self):
+        d = C.c_int32()
+        self._ck(self.L.acvd_clean_clustering(self.h, C.byref(d)))
+        return d.value
+
+    def fill_holes(self):
+        self._ck(self.L.acvd_fill_holes(self.h))
+
+    def reassign_round(self, constrained=1, quadrics_level=3, connexity=0):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.L.acvd_reassign_round(self.h, constrained, quadrics_level, connexity, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(proposals=a.value, modifications=b.value, tests=c.value)
+
+    def cluster_stats(self):
+        np_ = self.L.acvd_payload_size(self.metric)
+        sums = np.zeros((self.K, np_))
+        cen = np.zeros((self.K, 3))
+        en = np.zeros(self.K)
+        sz = np.zeros(self.K, dtype=np.int32)
+        self._ck(self.L.acvd_get_cluster_stats(self.h, _p(sums), _p(cen), _p(en), _p(sz)))
+        return sums, cen, en, sz
+
+    def global_energy(self):
+        e = C.c_double()
+        self._ck(self.L.acvd_global_energy(self.h, C.byref(e)))
+        return e.value
+
+    def energy_log(self):
+        n = C.c_int32()
+        self._ck(self.L.acvd_get_energy_log(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value)
+        self._ck(self.L.acvd_get_energy_log(self.h, _p(out), n.value, C.byref(n)))
+        return out
+
+    def representative_points(self, quadrics9, points3, max_sv=3, sv_threshold=1e-3):
+        q = np.ascontiguousarray(quadrics9, dtype=np.float64).reshape(-1, 9)
+        p = np.array(points3, dtype=np.float64).reshape(-1, 3).copy()
+        rd = np.zeros(q.shape[0], dtype=np.int32)
+        self._ck(self.L.acvd_representative_points(self.h, q.shape[0], _p(q), _p(p), max_sv, sv_threshold, _p(rd)))
+        return p, rd
+
+    # ---- integer stages
+    def boundary_flags(self):
+        out = np.zeros(self.V, dtype=np.uint8)
+        self._ck(self.L.acvd_boundary_flags(self.h, _p(out)))
+        return out
+
+    def cluster_adjacency(self):
+        n = C.c_int64()
+        self._ck(self.L.acvd_cluster_adjacency(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int64)
+        self._ck(self.L.acvd_cluster_adjacency(self.h, _p(out), n.value, C.byref(n)))
+        return np.stack([out >> 32, out & 0xFFFFFFFF], axis=1).astype(np.int32)
+
+    def dual_triangles(self):
+        n = C.c_int64()
+        self._ck(self.L.acvd_dual_triangles(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 3), dtype=np.int32)
+        if n.value:
+            self._ck(self.L.acvd_dual_triangles(self.h, _p(out), n.value, C.byref(n)))
+        return out
+
+    # ---- multi-GPU
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        L = load_library()
+        buf = C.create_string_buffer(NCCL_ID_BYTES)
+        rc = L.acvd_dist_unique_id(buf)
+        if rc != 0:
+            raise AcvdError(rc, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def dist_init(self, rank, world, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, NCCL_ID_BYTES)
+        self._ck(self.L.acvd_dist_init(self.h, rank, world, buf))

@@ -1,0 +1,812 @@
+// acvd_b200 C ABI (include/acvd_b200.h): context, host-side convergence driver, kernel launches.
+// sm_100a only; there is no CPU path — every entry point needs a live CUDA context.
+#include "../../include/acvd_b200.h"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cleanup.cuh"
+#include "common.cuh"
+#include "ctx.cuh"
+#include "host_sampling.hpp"
+#include "mesh.cuh"
+#include "metric.cuh"
+#include "reassign.cuh"
+
+static void* cub_temp(acvd_ctx* c, size_t bytes) {
+    c->cub_temp.alloc(bytes + 16);
+    return c->cub_temp.p;
+}
+
+static int bits_for(uint64_t maxval) { int b = 1; while (b < 64 && (maxval >> b)) b++; return b; }
+
+// sort 64-bit keys in place (result guaranteed in `keys`), returns nothing; n may be large
+static void sort_keys64(acvd_ctx* c, unsigned long long* keys, unsigned long long* alt, int64_t n, int end_bit) {
+    cub::DoubleBuffer<unsigned long long> db(keys, alt);
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, n, 0, end_bit, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceRadixSort::SortKeys(t, tb, db, n, 0, end_bit, c->stream));
+    if (db.Current() != keys)
+        ACVD_CUDA(cudaMemcpyAsync(keys, db.Current(), n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int acvd_abi_version(void) { return ACVD_B200_ABI_VERSION; }
+extern "C" int acvd_payload_size(int metric) { return (metric < 0 || metric > 3) ? ACVD_EINVAL : payload_np(metric); }
+
+extern "C" const char* acvd_last_error(acvd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int acvd_create(acvd_ctx** out, int device) {
+    if (!out) return fail(nullptr, ACVD_EINVAL, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, ACVD_ENODEVICE, "no CUDA device: acvd_b200 has no CPU path");
+    }
+    acvd_ctx* c = new acvd_ctx();
+    try {
+        if (device < 0) ACVD_CUDA(cudaGetDevice(&device));
+        if (device >= n) { delete c; return fail(nullptr, ACVD_EINVAL, "device index out of range"); }
+        c->device = device;
+        ACVD_CUDA(cudaSetDevice(device));
+        ACVD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto& ev : c->ev) ACVD_CUDA(cudaEventCreate(&ev));
+        ACVD_CUDA(cudaMallocHost(&c->h_ctr, sizeof(RoundCounters)));
+        ACVD_CUDA(cudaMallocHost(&c->h_scalars, 8 * sizeof(unsigned long long)));
+        c->ctr.alloc(1);
+        c->scalars.alloc(8);
+    } catch (const CudaError& err) {
+        std::string m = std::string("CUDA error in acvd_create: ") + cudaGetErrorString(err.code);
+        delete c;
+        return fail(nullptr, ACVD_ECUDA, m);
+    }
+    *out = c;
+    return ACVD_OK;
+}
+
+extern "C" int acvd_destroy(acvd_ctx* c) {
+    if (!c) return ACVD_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    delete c;
+    return ACVD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mesh
+static void build_rows(acvd_ctx* c, unsigned long long* keys, int64_t n_valid, DevBuf<int>& ptr, int* low) {
+    ptr.alloc((size_t)c->V + 1);
+    k_rows_from_sorted<<<grid_for(n_valid + 1), kThreads, 0, c->stream>>>(n_valid, c->V, keys, ptr.p, low);
+    ACVD_LAUNCH_CHECK();
+}
+
+extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz, const int32_t* tri) {
+    ACVD_API_BEGIN(c)
+    if (V <= 0 || F <= 0 || !xyz || !tri) throw std::runtime_error("acvd_set_mesh: bad arguments");
+    c->V = V; c->F = F;
+    c->have_items = false; c->stats_valid = false;
+    c->xyz.alloc(3 * (size_t)V);
+    c->tri.alloc(3 * (size_t)F);
+    ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->h_tri.assign(tri, tri + 3 * (size_t)F);
+    const int vbits = bits_for((uint64_t)V);
+    // --- CSR adjacency: 6F directed half-edges -> sort -> unique
+    {
+        int64_t n = 6 * (int64_t)F;
+        DevBuf<unsigned long long> keys, alt, uniq;
+        DevBuf<int64_t> d_num;
+        keys.alloc(n); alt.alloc(n); uniq.alloc(n); d_num.alloc(1);
+        k_emit_halfedges<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, keys.p);
+        ACVD_LAUNCH_CHECK();
+        sort_keys64(c, keys.p, alt.p, n, 64);   // invalid keys (~0) sort to the end
+        size_t tb = 0;
+        ACVD_CUDA(cub::DeviceSelect::Unique(nullptr, tb, keys.p, uniq.p, d_num.p, n, c->stream));
+        void* t = cub_temp(c, tb);
+        ACVD_CUDA(cub::DeviceSelect::Unique(t, tb, keys.p, uniq.p, d_num.p, n, c->stream));
+        int64_t nu = 0;
+        ACVD_CUDA(cudaMemcpyAsync(&nu, d_num.p, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        unsigned long long last = 0;
+        if (nu > 0) {
+            ACVD_CUDA(cudaMemcpy(&last, uniq.p + (nu - 1), sizeof last, cudaMemcpyDeviceToHost));
+            if (last == ~0ull) nu--;
+        }
+        if (nu >= (int64_t)1 << 31) throw std::runtime_error("acvd_set_mesh: more than 2^31 adjacency entries");
+        c->nnz = nu;
+        c->col.alloc((size_t)std::max<int64_t>(nu, 1));
+        build_rows(c, uniq.p, nu, c->row_ptr, c->col.p);
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    // --- vertex -> face incidence (ascending face id per vertex)
+    {
+        int64_t n = 3 * (int64_t)F;
+        DevBuf<unsigned long long> alt;
+        c->vf_keys.alloc(n); alt.alloc(n);
+        k_emit_incidence<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, c->vf_keys.p);
+        ACVD_LAUNCH_CHECK();
+        sort_keys64(c, c->vf_keys.p, alt.p, n, 64);
+        // inactive faces (key ~0) sort to the end; k_rows_from_sorted clamps their source to V
+        build_rows(c, c->vf_keys.p, n, c->vf_ptr, nullptr);
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_num_edges(acvd_ctx* c, int64_t* E) {
+    if (!c || !E) return fail(c, ACVD_EINVAL, "null argument");
+    *E = c->nnz / 2;
+    return ACVD_OK;
+}
+
+extern "C" int acvd_get_csr(acvd_ctx* c, int32_t* row_ptr, int32_t* col) {
+    ACVD_API_BEGIN(c)
+    if (!c->V) throw std::runtime_error("acvd_get_csr: no mesh");
+    if (row_ptr) ACVD_CUDA(cudaMemcpy(row_ptr, c->row_ptr.p, ((size_t)c->V + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (col) ACVD_CUDA(cudaMemcpy(col, c->col.p, (size_t)c->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// items
+template <int M>
+static void compose_items(acvd_ctx* c, const double* d_sum, double ratio, const float* d_pd) {
+    k_compose_items<M><<<grid_for(c->V), kThreads, 0, c->stream>>>(c->V, d_sum, ratio, c->weight.p, c->area.p, c->xyz.p,
+                                                                  c->tri.p, c->vf_ptr.p, c->vf_keys.p, d_pd, c->items.p);
+    ACVD_LAUNCH_CHECK();
+}
+
+static void compute_areas(acvd_ctx* c) {
+    c->area.alloc(c->V);
+    k_vertex_area<<<grid_for(c->V), kThreads, 0, c->stream>>>(c->V, c->vf_ptr.p, c->vf_keys.p, c->xyz.p, c->tri.p, c->area.p);
+    ACVD_LAUNCH_CHECK();
+}
+
+extern "C" int acvd_build_items(acvd_ctx* c, int metric, double gradation, const double* custom, const float* pd) {
+    ACVD_API_BEGIN(c)
+    if (!c->V) throw std::runtime_error("acvd_build_items: set the mesh first");
+    if (metric < 0 || metric > 3) throw std::runtime_error("acvd_build_items: unknown metric");
+    const int V = c->V;
+    const bool aniso = (metric == M_ANISO || metric == M_ANISOQ);
+    if (aniso && !pd) throw std::runtime_error("acvd_build_items: anisotropic metrics need principal directions");
+    // which runs read the indicator: iso when given (vtkIsotropicMetric...:256-259), qem when gradation > 0 (:333-334),
+    // anisotropic when gradation != 0 (:384-392)
+    bool use_custom = custom && (metric == M_ISO ? true : (metric == M_QEM ? gradation > 0 : gradation != 0));
+    if (!custom && ((metric == M_QEM && gradation > 0) || (aniso && gradation != 0)))
+        throw std::runtime_error("acvd_build_items: gradation needs custom_weights (curvature indicator)");
+    c->metric = metric;
+    c->weight.alloc(V);
+    c->items.alloc((size_t)V * payload_npad(metric));
+    compute_areas(c);
+    DevBuf<double> d_custom, d_sum;
+    DevBuf<float> d_pd;
+    if (use_custom) {
+        d_custom.alloc(V);
+        ACVD_CUDA(cudaMemcpyAsync(d_custom.p, custom, (size_t)V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (aniso) {
+        d_pd.alloc(6 * (size_t)V);
+        ACVD_CUDA(cudaMemcpyAsync(d_pd.p, pd, 6 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    k_raw_weight<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->area.p, d_custom.p, gradation, use_custom ? 1 : 0, aniso ? 1 : 0, c->weight.p);
+    ACVD_LAUNCH_CHECK();
+    d_sum.alloc(1);
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceReduce::Sum(nullptr, tb, c->weight.p, d_sum.p, V, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceReduce::Sum(t, tb, c->weight.p, d_sum.p, V, c->stream));
+    const double ratio = (metric == M_QEM) ? 1e4 : 1e5;   // vtkQEMetricForClustering.h:338 vs 1e5 elsewhere
+    switch (metric) {
+        case M_ISO: compose_items<M_ISO>(c, d_sum.p, ratio, nullptr); break;
+        case M_QEM: compose_items<M_QEM>(c, d_sum.p, ratio, nullptr); break;
+        case M_ANISO: compose_items<M_ANISO>(c, d_sum.p, ratio, d_pd.p); break;
+        default: compose_items<M_ANISOQ>(c, d_sum.p, ratio, d_pd.p); break;
+    }
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_items = true; c->stats_valid = false;
+    ACVD_API_END(c)
+}
+
+__global__ void k_extract_weight(int V, int npad, const double* __restrict__ items, double* w) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) w[v] = items[(int64_t)v * npad + 3];
+}
+
+extern "C" int acvd_set_items(acvd_ctx* c, int metric, const double* payload) {
+    ACVD_API_BEGIN(c)
+    if (!c->V || !payload || metric < 0 || metric > 3) throw std::runtime_error("acvd_set_items: bad arguments");
+    const int V = c->V, np = payload_np(metric), npad = payload_npad(metric);
+    c->metric = metric;
+    c->items.alloc((size_t)V * npad);
+    c->weight.alloc(V);
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)V * np);
+    ACVD_CUDA(cudaMemcpyAsync(tmp.p, payload, (size_t)V * np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_pack_rows<<<grid_for((int64_t)V * npad), kThreads, 0, c->stream>>>(V, np, npad, tmp.p, c->items.p, 1);
+    ACVD_LAUNCH_CHECK();
+    k_extract_weight<<<grid_for(V), kThreads, 0, c->stream>>>(V, npad, c->items.p, c->weight.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_items = true; c->stats_valid = false;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_items(acvd_ctx* c, double* payload) {
+    ACVD_API_BEGIN(c)
+    if (!c->have_items || !payload) throw std::runtime_error("acvd_get_items: no items");
+    const int V = c->V, np = payload_np(c->metric), npad = payload_npad(c->metric);
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)V * np);
+    k_pack_rows<<<grid_for((int64_t)V * npad), kThreads, 0, c->stream>>>(V, np, npad, c->items.p, tmp.p, 0);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(payload, tmp.p, (size_t)V * np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_vertex_areas(acvd_ctx* c, double* areas) {
+    ACVD_API_BEGIN(c)
+    if (!c->V || !areas) throw std::runtime_error("acvd_get_vertex_areas: no mesh");
+    compute_areas(c);
+    ACVD_CUDA(cudaMemcpyAsync(areas, c->area.p, (size_t)c->V * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// clusters
+extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
+    ACVD_API_BEGIN(c)
+    if (K <= 0) throw std::runtime_error("acvd_set_num_clusters: K must be positive");
+    if (!c->have_items) throw std::runtime_error("acvd_set_num_clusters: build or set the items first");
+    const int V = c->V, npad = payload_npad(c->metric);
+    c->K = K;
+    c->cid.alloc(V);
+    c->csize.alloc(K); c->mod_round.alloc(K); c->anchor.alloc(K); c->frozen.alloc(K);
+    c->csum.alloc((size_t)K * npad); c->cenergy.alloc(K); c->ccentroid.alloc(3 * (size_t)K);
+    c->best.alloc(K); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->prop_e.alloc(V);
+    ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)V * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->mod_round.p, 0, (size_t)K * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->anchor.p, 0xff, (size_t)K * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->frozen.p, 0, (size_t)K, c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->csize.p, 0, (size_t)K * sizeof(int), c->stream));
+    std::vector<int> all_null(V, K);
+    ACVD_CUDA(cudaMemcpyAsync(c->cid.p, all_null.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->has_frozen = c->has_anchor = false;
+    c->fixed.clear();
+    c->round = 1;
+    c->stats_valid = false;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_set_clustering(acvd_ctx* c, const int32_t* cl) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !cl) throw std::runtime_error("acvd_set_clustering: set the number of clusters first");
+    ACVD_CUDA(cudaMemcpyAsync(c->cid.p, cl, (size_t)c->V * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats_valid = false;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_clustering(acvd_ctx* c, int32_t* cl) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !cl) throw std::runtime_error("acvd_get_clustering: no clustering");
+    ACVD_CUDA(cudaMemcpyAsync(cl, c->cid.p, (size_t)c->V * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_set_frozen(acvd_ctx* c, const uint8_t* frozen) {
+    ACVD_API_BEGIN(c)
+    if (!c->K) throw std::runtime_error("acvd_set_frozen: set the number of clusters first");
+    if (frozen) {
+        ACVD_CUDA(cudaMemcpy(c->frozen.p, frozen, (size_t)c->K, cudaMemcpyHostToDevice));
+        c->has_frozen = std::any_of(frozen, frozen + c->K, [](uint8_t f) { return f != 0; });
+    } else {
+        ACVD_CUDA(cudaMemset(c->frozen.p, 0, (size_t)c->K));
+        c->has_frozen = false;
+    }
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_set_fixed_clusters(acvd_ctx* c, const int64_t* items, int32_t n) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || n < 0 || n > c->K || (n && !items)) throw std::runtime_error("acvd_set_fixed_clusters: bad arguments");
+    std::vector<int> a(c->K, -1);
+    c->fixed.assign(items, items + n);
+    for (int i = 0; i < n; i++) {
+        if (items[i] < 0 || items[i] >= c->V) throw std::runtime_error("acvd_set_fixed_clusters: item out of range");
+        a[i] = (int)items[i];
+    }
+    ACVD_CUDA(cudaMemcpy(c->anchor.p, a.data(), (size_t)c->K * sizeof(int), cudaMemcpyHostToDevice));
+    c->has_anchor = n > 0;
+    c->stats_valid = false;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_initial_sampling(acvd_ctx* c) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !c->have_items) throw std::runtime_error("acvd_initial_sampling: need items and a cluster count");
+    std::vector<double> w(c->V);
+    ACVD_CUDA(cudaMemcpy(w.data(), c->weight.p, (size_t)c->V * sizeof(double), cudaMemcpyDeviceToHost));
+    HostRings rings;
+    rings.build(c->V, c->F, c->h_tri.data());
+    std::vector<int> out;
+    initial_random_sampling(c->V, c->K, rings, w.data(), c->fixed, out);
+    ACVD_CUDA(cudaMemcpy(c->cid.p, out.data(), (size_t)c->V * sizeof(int), cudaMemcpyHostToDevice));
+    ACVD_CUDA(cudaMemset(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int)));
+    c->stats_valid = false;
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics / clean / fill
+static EvalCfg make_cfg(int constrained, int qlevel, double thr) {
+    EvalCfg cfg;
+    cfg.constrained = constrained; cfg.qlevel = qlevel; cfg.thr = thr > 0 ? thr : 1e-3;
+    return cfg;
+}
+
+// QEM in its unconstrained phase without anchors evaluates the isotropic energy
+static bool qem_as_iso(const acvd_ctx* c, int constrained, int qlevel) {
+    return c->metric == M_QEM && !c->has_anchor && (!constrained || !qlevel);
+}
+
+static void recompute_statistics(acvd_ctx* c, int constrained, int qlevel, double thr) {
+    const int V = c->V, K = c->K;
+    c->sort_k0.alloc(V); c->sort_k1.alloc(V); c->sort_v0.alloc(V); c->sort_v1.alloc(V); c->seg.alloc((size_t)K + 2);
+    ACVD_CUDA(cudaMemcpyAsync(c->sort_k0.p, c->cid.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->sort_v0.p);
+    ACVD_LAUNCH_CHECK();
+    size_t tb = 0;
+    const int end_bit = bits_for((uint64_t)K + 1);
+    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, c->sort_k0.p, c->sort_k1.p, c->sort_v0.p, c->sort_v1.p, V, 0, end_bit, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, c->sort_k0.p, c->sort_k1.p, c->sort_v0.p, c->sort_v1.p, V, 0, end_bit, c->stream));
+    k_segments<<<grid_for(K + 2), kThreads, 0, c->stream>>>(V, K, c->sort_k1.p, c->seg.p);
+    ACVD_LAUNCH_CHECK();
+    EvalCfg cfg = make_cfg(constrained, qlevel, thr);
+    const int* anchor = c->has_anchor ? c->anchor.p : nullptr;
+    const int blocks = grid_for((int64_t)K * 32);
+#define STATS(MM, EE) k_cluster_stats<MM, EE><<<blocks, kThreads, 0, c->stream>>>(K, c->seg.p, c->sort_v1.p, c->items.p, c->csum.p, \
+                                                                        c->cenergy.p, c->ccentroid.p, c->csize.p, anchor, c->xyz.p, cfg)
+    switch (c->metric) {
+        case M_ISO: STATS(M_ISO, M_ISO); break;
+        case M_QEM:
+            if (qem_as_iso(c, constrained, qlevel)) STATS(M_QEM, M_ISO);   // same formula as the rounds use in this phase
+            else STATS(M_QEM, M_QEM);
+            break;
+        case M_ANISO: STATS(M_ANISO, M_ANISO); break;
+        default: STATS(M_ANISOQ, M_ANISOQ); break;
+    }
+#undef STATS
+    ACVD_LAUNCH_CHECK();
+    c->stats_valid = true;
+    c->stats_constrained = constrained; c->stats_qlevel = qlevel;
+}
+
+extern "C" int acvd_recompute_statistics(acvd_ctx* c, int constrained, int qlevel) {
+    ACVD_API_BEGIN(c)
+    if (!c->K) throw std::runtime_error("acvd_recompute_statistics: no clustering");
+    recompute_statistics(c, constrained, qlevel, 0);
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+static int clean_clustering(acvd_ctx* c) {
+    const int V = c->V, K = c->K;
+    c->label.alloc(V); c->comp_size.alloc(V); c->n_comp.alloc(K); c->winner.alloc(K);
+    k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->label.p);
+    ACVD_LAUNCH_CHECK();
+    int* d_changed = reinterpret_cast<int*>(c->scalars.p);
+    for (int iter = 0; iter < 100000; iter++) {
+        ACVD_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(int), c->stream));
+        for (int rep = 0; rep < 4; rep++) {
+            k_cc_propagate<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, d_changed);
+            ACVD_LAUNCH_CHECK();
+        }
+        int changed = 0;
+        ACVD_CUDA(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        if (!changed) break;
+    }
+    ACVD_CUDA(cudaMemsetAsync(c->comp_size.p, 0, (size_t)V * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->n_comp.p, 0, (size_t)K * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->winner.p, 0, (size_t)K * sizeof(unsigned long long), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    const int* anchor = c->has_anchor ? c->anchor.p : nullptr;
+    k_cc_sizes<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, anchor);
+    k_cc_winner<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, c->n_comp.p, c->winner.p);
+    k_count_ge2<<<grid_for(K), kThreads, 0, c->stream>>>(K, c->n_comp.p, c->scalars.p + 1);
+    k_cc_apply<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->n_comp.p, c->winner.p, c->scalars.p + 2);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats_valid = false;
+    return (int)c->h_scalars[1];
+}
+
+static void fill_holes(acvd_ctx* c) {
+    const int V = c->V, K = c->K;
+    c->null_list.alloc(V);
+    ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    k_collect_null<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->null_list.p, c->scalars.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    const int n = (int)c->h_scalars[0];
+    if (n == 0) return;
+    c->pick.alloc(n);
+    // the list order depends on atomics; sort it so the (deterministic) result does not depend on it
+    {
+        c->sort_k0.alloc(V);
+        size_t tb = 0;
+        ACVD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, c->null_list.p, c->sort_k0.p, n, 0, 32, c->stream));
+        void* t = cub_temp(c, tb);
+        ACVD_CUDA(cub::DeviceRadixSort::SortKeys(t, tb, c->null_list.p, c->sort_k0.p, n, 0, 32, c->stream));
+        ACVD_CUDA(cudaMemcpyAsync(c->null_list.p, c->sort_k0.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    int64_t remaining = n;
+    while (remaining > 0) {
+        ACVD_CUDA(cudaMemsetAsync(c->scalars.p + 3, 0, sizeof(unsigned long long), c->stream));
+        k_fill_pick<<<grid_for(n), kThreads, 0, c->stream>>>(n, K, c->null_list.p, c->row_ptr.p, c->col.p, c->cid.p, c->pick.p);
+        k_fill_apply<<<grid_for(n), kThreads, 0, c->stream>>>(n, c->null_list.p, c->pick.p, c->cid.p, c->scalars.p + 3);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 3, c->scalars.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        int64_t filled = (int64_t)c->h_scalars[3];
+        if (filled == 0) break;   // unreachable holes stay NULL, as in the reference (:619-631)
+        remaining -= filled;
+    }
+    c->stats_valid = false;
+}
+
+extern "C" int acvd_clean_clustering(acvd_ctx* c, int32_t* disconnected) {
+    ACVD_API_BEGIN(c)
+    if (!c->K) throw std::runtime_error("acvd_clean_clustering: no clustering");
+    int d = clean_clustering(c);
+    if (disconnected) *disconnected = d;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_fill_holes(acvd_ctx* c) {
+    ACVD_API_BEGIN(c)
+    if (!c->K) throw std::runtime_error("acvd_fill_holes: no clustering");
+    fill_holes(c);
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// reassignment rounds
+struct RoundResult { unsigned long long proposals, mods, tests, evaluated, boundary; float ms_propose, ms_commit; };
+
+static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all) {
+    ReassignArgs A;
+    A.V = c->V; A.K = c->K;
+    A.row_ptr = c->row_ptr.p; A.col = c->col.p; A.cid = c->cid.p;
+    A.items = c->items.p; A.csum = c->csum.p; A.cenergy = c->cenergy.p; A.csize = c->csize.p;
+    A.mod_round = c->mod_round.p;
+    A.frozen = c->has_frozen ? c->frozen.p : nullptr;
+    A.anchor = c->has_anchor ? c->anchor.p : nullptr;
+    A.xyz = c->xyz.p;
+    A.best = c->best.p; A.prop_dst = c->prop_dst.p; A.prop_key = c->prop_key.p; A.prop_e = c->prop_e.p;
+    A.plist = c->plist.p; A.ctr = c->ctr.p;
+    A.round = c->round; A.force_all = force_all; A.connexity = connexity; A.cfg = cfg;
+    return A;
+}
+
+static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso) {
+    ReassignArgs A = make_args(c, cfg, connexity, force_all);
+    ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
+    const int gp = grid_for(c->V), gc = kNumSMs * 4;
+    ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    switch (c->metric) {
+        case M_ISO: k_propose<M_ISO, 4><<<gp, kThreads, 0, c->stream>>>(A); break;
+        case M_QEM:
+            if (as_iso) k_propose<M_ISO, 14><<<gp, kThreads, 0, c->stream>>>(A);
+            else k_propose<M_QEM, 14><<<gp, kThreads, 0, c->stream>>>(A);
+            break;
+        case M_ANISO: k_propose<M_ANISO, 14><<<gp, kThreads, 0, c->stream>>>(A); break;
+        default: k_propose<M_ANISOQ, 22><<<gp, kThreads, 0, c->stream>>>(A); break;
+    }
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    switch (c->metric) {
+        case M_ISO: k_commit<M_ISO, M_ISO><<<gc, kThreads, 0, c->stream>>>(A); break;
+        case M_QEM:
+            if (as_iso) k_commit<M_ISO, M_QEM><<<gc, kThreads, 0, c->stream>>>(A);
+            else k_commit<M_QEM, M_QEM><<<gc, kThreads, 0, c->stream>>>(A);
+            break;
+        case M_ANISO: k_commit<M_ANISO, M_ANISO><<<gc, kThreads, 0, c->stream>>>(A); break;
+        default: k_commit<M_ANISOQ, M_ANISOQ><<<gc, kThreads, 0, c->stream>>>(A); break;
+    }
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
+    c->round++;
+}
+
+static RoundResult finish_round(acvd_ctx* c) {
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    RoundResult r;
+    r.proposals = c->h_ctr->proposals; r.mods = c->h_ctr->mods; r.tests = c->h_ctr->tests;
+    r.evaluated = c->h_ctr->evaluated; r.boundary = c->h_ctr->boundary;
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_propose, c->ev[0], c->ev[1]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
+    return r;
+}
+
+static double global_energy(acvd_ctx* c) {
+    // ComputeGlobalEnergy sums in long double on the host (:1319-1346); K doubles is a small copy
+    std::vector<double> e(c->K);
+    ACVD_CUDA(cudaMemcpyAsync(e.data(), c->cenergy.p, (size_t)c->K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    long double s = 0;
+    for (double x : e) s += (long double)x;
+    return (double)s;
+}
+
+// algorithmic bytes of one propose launch (DESIGN.md "bytes model"): frontier scan of every vertex
+// (row_ptr 4 + cid 4 + deg * (col 4 + neighbour cid 4)) + per evaluated vertex the item row, the source
+// cluster row and its (size, energy) + per test the destination row and its energy + proposal write-back
+static int64_t propose_bytes(const acvd_ctx* c, const RoundResult& r, bool as_iso) {
+    const int64_t nl = 8 * (int64_t)(as_iso ? 4 : payload_npad(c->metric));
+    return 8 * (int64_t)c->V + 8 * c->nnz + (int64_t)r.evaluated * (2 * nl + 16) + (int64_t)r.tests * (nl + 8) +
+           (int64_t)r.proposals * 28;
+}
+
+extern "C" int acvd_reassign_round(acvd_ctx* c, int constrained, int qlevel, int connexity, int64_t* proposals,
+                                   int64_t* mods, int64_t* tests) {
+    ACVD_API_BEGIN(c)
+    if (!c->K) throw std::runtime_error("acvd_reassign_round: no clustering");
+    bool as_iso = qem_as_iso(c, constrained, qlevel);
+    if (!c->stats_valid || c->stats_constrained != constrained || c->stats_qlevel != qlevel)
+        recompute_statistics(c, constrained, qlevel, 0);
+    EvalCfg cfg = make_cfg(constrained, qlevel, 0);
+    launch_round(c, cfg, connexity, 1, as_iso);
+    RoundResult r = finish_round(c);
+    if (proposals) *proposals = (int64_t)r.proposals;
+    if (mods) *mods = (int64_t)r.mods;
+    if (tests) *tests = (int64_t)r.tests;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* rep) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !c->have_items) throw std::runtime_error("acvd_minimize: need mesh, items and clustering");
+    acvd_params p;
+    memset(&p, 0, sizeof p);
+    if (pin) p = *pin;
+    if (p.max_loops <= 0) p.max_loops = 5000000;
+    if (p.max_convergences <= 0) p.max_convergences = 1000000000;
+    if (p.early_stop_div <= 0) p.early_stop_div = 1000;
+    if (p.quadrics_level < 0) p.quadrics_level = 0;
+    if (pin == nullptr) p.quadrics_level = 3;
+    const double thr = p.sv_threshold > 0 ? p.sv_threshold : 1e-3;
+    auto t0 = std::chrono::steady_clock::now();
+    acvd_report R;
+    memset(&R, 0, sizeof R);
+    c->energy_log.clear();
+
+    // SetConstrainedClustering(0) when UnconstrainedInitialization (:683-688); only QEM honours it
+    int constrained = (c->metric == M_QEM && p.unconstrained_init) ? 0 : 1;
+    int connexity = p.connexity;
+    const int qlevel = p.quadrics_level;
+    cudaEvent_t ec0, ec1;
+    ACVD_CUDA(cudaEventCreate(&ec0));
+    ACVD_CUDA(cudaEventCreate(&ec1));
+    auto timed_clean = [&](auto&& fn) {
+        ACVD_CUDA(cudaEventRecord(ec0, c->stream));
+        fn();
+        ACVD_CUDA(cudaEventRecord(ec1, c->stream));
+        ACVD_CUDA(cudaEventSynchronize(ec1));
+        float ms = 0;
+        ACVD_CUDA(cudaEventElapsedTime(&ms, ec0, ec1));
+        R.ms_clean += ms;
+    };
+    // prime: FillHoles, ReComputeStatistics, SetAllClustersToModified (:727-730)
+    timed_clean([&] { fill_holes(c); recompute_statistics(c, constrained, qlevel, thr); });
+    int force_all = 1;
+    int nconv = 0;
+    // earlyStopItems = items of non-frozen clusters (:733-736)
+    int64_t early_items = c->V;
+    if (c->has_frozen) {
+        std::vector<int> sz(c->K);
+        std::vector<unsigned char> fr(c->K);
+        ACVD_CUDA(cudaMemcpy(sz.data(), c->csize.p, (size_t)c->K * sizeof(int), cudaMemcpyDeviceToHost));
+        ACVD_CUDA(cudaMemcpy(fr.data(), c->frozen.p, (size_t)c->K, cudaMemcpyDeviceToHost));
+        early_items = 0;
+        for (int i = 0; i < c->K; i++) if (!fr[i]) early_items += sz[i];
+    }
+    int64_t loops = 0;
+    while (true) {
+        EvalCfg cfg = make_cfg(constrained, qlevel, thr);
+        const bool as_iso = qem_as_iso(c, constrained, qlevel);
+        launch_round(c, cfg, connexity, force_all, as_iso);
+        force_all = 0;
+        RoundResult r = finish_round(c);
+        loops++;
+        R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;
+        R.ms_propose += r.ms_propose; R.ms_commit += r.ms_commit;
+        R.propose_launches++; R.propose_bytes += propose_bytes(c, r, as_iso);
+        if (p.log_energy) c->energy_log.push_back(global_energy(c));
+        const int64_t mods = (int64_t)r.mods;
+        // convergence event (:773-776); a round commits a conflict-free subset, so the analogue of the
+        // reference's "modifications in one sweep" is the number of live improving proposals
+        const bool event = (mods == 0) || (loops > p.max_loops) ||
+                           ((int64_t)r.proposals <= early_items / p.early_stop_div && nconv <= 1);
+        if (!event) continue;
+        if (c->metric == M_QEM && p.unconstrained_init && nconv == 0) constrained = 1;   // (:778-781)
+        if (nconv >= 1) connexity = 1;                                                  // (:790)
+        nconv++;
+        R.convergences++;
+        int disc = 0;
+        timed_clean([&] { disc = clean_clustering(c); fill_holes(c); });
+        R.disconnected = disc;
+        const bool done = (disc == 0 && mods == 0) || loops >= p.max_loops || nconv >= p.max_convergences;
+        // the reference leaves the incremental sums in place on exit; we always export fresh statistics
+        timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
+        if (done) break;
+        force_all = 1;
+    }
+    R.energy = global_energy(c);
+    cudaEventDestroy(ec0);
+    cudaEventDestroy(ec1);
+    R.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rep) *rep = R;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_cluster_stats(acvd_ctx* c, double* sums, double* centroid, double* energy, int32_t* sizes) {
+    ACVD_API_BEGIN(c)
+    if (!c->K) throw std::runtime_error("acvd_get_cluster_stats: no clustering");
+    if (!c->stats_valid) recompute_statistics(c, c->stats_constrained, c->stats_qlevel, 0);
+    const int K = c->K, np = payload_np(c->metric), npad = payload_npad(c->metric);
+    if (sums) {
+        DevBuf<double> tmp;
+        tmp.alloc((size_t)K * np);
+        k_pack_rows<<<grid_for((int64_t)K * npad), kThreads, 0, c->stream>>>(K, np, npad, c->csum.p, tmp.p, 0);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaMemcpyAsync(sums, tmp.p, (size_t)K * np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (centroid) ACVD_CUDA(cudaMemcpyAsync(centroid, c->ccentroid.p, 3 * (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (energy) ACVD_CUDA(cudaMemcpyAsync(energy, c->cenergy.p, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (sizes) ACVD_CUDA(cudaMemcpyAsync(sizes, c->csize.p, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_global_energy(acvd_ctx* c, double* energy) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !energy) throw std::runtime_error("acvd_global_energy: no clustering");
+    if (!c->stats_valid) recompute_statistics(c, c->stats_constrained, c->stats_qlevel, 0);
+    *energy = global_energy(c);
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_energy_log(acvd_ctx* c, double* out, int32_t cap, int32_t* n) {
+    if (!c) return fail(nullptr, ACVD_EINVAL, "null context");
+    if (n) *n = (int32_t)c->energy_log.size();
+    if (out) for (int i = 0; i < cap && i < (int)c->energy_log.size(); i++) out[i] = c->energy_log[i];
+    return ACVD_OK;
+}
+
+extern "C" int acvd_representative_points(acvd_ctx* c, int32_t n, const double* Q9, double* P3, int32_t max_sv,
+                                          double thr, int32_t* rank_def) {
+    ACVD_API_BEGIN(c)
+    if (n < 0 || (n && (!Q9 || !P3))) throw std::runtime_error("acvd_representative_points: bad arguments");
+    if (n == 0) return ACVD_OK;
+    DevBuf<double> q, p;
+    DevBuf<int> rd;
+    q.alloc(9 * (size_t)n); p.alloc(3 * (size_t)n); rd.alloc(n);
+    ACVD_CUDA(cudaMemcpyAsync(q.p, Q9, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(p.p, P3, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_representative_points<<<grid_for(n), kThreads, 0, c->stream>>>(n, q.p, p.p, max_sv, thr > 0 ? thr : 1e-3, rd.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(P3, p.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (rank_def) ACVD_CUDA(cudaMemcpyAsync(rank_def, rd.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// integer stages
+extern "C" int acvd_boundary_flags(acvd_ctx* c, uint8_t* flags) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !flags) throw std::runtime_error("acvd_boundary_flags: no clustering");
+    DevBuf<unsigned char> d;
+    d.alloc(c->V);
+    k_boundary_flags<<<grid_for(c->V), kThreads, 0, c->stream>>>(c->V, c->row_ptr.p, c->col.p, c->cid.p, d.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(flags, d.p, (size_t)c->V, cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_cluster_adjacency(acvd_ctx* c, int64_t* out, int64_t cap, int64_t* n_out) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !n_out) throw std::runtime_error("acvd_cluster_adjacency: bad arguments");
+    const int64_t n = c->nnz;
+    DevBuf<unsigned long long> keys, alt, uniq;
+    DevBuf<int64_t> d_num;
+    keys.alloc(n); alt.alloc(n); uniq.alloc(n); d_num.alloc(1);
+    k_adjacency_keys<<<grid_for(c->V), kThreads, 0, c->stream>>>(c->V, c->K, c->row_ptr.p, c->col.p, c->cid.p, keys.p);
+    ACVD_LAUNCH_CHECK();
+    sort_keys64(c, keys.p, alt.p, n, 64);
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceSelect::Unique(nullptr, tb, keys.p, uniq.p, d_num.p, n, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceSelect::Unique(t, tb, keys.p, uniq.p, d_num.p, n, c->stream));
+    int64_t nu = 0;
+    ACVD_CUDA(cudaMemcpyAsync(&nu, d_num.p, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    if (nu > 0) {
+        unsigned long long last = 0;
+        ACVD_CUDA(cudaMemcpy(&last, uniq.p + (nu - 1), sizeof last, cudaMemcpyDeviceToHost));
+        if (last == ~0ull) nu--;
+    }
+    *n_out = nu;
+    if (out && nu > 0) ACVD_CUDA(cudaMemcpy(out, uniq.p, (size_t)std::min(nu, cap) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_dual_triangles(acvd_ctx* c, int32_t* out, int64_t cap, int64_t* n_out) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !n_out) throw std::runtime_error("acvd_dual_triangles: bad arguments");
+    if (c->K >= (1 << 21)) throw std::runtime_error("acvd_dual_triangles: K must be below 2^21");
+    const int F = c->F;
+    DevBuf<unsigned long long> k0, k1;
+    DevBuf<int> f0, f1, first, first_sorted;
+    k0.alloc(F); k1.alloc(F); f0.alloc(F); f1.alloc(F); first.alloc(F); first_sorted.alloc(F);
+    k_dual_keys<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->K, c->tri.p, c->cid.p, k0.p, f0.p);
+    ACVD_LAUNCH_CHECK();
+    size_t tb = 0;   // stable: equal keys keep ascending face order
+    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, f0.p, f1.p, F, 0, 64, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, k0.p, k1.p, f0.p, f1.p, F, 0, 64, c->stream));
+    k_dual_first<<<grid_for(F), kThreads, 0, c->stream>>>(F, k1.p, f1.p, first.p);
+    ACVD_LAUNCH_CHECK();
+    // ascending first-face ids = first-occurrence order over the input faces; sentinels sort to the end
+    ACVD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, first.p, first_sorted.p, F, 0, 32, c->stream));
+    t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceRadixSort::SortKeys(t, tb, first.p, first_sorted.p, F, 0, 32, c->stream));
+    // count = first index holding the sentinel
+    std::vector<int> h;   // binary search on the device-sorted array through small copies
+    int lo = 0, hi = F;
+    while (lo < hi) {
+        int mid = (lo + hi) / 2, val = 0;
+        ACVD_CUDA(cudaMemcpyAsync(&val, first_sorted.p + mid, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        if (val == 0x7fffffff) hi = mid; else lo = mid + 1;
+    }
+    const int n = lo;
+    *n_out = n;
+    if (out && n > 0) {
+        int m = (int)std::min<int64_t>(n, cap);
+        DevBuf<int> d_out;
+        d_out.alloc(3 * (size_t)m);
+        k_dual_emit<<<grid_for(m), kThreads, 0, c->stream>>>(m, first_sorted.p, c->tri.p, c->cid.p, d_out.p);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaMemcpyAsync(out, d_out.p, 3 * (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU plumbing lives in acvd_dist.cu

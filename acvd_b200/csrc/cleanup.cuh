@@ -1,0 +1,224 @@
+// Per-cluster statistic accumulation, cluster cleaning (connected components), hole filling, and the
+// integer stages that follow the hot path.
+//
+//   ReComputeStatistics / ReComputeClustersSize  reference Common/vtkUniformClustering.h:353-403
+//   CleanClustering                              :406-549
+//   FillHolesInClustering                        :552-633
+//   boundary detection / cluster adjacency / dual triangles  DiscreteRemeshing/vtkDiscreteRemeshing.h:1003-1133
+#pragma once
+#include "metric.cuh"
+
+namespace acvd {
+
+__global__ void k_iota(int n, int* out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
+}
+
+// seg[c] = first index i with sorted_keys[i] >= c, for c in [0, K+1]; seg[K+1] = V
+__global__ void k_segments(int V, int K, const int* __restrict__ sorted_keys, int* seg) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= K + 1; c += gridDim.x * blockDim.x) {
+        int lo = 0, hi = V;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted_keys[mid] < c) lo = mid + 1; else hi = mid; }
+        seg[c] = (c == K + 1) ? V : lo;
+    }
+}
+
+// One warp per cluster: lanes stride over the cluster's items (sorted by vertex id, so the summation
+// order is fixed), each payload component is reduced with warp shuffles; lane 0 stores sums, size,
+// representative point and energy.  Deterministic.  M: metric of the stored rows; EM: metric whose
+// energy formula is evaluated (QEM's unconstrained phase uses the isotropic one).
+template <int M, int EM>
+__global__ void __launch_bounds__(kThreads) k_cluster_stats(int K, const int* __restrict__ seg, const int* __restrict__ sorted_v,
+                                                            const double* __restrict__ items, double* csum, double* cenergy,
+                                                            double* ccentroid, int* csize, const int* __restrict__ anchor,
+                                                            const float* __restrict__ xyz, EvalCfg cfg) {
+    constexpr int NPAD = MetricTraits<M>::NPAD;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int c = blockIdx.x * warps_per_block + (threadIdx.x >> 5); c < K; c += gridDim.x * warps_per_block) {
+        const int b = seg[c], e = seg[c + 1];
+        double acc[NPAD];
+#pragma unroll
+        for (int k = 0; k < NPAD; k++) acc[k] = 0.0;
+        for (int i = b + lane; i < e; i += 32) {
+            double it[NPAD];
+            load_row_ro<NPAD>(items + (int64_t)sorted_v[i] * NPAD, it);
+#pragma unroll
+            for (int k = 0; k < NPAD; k++) acc[k] += it[k];
+        }
+#pragma unroll
+        for (int k = 0; k < NPAD; k++) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+            store_row<NPAD>(csum + (int64_t)c * NPAD, acc);
+            csize[c] = e - b;
+            double cen[3], apt[3];
+            const double* ap = nullptr;
+            if (EM == M_QEM && anchor && anchor[c] >= 0) {
+                int av = anchor[c];
+                apt[0] = xyz[3 * av]; apt[1] = xyz[3 * av + 1]; apt[2] = xyz[3 * av + 2];
+                ap = apt;
+            }
+            cenergy[c] = cluster_energy<EM>(acc, cfg, cen, ap);
+            ccentroid[3 * c] = cen[0]; ccentroid[3 * c + 1] = cen[1]; ccentroid[3 * c + 2] = cen[2];
+        }
+    }
+}
+
+// ---------------- connected components of every cluster (label = min vertex id of the component) ----------------
+__global__ void k_cc_propagate(int V, int K, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                               const int* __restrict__ cid, int* label, int* changed) {
+    bool any = false;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const int c = cid[v];
+        if (c >= K) continue;
+        int m = label[v];
+        const int m0 = m;
+        for (int e = row_ptr[v]; e < row_ptr[v + 1]; e++) {
+            int u = col[e];
+            if (cid[u] == c) { int lu = label[u]; if (lu < m) m = lu; }
+        }
+        // pointer jumping: labels only ever name vertices of the same component
+        int j = label[m];
+        while (j < m) { m = j; j = label[m]; }
+        if (m < m0) { atomicMin(&label[v], m); any = true; }
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) *changed = 1;
+}
+
+__global__ void k_cc_sizes(int V, int K, const int* __restrict__ cid, const int* __restrict__ label, int* comp_size,
+                           const int* __restrict__ anchor) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        int c = cid[v];
+        if (c >= K) continue;
+        // an anchored item weighs 1e9 so that its component always wins (:440-447)
+        int w = (anchor && anchor[c] == v) ? 1000000000 : 1;
+        atomicAdd(&comp_size[label[v]], w);
+    }
+}
+
+// Per cluster: number of recorded components and the winner (largest; first-discovered wins ties, :503).
+// Reference quirk kept: the component discovered at item 0 is never recorded because 0 doubles as the
+// "unvisited" sentinel of VisitedCluster (:463-467), so it is neither counted nor ever reset.
+__global__ void k_cc_winner(int V, int K, const int* __restrict__ cid, const int* __restrict__ label,
+                            const int* __restrict__ comp_size, int* n_comp, unsigned long long* winner) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        int c = cid[v];
+        if (c >= K || label[v] != v || v == 0) continue;
+        atomicAdd(&n_comp[c], 1);
+        unsigned long long key = ((unsigned long long)(unsigned)comp_size[v] << 32) | (unsigned)(0xffffffffu - (unsigned)v);
+        atomicMax(&winner[c], key);
+    }
+}
+
+__global__ void k_cc_apply(int V, int K, int* cid, const int* __restrict__ label, const int* __restrict__ n_comp,
+                           const unsigned long long* __restrict__ winner, unsigned long long* n_reset) {
+    unsigned cnt = 0;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        int c = cid[v];
+        if (c >= K) continue;
+        int root = label[v];
+        if (root == 0 || n_comp[c] < 2) continue;
+        unsigned win_root = 0xffffffffu - (unsigned)(winner[c] & 0xffffffffull);
+        if ((unsigned)root != win_root) { cid[v] = K; cnt++; }
+    }
+    warp_count_add(n_reset, cnt);
+}
+
+__global__ void k_count_ge2(int K, const int* __restrict__ n_comp, unsigned long long* out) {
+    unsigned cnt = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x) cnt += n_comp[c] >= 2;
+    warp_count_add(out, cnt);
+}
+
+// ---------------- hole filling: level-synchronous adoption by NULL vertices ----------------
+__global__ void k_collect_null(int V, int K, const int* __restrict__ cid, int* list, unsigned long long* n) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x)
+        if (cid[v] >= K || cid[v] < 0) { int s = (int)atomicAdd(n, 1ull); list[s] = v; }
+}
+// pick[i] = cluster of the first assigned neighbour (ascending vertex id) of NULL vertex list[i], or -1
+__global__ void k_fill_pick(int n, int K, const int* __restrict__ list, const int* __restrict__ row_ptr,
+                            const int* __restrict__ col, const int* __restrict__ cid, int* pick) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int v = list[i];
+        int p = -1;
+        if (cid[v] >= K || cid[v] < 0)
+            for (int e = row_ptr[v]; e < row_ptr[v + 1] && p < 0; e++) { int b = cid[col[e]]; if (b >= 0 && b < K) p = b; }
+        pick[i] = p;
+    }
+}
+__global__ void k_fill_apply(int n, const int* __restrict__ list, const int* __restrict__ pick, int* cid, unsigned long long* n_filled) {
+    unsigned cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (pick[i] >= 0) { cid[list[i]] = pick[i]; cnt++; }
+    warp_count_add(n_filled, cnt);
+}
+
+// ---------------- integer stages ----------------
+__global__ void k_boundary_flags(int V, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                 const int* __restrict__ cid, unsigned char* flags) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        int a = cid[v];
+        unsigned char b = 0;
+        for (int e = row_ptr[v]; e < row_ptr[v + 1]; e++) if (cid[col[e]] != a) { b = 1; break; }
+        flags[v] = b;
+    }
+}
+// one key per directed CSR entry u<v with different, valid clusters: (lo << 32 | hi), else ~0
+__global__ void k_adjacency_keys(int V, int K, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                 const int* __restrict__ cid, unsigned long long* keys) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        int a = cid[v];
+        for (int e = row_ptr[v]; e < row_ptr[v + 1]; e++) {
+            int u = col[e];
+            int b = cid[u];
+            unsigned long long k = ~0ull;
+            if (u > v && a != b && a >= 0 && a < K && b >= 0 && b < K) {
+                unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
+                k = ((unsigned long long)lo << 32) | hi;
+            }
+            keys[e] = k;
+        }
+    }
+}
+// per face: sorted cluster triple packed 3 x 21 bits when the three clusters are distinct and valid, else ~0
+__global__ void k_dual_keys(int F, int K, const int* __restrict__ tri, const int* __restrict__ cid,
+                            unsigned long long* keys, int* face_id) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        int a = cid[tri[3 * f]], b = cid[tri[3 * f + 1]], c = cid[tri[3 * f + 2]];
+        unsigned long long k = ~0ull;
+        if (a >= 0 && b >= 0 && c >= 0 && a < K && b < K && c < K && a != b && a != c && b != c) {
+            int lo = min(a, min(b, c)), hi = max(a, max(b, c)), mid = a + b + c - lo - hi;
+            k = ((unsigned long long)lo << 42) | ((unsigned long long)mid << 21) | (unsigned long long)hi;
+        }
+        keys[f] = k;
+        face_id[f] = f;
+    }
+}
+// after a stable sort by key: flag[i] = 1 for the first face of every distinct valid key
+__global__ void k_dual_first(int F, const unsigned long long* __restrict__ keys, const int* __restrict__ face_id, int* first_face) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) {
+        bool first = keys[i] != ~0ull && (i == 0 || keys[i - 1] != keys[i]);
+        first_face[i] = first ? face_id[i] : 0x7fffffff;
+    }
+}
+__global__ void k_dual_emit(int n, const int* __restrict__ faces, const int* __restrict__ tri, const int* __restrict__ cid, int* out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int f = faces[i];
+        out[3 * i] = cid[tri[3 * f]]; out[3 * i + 1] = cid[tri[3 * f + 1]]; out[3 * i + 2] = cid[tri[3 * f + 2]];
+    }
+}
+
+// batched vtkQuadricTools::ComputeRepresentativePoint
+__global__ void k_representative_points(int n, const double* __restrict__ Q9, double* P3, int max_sv, double thr, int* rank_def) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double q[9], p[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) q[k] = Q9[9 * (int64_t)i + k];
+        p[0] = P3[3 * (int64_t)i]; p[1] = P3[3 * (int64_t)i + 1]; p[2] = P3[3 * (int64_t)i + 2];
+        int rd = representative_point(q, p, max_sv, thr);
+        P3[3 * (int64_t)i] = p[0]; P3[3 * (int64_t)i + 1] = p[1]; P3[3 * (int64_t)i + 2] = p[2];
+        if (rank_def) rank_def[i] = rd;
+    }
+}
+
+}  // namespace acvd

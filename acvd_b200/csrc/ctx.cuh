@@ -1,0 +1,81 @@
+// Context object behind the opaque acvd_ctx handle of include/acvd_b200.h, shared by the translation units.
+#pragma once
+#include <nccl.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/acvd_b200.h"
+#include "common.cuh"
+#include "reassign.cuh"
+
+using namespace acvd;
+
+struct acvd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // mesh
+    int V = 0, F = 0;
+    int64_t nnz = 0;   // 2E
+    DevBuf<float> xyz;
+    DevBuf<int> tri, row_ptr, col, vf_ptr;
+    DevBuf<unsigned long long> vf_keys;
+    std::vector<int> h_tri;          // host copy for the sequential initial sampling
+    // items
+    int metric = -1;
+    DevBuf<double> area, weight, items;
+    bool have_items = false;
+    // clusters
+    int K = 0;
+    DevBuf<int> cid, csize, mod_round, anchor;
+    DevBuf<unsigned char> frozen;
+    bool has_frozen = false, has_anchor = false;
+    std::vector<int64_t> fixed;
+    DevBuf<double> csum, cenergy, ccentroid;
+    bool stats_valid = false;
+    // reassignment scratch
+    DevBuf<unsigned long long> best, prop_key;
+    DevBuf<int> prop_dst, plist;
+    DevBuf<double2> prop_e;
+    DevBuf<RoundCounters> ctr;
+    RoundCounters* h_ctr = nullptr;   // pinned
+    int round = 1;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // generic scratch
+    DevBuf<char> cub_temp;
+    DevBuf<int> sort_k0, sort_k1, sort_v0, sort_v1, seg, label, comp_size, n_comp, null_list, pick;
+    DevBuf<unsigned long long> winner, scalars;   // scalars: small device counters
+    unsigned long long* h_scalars = nullptr;      // pinned, 8 entries
+    std::vector<double> energy_log;
+    int stats_constrained = 1, stats_qlevel = 3;
+    // multi-GPU (acvd_dist.cu)
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+inline std::string g_create_error;
+
+inline int fail(acvd_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define ACVD_API_BEGIN(ctx)                                                          \
+    if (!(ctx)) return fail(nullptr, ACVD_EINVAL, "null context");                   \
+    try {                                                                            \
+        ACVD_CUDA(cudaSetDevice((ctx)->device));
+#define ACVD_API_END(ctx)                                                            \
+    }                                                                                \
+    catch (const CudaError& e) {                                                     \
+        char buf[512];                                                               \
+        snprintf(buf, sizeof buf, "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e.code), \
+                 cudaGetErrorString(e.code), e.file, e.line, e.what);                \
+        cudaGetLastError();                                                          \
+        return fail((ctx), e.code == cudaErrorMemoryAllocation ? ACVD_ENOMEM : ACVD_ECUDA, buf); \
+    }                                                                                \
+    catch (const std::exception& e) { return fail((ctx), ACVD_EINVAL, e.what()); }   \
+    catch (...) { return fail((ctx), ACVD_EINVAL, "unknown error"); }                \
+    return ACVD_OK;
+

@@ -1,0 +1,173 @@
+// Device-side mesh preparation: CSR vertex adjacency from the triangle list, vertex->face incidence,
+// and the per-vertex item payloads of the four metrics.
+//
+// Replaces, for this path, the edge table / vertex rings of vtkSurfaceBase
+// (reference Common/vtkSurfaceBase.cxx:1166-1221, 1407-1468; accessors used by the engine:
+// DiscreteRemeshing/vtkVerticesProcessing.h:137-157) with int32 CSR, and Metric::BuildMetric
+// (vtkIsotropicMetricForClustering.h:214-291, vtkQEMetricForClustering.h:151-167, 297-362,
+// vtkQuadricAnisotropicMetricForClustering.h:366-487, vtkAnisotropicMetricForClustering.h:300-430).
+#pragma once
+#include "metric.cuh"
+
+namespace acvd {
+
+// 6 directed half-edges per face as (src << 32 | dst); faces whose first two vertices coincide are
+// inactive (vtkSurfaceBase.cxx:1443) and self loops are rejected (:1168-1172): those emit ~0.
+__global__ void k_emit_halfedges(int F, const int* __restrict__ tri, unsigned long long* keys) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        int v[3] = {tri[3 * f], tri[3 * f + 1], tri[3 * f + 2]};
+        bool active = v[0] != v[1];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            unsigned a = (unsigned)v[k], b = (unsigned)v[(k + 1) % 3];
+            bool ok = active && a != b;
+            keys[6 * (int64_t)f + 2 * k] = ok ? (((unsigned long long)a << 32) | b) : ~0ull;
+            keys[6 * (int64_t)f + 2 * k + 1] = ok ? (((unsigned long long)b << 32) | a) : ~0ull;
+        }
+    }
+}
+
+// (vertex << 32 | face) incidence keys, 3 per face
+__global__ void k_emit_incidence(int F, const int* __restrict__ tri, unsigned long long* keys) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        bool active = tri[3 * f] != tri[3 * f + 1];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            keys[3 * (int64_t)f + k] = active ? (((unsigned long long)(unsigned)tri[3 * f + k] << 32) | (unsigned)f) : ~0ull;
+    }
+}
+
+// From sorted keys (src << 32 | x): ptr[s] = first index with src >= s; low[i] = x.  ptr has V+1 entries.
+__global__ void k_rows_from_sorted(int64_t n, int V, const unsigned long long* __restrict__ keys, int* ptr, int* low) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+        // sources >= V (the ~0 keys of inactive faces, sorted last) are clamped so they close the last row
+        int64_t prev = (i == 0) ? -1 : min((int64_t)(keys[i - 1] >> 32), (int64_t)V);
+        int64_t cur = (i == n) ? (int64_t)V : min((int64_t)(keys[i] >> 32), (int64_t)V);
+        for (int64_t s = prev + 1; s <= cur; s++) ptr[s] = (int)i;
+        if (i < n && low) low[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
+    }
+}
+
+struct Tri3 { double a[3], b[3], c[3]; };
+
+__device__ __forceinline__ void load_face(const float* __restrict__ xyz, const int* __restrict__ tri, int f, Tri3& t) {
+    int i0 = tri[3 * f], i1 = tri[3 * f + 1], i2 = tri[3 * f + 2];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { t.a[k] = xyz[3 * (int64_t)i0 + k]; t.b[k] = xyz[3 * (int64_t)i1 + k]; t.c[k] = xyz[3 * (int64_t)i2 + k]; }
+}
+
+// [VTK, from memory] vtkTriangle::TriangleArea: 0.5 |(p3 - p2) x (p1 - p2)|
+__device__ __forceinline__ double tri_area(const Tri3& t) {
+    double ax = t.c[0] - t.b[0], ay = t.c[1] - t.b[1], az = t.c[2] - t.b[2];
+    double bx = t.a[0] - t.b[0], by = t.a[1] - t.b[1], bz = t.a[2] - t.b[2];
+    double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    return 0.5 * sqrt(nx * nx + ny * ny + nz * nz);
+}
+
+// [VTK, from memory] vtkTriangle::ComputeQuadric: n = x1 x x2 + x2 x x3 + x3 x x1, d = -det[x1;x2;x3];
+// coefficient order of vtkQuadricTools::AddTriangleQuadric (Common/vtkQuadricTools.cxx:68-78).
+__device__ __forceinline__ void tri_quadric_add(const Tri3& t, double* Q9) {
+    const double *x1 = t.a, *x2 = t.b, *x3 = t.c;
+    double n0 = (x1[1] * x2[2] - x1[2] * x2[1]) + (x2[1] * x3[2] - x2[2] * x3[1]) + (x3[1] * x1[2] - x3[2] * x1[1]);
+    double n1 = (x1[2] * x2[0] - x1[0] * x2[2]) + (x2[2] * x3[0] - x2[0] * x3[2]) + (x3[2] * x1[0] - x3[0] * x1[2]);
+    double n2 = (x1[0] * x2[1] - x1[1] * x2[0]) + (x2[0] * x3[1] - x2[1] * x3[0]) + (x3[0] * x1[1] - x3[1] * x1[0]);
+    double det = x1[0] * x2[1] * x3[2] + x2[0] * x3[1] * x1[2] + x3[0] * x1[1] * x2[2]
+               - x1[0] * x3[1] * x2[2] - x2[0] * x1[1] * x3[2] - x3[0] * x2[1] * x1[2];
+    double d = -det;
+    Q9[0] += n0 * n0; Q9[1] += n0 * n1; Q9[2] += n0 * n2; Q9[3] += n0 * d;
+    Q9[4] += n1 * n1; Q9[5] += n1 * n2; Q9[6] += n1 * d;
+    Q9[7] += n2 * n2; Q9[8] += n2 * d;
+}
+
+// vertex area = sum incident face areas / 3 (Common/vtkSurface.cxx:1342-1359), faces in ascending id
+__global__ void k_vertex_area(int V, const int* __restrict__ vf_ptr, const unsigned long long* __restrict__ vf_keys,
+                              const float* __restrict__ xyz, const int* __restrict__ tri, double* area) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        double A = 0;
+        for (int i = vf_ptr[v]; i < vf_ptr[v + 1]; i++) {
+            Tri3 t; load_face(xyz, tri, (int)(vf_keys[i] & 0xffffffffull), t);
+            A += tri_area(t) / 3.0;
+        }
+        area[v] = A;
+    }
+}
+
+// weight = area [* indicator^gradation]; float-rounded for the anisotropic metrics (their Item::Weight is float)
+__global__ void k_raw_weight(int V, const double* __restrict__ area, const double* __restrict__ custom, double gradation,
+                             int use_custom, int as_float, double* weight) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        double w = area[v];
+        if (use_custom) w = w * pow(custom[v], gradation);
+        weight[v] = as_float ? (double)(float)w : w;
+    }
+}
+
+// clamp to [avg/ratio, avg*ratio] (ClampWeights) and compose the payload row
+template <int M>
+__global__ void k_compose_items(int V, const double* __restrict__ sum_w, double ratio, double* weight,
+                                const double* __restrict__ area, const float* __restrict__ xyz, const int* __restrict__ tri,
+                                const int* __restrict__ vf_ptr, const unsigned long long* __restrict__ vf_keys,
+                                const float* __restrict__ pd, double* items) {
+    constexpr int NPAD = MetricTraits<M>::NPAD;
+    const double avg = *sum_w / (double)V;
+    const double mn = avg / ratio, mx = avg * ratio;
+    constexpr bool is_float = (M == M_ANISO || M == M_ANISOQ);
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        double w = weight[v];
+        if (w > mx) w = is_float ? (double)(float)mx : mx;
+        if (w < mn) w = is_float ? (double)(float)mn : mn;
+        weight[v] = w;
+        double row[NPAD];
+#pragma unroll
+        for (int k = 0; k < NPAD; k++) row[k] = 0.0;
+        double p[3] = {(double)xyz[3 * (int64_t)v], (double)xyz[3 * (int64_t)v + 1], (double)xyz[3 * (int64_t)v + 2]};
+        if (!is_float) {
+            row[0] = p[0] * w; row[1] = p[1] * w; row[2] = p[2] * w; row[3] = w;
+        } else {
+            float val[3] = {(float)p[0], (float)p[1], (float)p[2]};
+            float wf = (float)w;
+            double A = area[v];
+            double d[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) d[j] = pd ? (double)pd[6 * (int64_t)v + j] : 0.0;
+            float T[6];
+            T[0] = (float)(A * d[0] * d[0] + A * d[3] * d[3]);
+            T[1] = (float)(A * d[0] * d[1] + A * d[3] * d[4]);
+            T[2] = (float)(A * d[0] * d[2] + A * d[3] * d[5]);
+            T[3] = (float)(A * d[1] * d[1] + A * d[5] * d[5]);   // reference quirk: d[5] where d[4] is expected
+            T[4] = (float)(A * d[1] * d[2] + A * d[4] * d[5]);
+            T[5] = (float)(A * d[2] * d[2] + A * d[5] * d[5]);
+            float X0 = T[0] * val[0] + T[1] * val[1] + T[2] * val[2];
+            float X1 = T[1] * val[0] + T[3] * val[1] + T[4] * val[2];
+            float X2 = T[2] * val[0] + T[4] * val[1] + T[5] * val[2];
+            row[0] = (double)(val[0] * wf); row[1] = (double)(val[1] * wf); row[2] = (double)(val[2] * wf); row[3] = (double)wf;
+#pragma unroll
+            for (int k = 0; k < 6; k++) row[4 + k] = (double)T[k];
+            row[10] = (double)X0; row[11] = (double)X1; row[12] = (double)X2;
+        }
+        if (M == M_QEM || M == M_ANISOQ) {
+            constexpr int QO = MetricTraits<M>::QOFF;
+            double Q[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) Q[k] = 0.0;
+            for (int i = vf_ptr[v]; i < vf_ptr[v + 1]; i++) {
+                Tri3 t; load_face(xyz, tri, (int)(vf_keys[i] & 0xffffffffull), t);
+                tri_quadric_add(t, Q);
+            }
+#pragma unroll
+            for (int k = 0; k < 9; k++) row[QO + k] = Q[k];
+        }
+        store_row<NPAD>(items + (int64_t)v * NPAD, row);
+    }
+}
+
+// host payload (V x NP, packed) <-> device rows (V x NPAD)
+__global__ void k_pack_rows(int64_t n, int np, int npad, const double* __restrict__ in, double* out, int to_padded) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * npad; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / npad; int k = (int)(i % npad);
+        if (to_padded) out[i] = (k < np) ? in[r * np + k] : 0.0;
+        else if (k < np) out[r * np + k] = in[i];
+    }
+}
+
+}  // namespace acvd

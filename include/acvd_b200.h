@@ -1,0 +1,159 @@
+/*
+ * acvd_b200 — C ABI of the B200-native ACVD clustering hot path.
+ *
+ * The reference (valette/ACVD) has no FFI; its extension points for this path are the
+ * virtual hooks of the clustering engine and the duck-typed Metric template parameter
+ * (reference Common/vtkUniformClustering.h:139-142, 212, 261-267;
+ *  DiscreteRemeshing/vtkSurfaceClustering.h:44-52 selects the engine at compile time).
+ * Each entry point below names the reference member it replaces.  The host classes in
+ * acvd_b200/csrc/host (vtkIsotropicDiscreteRemeshing & co.) call only these functions.
+ *
+ * Conventions: plain pointers and sizes, caller owns every host pointer, the library
+ * copies in/out and retains nothing after a call returns.  Every function returns 0 on
+ * success or a negative ACVD_E* code; acvd_last_error() gives the message.  No C++
+ * exception crosses this boundary.  There is NO CPU fallback: without a CUDA device
+ * acvd_create fails with ACVD_ENODEVICE.
+ */
+#ifndef ACVD_B200_H
+#define ACVD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACVD_B200_ABI_VERSION 1
+
+typedef struct acvd_ctx acvd_ctx;
+
+enum {
+    ACVD_OK = 0,
+    ACVD_EINVAL = -1,     /* bad argument / call order */
+    ACVD_ENODEVICE = -2,  /* no CUDA device: the product has no CPU path */
+    ACVD_ECUDA = -3,      /* CUDA runtime error (message in acvd_last_error) */
+    ACVD_ENCCL = -4,      /* NCCL error */
+    ACVD_ENOMEM = -5
+};
+
+/* Metric kinds == the four Metric classes of the reference:
+ * vtkIsotropicMetricForClustering, vtkQEMetricForClustering,
+ * vtkAnisotropicMetricForClustering, vtkQuadricAnisotropicMetricForClustering. */
+enum { ACVD_METRIC_ISO = 0, ACVD_METRIC_QEM = 1, ACVD_METRIC_ANISO = 2, ACVD_METRIC_ANISOQ = 3 };
+
+/* Number of accumulated doubles per item/cluster: S[3] W | +Q[9] | +T[6] X[3] | +T X Q  (4/13/13/22). */
+int acvd_payload_size(int metric);
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* device < 0: use the current CUDA device. */
+int acvd_create(acvd_ctx** out, int device);
+int acvd_destroy(acvd_ctx* ctx);
+const char* acvd_last_error(acvd_ctx* ctx); /* ctx may be NULL: last create error */
+int acvd_abi_version(void);
+
+/* ---- mesh: replaces vtkSurfaceClustering::SetInput (DiscreteRemeshing/vtkSurfaceClustering.h:179)
+ * and the adapter accessors GetEdgeItems/GetItemNeighbours/GetItemEdges
+ * (DiscreteRemeshing/vtkVerticesProcessing.h:137-157): uploads float32 points + int32 triangles
+ * and builds the CSR vertex adjacency (int32 row_ptr[V+1], col[2E], rows sorted) on the device. */
+int acvd_set_mesh(acvd_ctx* ctx, int32_t V, int32_t F, const float* xyz, const int32_t* tri);
+int acvd_get_num_edges(acvd_ctx* ctx, int64_t* E);
+int acvd_get_csr(acvd_ctx* ctx, int32_t* row_ptr /*V+1*/, int32_t* col /*2E*/);
+
+/* ---- items: replaces Metric::BuildMetric (vtkIsotropicMetricForClustering.h:214-271,
+ * vtkQEMetricForClustering.h:297-345, vtk(Quadric)AnisotropicMetricForClustering.h BuildMetric):
+ * vertex areas, weights = area * indicator^gradation clamped to [mean/R, mean*R], Value = w*p,
+ * per-vertex quadrics / tensors, all computed on the device.
+ * custom_weights: V doubles (curvature indicator) or NULL; principal_dirs: 6V floats or NULL. */
+int acvd_build_items(acvd_ctx* ctx, int metric, double gradation, const double* custom_weights,
+                     const float* principal_dirs);
+/* Alternative: caller-provided payload, V x acvd_payload_size(metric) doubles, row-major. */
+int acvd_set_items(acvd_ctx* ctx, int metric, const double* payload);
+int acvd_get_items(acvd_ctx* ctx, double* payload);
+int acvd_get_vertex_areas(acvd_ctx* ctx, double* areas /*V*/);
+
+/* ---- clusters: SetNumberOfClusters (Common/vtkUniformClustering.h:62-69), Clustering array
+ * (:201-202), IsClusterFreezed (:328-329), FixedClusters / Cluster::AnchorItem
+ * (:331-332, vtkQEMetricForClustering.h:127-129).  Cluster id K is the NULL cluster. */
+int acvd_set_num_clusters(acvd_ctx* ctx, int32_t K);
+int acvd_set_clustering(acvd_ctx* ctx, const int32_t* clustering /*V*/);
+int acvd_get_clustering(acvd_ctx* ctx, int32_t* clustering /*V*/);
+int acvd_set_frozen(acvd_ctx* ctx, const uint8_t* frozen /*K, NULL clears*/);
+int acvd_set_fixed_clusters(acvd_ctx* ctx, const int64_t* anchor_items, int32_t n);
+
+/* ---- initial sampling: ComputeInitialRandomSampling (Common/vtkUniformClustering.h:1178-1316).
+ * Sequential by construction (mt19937 seed 0 + weight-bounded BFS in the reference's ring order);
+ * runs on the host inside this library from the uploaded mesh and the device-built weights,
+ * then uploads the result as the current clustering.  Not part of the timed clustering
+ * (the reference's own timer starts after it, vtkUniformClustering.h:690). */
+int acvd_initial_sampling(acvd_ctx* ctx);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+typedef struct acvd_params {
+    int32_t unconstrained_init;   /* UnconstrainedInitialization (vtkUniformClustering.h:322-323) */
+    int32_t quadrics_level;       /* QuadricsOptimizationLevel, default 3 (vtkQEMetricForClustering.h:368) */
+    int32_t connexity;            /* initial ConnexityConstraint (0; the -m loop resets it to 0) */
+    int32_t max_loops;            /* MaxNumberOfLoops, <=0 -> 5000000 */
+    int32_t max_convergences;     /* MaxNumberOfConvergences, <=0 -> 1000000000 */
+    int32_t early_stop_div;       /* <=0 -> 1000 (vtkUniformClustering.h:775) */
+    int32_t log_energy;           /* keep a per-round global-energy trace (energy.txt analogue) */
+    int32_t rounds_per_sync;      /* rounds between host polls of the counters, <=0 -> 1 */
+    double sv_threshold;          /* <=0 -> 1e-3 (Common/vtkQuadricTools.h:36) */
+} acvd_params;
+
+typedef struct acvd_report {
+    int64_t rounds;          /* reassignment rounds (the parallel analogue of NumberOfLoops) */
+    int64_t convergences;    /* convergence events */
+    int64_t tests;           /* vertex tests: evaluated (item, target cluster) candidates incl. blocked */
+    int64_t modifications;   /* committed moves */
+    int64_t proposals;       /* improving candidates submitted to conflict resolution */
+    int64_t disconnected;    /* clusters split by the last CleanClustering */
+    double energy;           /* ComputeGlobalEnergy (vtkUniformClustering.h:1319-1346) */
+    double ms_total;         /* wall time of the call */
+    double ms_propose;       /* device time in the reassignment (propose) kernel */
+    double ms_commit;        /* device time in conflict resolution + commit */
+    double ms_clean;         /* device time in stats / clean / fill */
+    int64_t propose_launches;
+    int64_t propose_bytes;   /* algorithmic bytes moved by the propose kernel (SURVEY §8d model) */
+} acvd_report;
+
+/* MinimizeEnergy (Common/vtkUniformClustering.h:725-830) with ProcessOneLoop (:833-995) replaced by
+ * conflict-free parallel rounds.  Phases, convergence events, CleanClustering / FillHoles /
+ * ReComputeStatistics follow the reference schedule. */
+int acvd_minimize(acvd_ctx* ctx, const acvd_params* params, acvd_report* report);
+
+/* ReComputeStatistics (:376-403): per-cluster sums, sizes, centroid, energy from the clustering. */
+int acvd_recompute_statistics(acvd_ctx* ctx, int constrained, int quadrics_level);
+/* CleanClustering (:406-549) / FillHolesInClustering (:552-633); *disconnected = clusters cleaned. */
+int acvd_clean_clustering(acvd_ctx* ctx, int32_t* disconnected);
+int acvd_fill_holes(acvd_ctx* ctx);
+/* One reassignment round on the current state (ProcessOneLoop analogue); outputs may be NULL. */
+int acvd_reassign_round(acvd_ctx* ctx, int constrained, int quadrics_level, int connexity,
+                        int64_t* proposals, int64_t* modifications, int64_t* tests);
+/* any pointer may be NULL; sums is K x acvd_payload_size(metric) */
+int acvd_get_cluster_stats(acvd_ctx* ctx, double* sums, double* centroid /*3K*/, double* energy /*K*/,
+                           int32_t* sizes /*K*/);
+int acvd_global_energy(acvd_ctx* ctx, double* energy);
+int acvd_get_energy_log(acvd_ctx* ctx, double* out, int32_t cap, int32_t* n);
+
+/* vtkQuadricTools::ComputeRepresentativePoint (Common/vtkQuadricTools.cxx:168-177), batched:
+ * n quadrics (9 doubles each) and points (3 doubles each, updated in place), rank deficiency out. */
+int acvd_representative_points(acvd_ctx* ctx, int32_t n, const double* quadrics9, double* points3,
+                               int32_t max_sv, double sv_threshold, int32_t* rank_deficiency);
+
+/* ---- integer stages after the hot path (vtkDiscreteRemeshing.h:1003-1133) ---------------- */
+/* boundary flag per vertex (has a neighbour in another cluster) */
+int acvd_boundary_flags(acvd_ctx* ctx, uint8_t* flags /*V*/);
+/* sorted unique (lo<<32|hi) cluster pairs joined by a mesh edge; pass out=NULL to query the count */
+int acvd_cluster_adjacency(acvd_ctx* ctx, int64_t* out, int64_t cap, int64_t* n);
+/* dual-mesh triangles in first-occurrence order over input faces; out=NULL queries the count */
+int acvd_dual_triangles(acvd_ctx* ctx, int32_t* out /*3*cap*/, int64_t cap, int64_t* n);
+
+/* ---- multi-GPU (one process per GPU; vertex-range partition) ------------------ */
+#define ACVD_NCCL_ID_BYTES 128
+int acvd_dist_unique_id(void* id_out /*ACVD_NCCL_ID_BYTES*/);
+int acvd_dist_init(acvd_ctx* ctx, int rank, int world, const void* id /*ACVD_NCCL_ID_BYTES*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACVD_B200_H */

@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer stages bit-exact given an identical cluster assignment;
+per-cluster sums and quadrics within 1e-6 relative; converged energy within 1 % of the sequential
+reference restatement.
+"""
+import numpy as np
+import pytest
+
+from acvd_b200 import meshgen
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6   # sums / quadrics tolerance stated by north_star
+
+
+def rel_err(a, b):
+    scale = np.maximum(np.abs(b).max(axis=0, keepdims=True), 1e-300)
+    return float((np.abs(a - b) / scale).max())
+
+
+@pytest.fixture(scope="module")
+def sphere():
+    return meshgen.geodesic_icosphere(32)   # V = 10 242
+
+
+@pytest.fixture(scope="module")
+def torus():
+    p, t = meshgen.torus_grid(160, 100, noise=0.002, seed=1)
+    return p, t, meshgen.torus_curvature_indicator(160, 100)
+
+
+def make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K, gradation=0.0, cw=None, pd=None):
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric(metric, gradation, cw, pd)
+    o.set_num_clusters(K)
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    g.build_items(metric, gradation, cw, pd)
+    g.set_num_clusters(K)
+    return o, g
+
+
+def test_csr_matches_oracle_adjacency(oracle_mod, gpu_ctx_factory, sphere):
+    p, t = sphere
+    o = oracle_mod.Oracle(p, t)
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    assert g.num_edges() == o.E
+    rp_o, col_o = o.csr()
+    rp_g, col_g = g.csr()
+    assert np.array_equal(rp_o, rp_g)          # same degrees
+    for v in (0, 1, 11, 12, 500, p.shape[0] - 1):
+        assert sorted(col_o[rp_o[v]:rp_o[v + 1]]) == list(col_g[rp_g[v]:rp_g[v + 1]])
+    # rows sorted, whole neighbour sets equal
+    so = np.concatenate([np.sort(col_o[rp_o[v]:rp_o[v + 1]]) for v in range(p.shape[0])])
+    assert np.array_equal(so, col_g)
+
+
+@pytest.mark.parametrize("metric", ["iso", "qem"])
+def test_items_match_oracle(oracle_mod, gpu_ctx_factory, torus, metric):
+    p, t, ind = torus
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, 50, 1.5, ind)
+    io, ig = o.items(), g.items()
+    assert io.shape == ig.shape
+    assert rel_err(ig, io) < REL
+    assert rel_err(g.vertex_areas()[:, None], o.vertex_areas()[:, None]) < 1e-12
+
+
+def test_items_match_oracle_aniso(oracle_mod, gpu_ctx_factory, sphere):
+    p, t = sphere
+    rng = np.random.default_rng(3)
+    pd = rng.normal(size=(p.shape[0], 6)).astype(np.float32)
+    ind = rng.uniform(0.5, 2.0, size=p.shape[0])
+    for metric in ("aniso", "anisoq"):
+        o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, 50, 1.5, ind, pd)
+        assert rel_err(g.items(), o.items()) < REL
+
+
+@pytest.mark.parametrize("metric", ["iso", "qem", "aniso", "anisoq"])
+def test_recompute_statistics_matches_oracle(oracle_mod, gpu_ctx_factory, sphere, metric):
+    p, t = sphere
+    K = 200
+    rng = np.random.default_rng(5)
+    pd = rng.normal(size=(p.shape[0], 6)).astype(np.float32) if metric.startswith("aniso") else None
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K, 0.0, None, pd)
+    g.set_items(metric, o.items())            # identical item bytes
+    cl = o.initial_sampling()
+    g.set_clustering(cl)
+    o.recompute_statistics()
+    g.recompute_statistics(1, 3)
+    so, co, eo, zo = o.cluster_stats()
+    sg, cg, eg, zg = g.cluster_stats()
+    assert np.array_equal(zo, zg)             # sizes exact
+    assert rel_err(sg, so) < REL
+    assert np.abs(cg - co).max() < 1e-6 * max(1.0, np.abs(co).max())
+    assert np.abs(eg - eo).max() <= REL * np.abs(eo).max()
+    assert abs(g.global_energy() - o.global_energy()) <= REL * abs(o.global_energy())
+
+
+def test_representative_points_match_oracle(oracle_mod, gpu_ctx_factory):
+    rng = np.random.default_rng(7)
+    n = 4096
+    Q = np.zeros((n, 9))
+    # sums of 1..3 plane quadrics: full rank, rank-deficient (plane, crease) and noisy cases
+    for i in range(n):
+        for _ in range(1 + i % 3):
+            nrm = rng.normal(size=3)
+            nrm /= np.linalg.norm(nrm)
+            d = rng.normal()
+            v = np.append(nrm, d)
+            q = np.outer(v, v)
+            Q[i] += [q[0, 0], q[0, 1], q[0, 2], q[0, 3], q[1, 1], q[1, 2], q[1, 3], q[2, 2], q[2, 3]]
+    P = rng.normal(size=(n, 3))
+    g = gpu_ctx_factory()
+    for level in (3, 2, 1):
+        pg, rg = g.representative_points(Q, P, level, 1e-3)
+        for i in range(n):
+            po, ro = oracle_mod.representative_point(Q[i], P[i], level, 1e-3)
+            assert ro == rg[i]
+            assert np.abs(po - pg[i]).max() < 1e-8 * max(1.0, np.abs(po).max())
+
+
+def test_integer_stages_bit_exact(oracle_mod, gpu_ctx_factory, sphere):
+    p, t = sphere
+    K = 300
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K)
+    o.initial_sampling()
+    o.minimize()
+    cl = o.clustering()
+    g.set_clustering(cl)
+    assert np.array_equal(g.boundary_flags(), o.boundary_flags())
+    assert np.array_equal(g.cluster_adjacency(), o.cluster_adjacency())
+    assert np.array_equal(g.dual_triangles(), o.dual_triangles())
+
+
+def test_clean_clustering_bit_exact(oracle_mod, gpu_ctx_factory, sphere):
+    p, t = sphere
+    K = 100
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K)
+    cl = o.initial_sampling().copy()
+    # break clusters apart: transplant scattered vertices into other clusters
+    rng = np.random.default_rng(11)
+    idx = rng.choice(p.shape[0], 400, replace=False)
+    cl[idx] = rng.integers(0, K, size=400)
+    o.set_clustering(cl)
+    g.set_clustering(cl)
+    do = o.clean_clustering()
+    dg = g.clean_clustering()
+    assert do == dg and do > 0
+    assert np.array_equal(o.clustering(), g.clustering())
+    # fill: every vertex assigned afterwards, clusters connected after one more clean
+    g.fill_holes()
+    cg = g.clustering()
+    assert cg.min() >= 0 and cg.max() < K
+
+
+@pytest.mark.parametrize("metric,uncon", [("iso", 0), ("qem", 1), ("qem", 0)])
+def test_minimize_energy_within_one_percent(oracle_mod, gpu_ctx_factory, sphere, metric, uncon):
+    p, t = sphere
+    K = 200
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K)
+    g.set_items(metric, o.items())
+    cl0 = o.initial_sampling()
+    g.set_clustering(cl0)
+    o.set_params(unconstrained_init=uncon)
+    o.minimize()
+    o.recompute_statistics()
+    rep = g.minimize(unconstrained_init=uncon, log_energy=1)
+    cg = g.clustering()
+    # invariants of a converged clustering
+    assert cg.min() >= 0 and cg.max() < K
+    sizes = np.bincount(cg, minlength=K)
+    assert sizes.min() >= 1 and sizes.sum() == p.shape[0]
+    assert g.clean_clustering() == 0          # every cluster connected
+    log = g.energy_log()
+    assert rep["modifications"] > 0 and rep["rounds"] == len(log)
+    # energy: raw (energy.txt parity number) and translation-invariant sum w |p - c|^2
+    it = o.items()
+    w = it[:, 3]
+    const = float(np.sum((it[:, :3] ** 2).sum(axis=1) / w))
+    e_o, e_g = o.global_energy(), rep["energy"]
+    assert abs(e_g - e_o) <= 0.01 * abs(e_o)
+    if metric == "iso":
+        t_o, t_g = const + e_o, const + e_g
+        assert t_g <= 1.01 * t_o
+    # the oracle finds nothing to improve on the GPU result and vice versa
+    o2 = oracle_mod.Oracle(p, t)
+    o2.build_metric(metric)
+    o2.set_num_clusters(K)
+    o2.set_clustering(cg)
+    o2.set_connexity(1)
+    o2.prime()
+    assert o2.process_one_loop() == 0
+
+
+def test_energy_monotone_per_phase(oracle_mod, gpu_ctx_factory, torus):
+    p, t, ind = torus
+    K = 400
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K, 1.5, ind)
+    cl0 = o.initial_sampling()
+    g.set_clustering(cl0)
+    g.recompute_statistics()
+    e_prev = g.global_energy()
+    for _ in range(30):
+        r = g.reassign_round(1, 3, 0)
+        e = g.global_energy()
+        assert e <= e_prev + 1e-12 * abs(e_prev)
+        assert (r["modifications"] > 0) == (r["proposals"] > 0)
+        e_prev = e
+
+
+def test_round_trip_determinism(gpu_ctx_factory, sphere):
+    p, t = sphere
+    res = []
+    for _ in range(2):
+        g = gpu_ctx_factory()
+        g.set_mesh(p, t)
+        g.build_items("qem")
+        g.set_num_clusters(150)
+        g.initial_sampling()
+        g.minimize(unconstrained_init=1)
+        res.append(g.clustering())
+    assert np.array_equal(res[0], res[1])
+
+
+def test_initial_sampling_matches_oracle(oracle_mod, gpu_ctx_factory, sphere):
+    p, t = sphere
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", 123)
+    g.set_items("iso", o.items())
+    g.initial_sampling()
+    assert np.array_equal(g.clustering(), o.initial_sampling())
