@@ -37,7 +37,8 @@ class Report(C.Structure):
         ("rounds", C.c_int64), ("convergences", C.c_int64), ("tests", C.c_int64), ("modifications", C.c_int64),
         ("proposals", C.c_int64), ("disconnected", C.c_int64), ("energy", C.c_double), ("ms_total", C.c_double),
         ("ms_propose", C.c_double), ("ms_commit", C.c_double), ("ms_clean", C.c_double),
-        ("propose_launches", C.c_int64), ("propose_bytes", C.c_int64),
+        ("propose_launches", C.c_int64), ("propose_bytes", C.c_int64), ("ms_device", C.c_double),
+        ("kernel_launches", C.c_int64),
     ]
 
     def asdict(self):
@@ -62,6 +63,8 @@ SYMBOLS = [
     ("acvd_set_num_clusters", C.c_int, [_vp, _i32]),
     ("acvd_set_clustering", C.c_int, [_vp, _vp]),
     ("acvd_get_clustering", C.c_int, [_vp, _vp]),
+    ("acvd_save_clustering", C.c_int, [_vp]),
+    ("acvd_restore_clustering", C.c_int, [_vp]),
     ("acvd_set_frozen", C.c_int, [_vp, _vp]),
     ("acvd_set_fixed_clusters", C.c_int, [_vp, _vp, _i32]),
     ("acvd_initial_sampling", C.c_int, [_vp]),
@@ -186,6 +189,12 @@ class Context:
             out = np.zeros(self.V, dtype=np.int32)
         self._ck(self.L.acvd_get_clustering(self.h, _p(out)))
         return out
+
+    def save_clustering(self):
+        self._ck(self.L.acvd_save_clustering(self.h))
+
+    def restore_clustering(self):
+        self._ck(self.L.acvd_restore_clustering(self.h))
 
     def set_frozen(self, flags):
         a = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)

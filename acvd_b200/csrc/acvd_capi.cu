@@ -19,6 +19,14 @@
 #include "metric.cuh"
 #include "reassign.cuh"
 
+// every launch site of our own kernels has the context in scope as `c`: count them for the report
+#undef ACVD_LAUNCH_CHECK
+#define ACVD_LAUNCH_CHECK()              \
+    do {                                 \
+        c->launches++;                   \
+        ACVD_CUDA(cudaGetLastError());   \
+    } while (0)
+
 static void* cub_temp(acvd_ctx* c, size_t bytes) {
     c->cub_temp.alloc(bytes + 16);
     return c->cub_temp.p;
@@ -101,7 +109,6 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     c->tri.alloc(3 * (size_t)F);
     ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    c->h_tri.assign(tri, tri + 3 * (size_t)F);
     const int vbits = bits_for((uint64_t)V);
     // --- CSR adjacency: 6F directed half-edges -> sort -> unique
     {
@@ -309,6 +316,25 @@ extern "C" int acvd_get_clustering(acvd_ctx* c, int32_t* cl) {
     ACVD_API_END(c)
 }
 
+extern "C" int acvd_save_clustering(acvd_ctx* c) {
+    ACVD_API_BEGIN(c)
+    if (!c->K) throw std::runtime_error("acvd_save_clustering: no clustering");
+    c->cid_saved.alloc(c->V);
+    ACVD_CUDA(cudaMemcpyAsync(c->cid_saved.p, c->cid.p, (size_t)c->V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_restore_clustering(acvd_ctx* c) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !c->cid_saved.p) throw std::runtime_error("acvd_restore_clustering: nothing saved");
+    ACVD_CUDA(cudaMemcpyAsync(c->cid.p, c->cid_saved.p, (size_t)c->V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats_valid = false;
+    ACVD_API_END(c)
+}
+
 extern "C" int acvd_set_frozen(acvd_ctx* c, const uint8_t* frozen) {
     ACVD_API_BEGIN(c)
     if (!c->K) throw std::runtime_error("acvd_set_frozen: set the number of clusters first");
@@ -342,8 +368,10 @@ extern "C" int acvd_initial_sampling(acvd_ctx* c) {
     if (!c->K || !c->have_items) throw std::runtime_error("acvd_initial_sampling: need items and a cluster count");
     std::vector<double> w(c->V);
     ACVD_CUDA(cudaMemcpy(w.data(), c->weight.p, (size_t)c->V * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<int> h_tri(3 * (size_t)c->F);
+    ACVD_CUDA(cudaMemcpy(h_tri.data(), c->tri.p, h_tri.size() * sizeof(int), cudaMemcpyDeviceToHost));
     HostRings rings;
-    rings.build(c->V, c->F, c->h_tri.data());
+    rings.build(c->V, c->F, h_tri.data());
     std::vector<int> out;
     initial_random_sampling(c->V, c->K, rings, w.data(), c->fixed, out);
     ACVD_CUDA(cudaMemcpy(c->cid.p, out.data(), (size_t)c->V * sizeof(int), cudaMemcpyHostToDevice));
@@ -432,6 +460,7 @@ static int clean_clustering(acvd_ctx* c) {
     k_cc_winner<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, c->n_comp.p, c->winner.p);
     k_count_ge2<<<grid_for(K), kThreads, 0, c->stream>>>(K, c->n_comp.p, c->scalars.p + 1);
     k_cc_apply<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->n_comp.p, c->winner.p, c->scalars.p + 2);
+    c->launches += 3;
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
@@ -464,6 +493,7 @@ static void fill_holes(acvd_ctx* c) {
         ACVD_CUDA(cudaMemsetAsync(c->scalars.p + 3, 0, sizeof(unsigned long long), c->stream));
         k_fill_pick<<<grid_for(n), kThreads, 0, c->stream>>>(n, K, c->null_list.p, c->row_ptr.p, c->col.p, c->cid.p, c->pick.p);
         k_fill_apply<<<grid_for(n), kThreads, 0, c->stream>>>(n, c->null_list.p, c->pick.p, c->cid.p, c->scalars.p + 3);
+        c->launches += 1;
         ACVD_LAUNCH_CHECK();
         ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 3, c->scalars.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
@@ -606,9 +636,13 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     int constrained = (c->metric == M_QEM && p.unconstrained_init) ? 0 : 1;
     int connexity = p.connexity;
     const int qlevel = p.quadrics_level;
-    cudaEvent_t ec0, ec1;
+    cudaEvent_t ec0, ec1, et0, et1;
     ACVD_CUDA(cudaEventCreate(&ec0));
     ACVD_CUDA(cudaEventCreate(&ec1));
+    ACVD_CUDA(cudaEventCreate(&et0));
+    ACVD_CUDA(cudaEventCreate(&et1));
+    ACVD_CUDA(cudaEventRecord(et0, c->stream));
+    const int64_t launches0 = c->launches;
     auto timed_clean = [&](auto&& fn) {
         ACVD_CUDA(cudaEventRecord(ec0, c->stream));
         fn();
@@ -664,8 +698,16 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         force_all = 1;
     }
     R.energy = global_energy(c);
+    ACVD_CUDA(cudaEventRecord(et1, c->stream));
+    ACVD_CUDA(cudaEventSynchronize(et1));
+    float ms_dev = 0;
+    ACVD_CUDA(cudaEventElapsedTime(&ms_dev, et0, et1));
+    R.ms_device = ms_dev;
+    R.kernel_launches = c->launches - launches0;
     cudaEventDestroy(ec0);
     cudaEventDestroy(ec1);
+    cudaEventDestroy(et0);
+    cudaEventDestroy(et1);
     R.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rep) *rep = R;
     ACVD_API_END(c)

@@ -22,14 +22,14 @@ struct acvd_ctx {
     DevBuf<float> xyz;
     DevBuf<int> tri, row_ptr, col, vf_ptr;
     DevBuf<unsigned long long> vf_keys;
-    std::vector<int> h_tri;          // host copy for the sequential initial sampling
     // items
     int metric = -1;
     DevBuf<double> area, weight, items;
     bool have_items = false;
     // clusters
     int K = 0;
-    DevBuf<int> cid, csize, mod_round, anchor;
+    DevBuf<int> cid, cid_saved, csize, mod_round, anchor;
+    int64_t launches = 0;             // kernels launched (reported per call)
     DevBuf<unsigned char> frozen;
     bool has_frozen = false, has_anchor = false;
     std::vector<int64_t> fixed;

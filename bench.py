@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — ACVDQ clustering to convergence on synthetic meshes (BASELINE.json metric).
+
+One "step" = one full pass of the hot path: acvd_minimize() (MinimizeEnergy of the reference,
+Common/vtkUniformClustering.h:725-830) from the same initial sampling to convergence on the workload.
+The JSON line reports vertex tests/s (whole job), ms per step (= time to convergence), the roofline of the
+dominant kernel (the reassignment/propose kernel), an end-to-end number through the C ABI with host
+buffers, and a CPU baseline (the restated reference from oracle/) timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|C1|C4s|C2s] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "acvdq_vertex_tests_per_s"
+UNIT = "tests/s"
+
+WORKLOADS = {
+    # name: (description, generator kwargs)
+    "C4": "ACVDQ -s 100 on a 40,000,002-vertex displaced geodesic sphere -> 400k clusters (BASELINE configs[3])",
+    "C4s": "1/100-scale C4: 400,002-vertex displaced sphere -> 4k clusters",
+    "C2": "ACVDQ gradation 1.5 (analytic curvature) on a 2.6M-vertex noisy torus -> 100k clusters (configs[1])",
+    "C2s": "1/16-scale C2",
+    "C1": "ACVD isotropic on a 163,842-vertex icosphere -> 3000 clusters (configs[0])",
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_workload(name):
+    from acvd_b200 import meshgen
+    w = meshgen.workload(name)
+    w["name"] = name
+    w["unconstrained_init"] = 1 if w["metric"] == "qem" else 0   # ACVDQ.cxx:325
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.dev)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic(workload):
+    """dram bytes per propose launch from the committed ncu capture for this workload, if any."""
+    path = os.path.join(ROOT, "profiles", "propose_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_sample(w, threads, loops, steps=1, warmup=0):
+    """Bounded sample of the restated reference (oracle) on the same workload: `loops` passes of
+    ProcessOneLoop from the initial sampling.  Returns per-step (tests, seconds) and setup info."""
+    from oracle import oracle
+    t0 = time.time()
+    o = oracle.Oracle(w["points"], w["triangles"])
+    o.build_metric(w["metric"], w["gradation"], w["indicator"])
+    o.set_num_clusters(w["K"])
+    cl0 = o.initial_sampling().copy()
+    setup_s = time.time() - t0
+    res = []
+    for it in range(warmup + steps):
+        o.set_num_clusters(w["K"])        # resets loops / counters / queue
+        o.set_clustering(cl0)
+        o.set_params(unconstrained_init=w["unconstrained_init"])
+        t0 = time.perf_counter()
+        if threads > 1:
+            o.minimize_threaded(threads, loops)
+        else:
+            o.minimize(loops)
+        dt = time.perf_counter() - t0
+        r = o.report()
+        if it >= warmup:
+            res.append((r["tests"], dt))
+    return res, setup_s
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (restated in oracle/, the
+    upstream sources need VTK and cannot be compiled here) with all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload(args.workload)
+    threads = os.cpu_count() or 1
+    loops = args.ref_loops
+    res, setup_s = cpu_sample(w, threads, loops, steps=args.steps, warmup=args.warmup)
+    tests = sum(r[0] for r in res)
+    secs = sum(r[1] for r in res)
+    val = tests / secs
+    sample = (f"{loops} ProcessOneLoop passes from the initial sampling per step (first, unconstrained phase) of the "
+              f"threaded restatement (vtkThreadedClustering scheme, {threads} threads) on the full {args.workload} mesh")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(res)), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "V": int(w["points"].shape[0]), "K": int(w["K"])},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "setup_s": setup_s,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("ACVD_BENCH_WORKLOAD", "C4"), choices=list(WORKLOADS))
+    ap.add_argument("--ref-loops", type=int, default=3, help="ProcessOneLoop passes per reference step")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("note: timing rules ask for >= 3 warm-up steps")
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the acvd_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from acvd_b200 import capi
+    t0 = time.time()
+    w = make_workload(args.workload)
+    V, F, K = int(w["points"].shape[0]), int(w["triangles"].shape[0]), int(w["K"])
+    log(f"[rank {rank}] workload {args.workload}: V={V} F={F} K={K} generated in {time.time()-t0:.1f}s")
+
+    # pinned host copies of the inputs (e2e copies come from pinned memory)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    _k1, h_xyz = pinned(w["points"])
+    _k2, h_tri = pinned(w["triangles"])
+    h_ind = None
+    if w["indicator"] is not None:
+        _k3, h_ind = pinned(w["indicator"])
+
+    ctx = capi.Context(local_rank)
+    if world > 1:
+        uid = [capi.Context.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.dist_init(rank, world, uid[0])
+    t0 = time.time()
+    ctx.set_mesh(h_xyz, h_tri)
+    ctx.build_items(w["metric"], w["gradation"], h_ind)
+    ctx.set_num_clusters(K)
+    ctx.initial_sampling()          # host, sequential; outside the timed region as in the reference (:690)
+    ctx.save_clustering()
+    _k4, h_cl0 = pinned(ctx.clustering())
+    log(f"[rank {rank}] setup (mesh+items+initial sampling) {time.time()-t0:.1f}s")
+    mparams = dict(unconstrained_init=w["unconstrained_init"])
+
+    def step():
+        ctx.restore_clustering()
+        return ctx.minimize(**mparams)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    reps = []
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            reps.append(step())
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    ms_dev = sum(r["ms_device"] for r in reps)
+    if dist is not None:
+        tt = torch.tensor([ms_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev = float(tt.item())
+    tests = sum(r["tests"] for r in reps)
+    value = tests / (ms_dev * 1e-3)
+    ms_per_step = ms_dev / args.steps
+
+    # ---- end to end through the C ABI from pinned host buffers (fresh context state every step)
+    e2e_tests = 0
+    _k5, h_out = pinned(np.zeros(V, dtype=np.int32))
+    barrier()
+    t_e2e0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.set_mesh(h_xyz, h_tri)
+        ctx.build_items(w["metric"], w["gradation"], h_ind)
+        ctx.set_num_clusters(K)
+        ctx.set_clustering(h_cl0)
+        r = ctx.minimize(**mparams)
+        ctx.clustering(h_out)
+        sums, cen, en, sz = ctx.cluster_stats()
+        e2e_tests += r["tests"]
+    barrier()
+    t_e2e = time.perf_counter() - t_e2e0
+    h2d = h_xyz.nbytes + h_tri.nbytes + h_cl0.nbytes + (h_ind.nbytes if h_ind is not None else 0)
+    np_pay = {"iso": 4, "qem": 13, "aniso": 13, "anisoq": 22}[w["metric"]]
+    d2h = h_out.nbytes + K * (np_pay * 8 + 24 + 8 + 4)
+    e2e = {"value": e2e_tests / t_e2e if args.e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "s_per_step": t_e2e / max(1, args.e2e_steps), "steps": args.e2e_steps}
+
+    # ---- roofline of the dominant kernel (k_propose), timed with CUDA events inside the library
+    peak, peak_src = measured_peak()
+    p_bytes = sum(r["propose_bytes"] for r in reps)
+    p_ms = sum(r["ms_propose"] for r in reps)
+    p_launches = sum(r["propose_launches"] for r in reps)
+    achieved = p_bytes / (p_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_propose (boundary-item reassignment)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
+                "peak_source": peak_src, "bytes_per_launch": p_bytes / max(1, p_launches),
+                "us_per_launch": 1e3 * p_ms / max(1, p_launches), "share_of_step": p_ms / ms_dev}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): sequential restated reference, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        loops = args.ref_loops
+        res, setup_s = cpu_sample(w, 1, loops)
+        cpu = {"value": res[0][0] / res[0][1], "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{loops} sequential ProcessOneLoop passes from the initial sampling on the full {args.workload} mesh "
+                         f"({res[0][0]} tests in {res[0][1]:.1f}s; first, unconstrained phase)"}
+
+    if rank == 0:
+        last = reps[-1]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "V": V, "F": F, "K": K,
+                       "metric_kind": w["metric"], "gradation": w["gradation"],
+                       "l2": "inputs larger than L2 (items+CSR >> 126 MB)" if V >= 2000000 else "inputs fit L2 (small workload)",
+                       "parallelism": f"vertex-range x{world}" if world > 1 else "single GPU"},
+            "time_to_convergence_s": ms_per_step * 1e-3, "wall_s_per_step": t_wall / args.steps,
+            "rounds": last["rounds"], "convergences": last["convergences"], "modifications": last["modifications"],
+            "energy": last["energy"], "tests_per_step": tests / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(sum(r["kernel_launches"] for r in reps)),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

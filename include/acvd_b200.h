@@ -77,6 +77,10 @@ int acvd_get_vertex_areas(acvd_ctx* ctx, double* areas /*V*/);
 int acvd_set_num_clusters(acvd_ctx* ctx, int32_t K);
 int acvd_set_clustering(acvd_ctx* ctx, const int32_t* clustering /*V*/);
 int acvd_get_clustering(acvd_ctx* ctx, int32_t* clustering /*V*/);
+/* device-resident copy of the current clustering / restore it (re-running from the same start
+ * without a host round trip; SetInitialClustering analogue, vtkUniformClustering.h:337-342) */
+int acvd_save_clustering(acvd_ctx* ctx);
+int acvd_restore_clustering(acvd_ctx* ctx);
 int acvd_set_frozen(acvd_ctx* ctx, const uint8_t* frozen /*K, NULL clears*/);
 int acvd_set_fixed_clusters(acvd_ctx* ctx, const int64_t* anchor_items, int32_t n);
 
@@ -114,6 +118,8 @@ typedef struct acvd_report {
     double ms_clean;         /* device time in stats / clean / fill */
     int64_t propose_launches;
     int64_t propose_bytes;   /* algorithmic bytes moved by the propose kernel (SURVEY §8d model) */
+    double ms_device;        /* CUDA-event time of the whole call on the context's stream */
+    int64_t kernel_launches; /* kernels this call launched */
 } acvd_report;
 
 /* MinimizeEnergy (Common/vtkUniformClustering.h:725-830) with ProcessOneLoop (:833-995) replaced by
