@@ -36,8 +36,9 @@ class Report(C.Structure):
     _fields_ = [
         ("rounds", C.c_int64), ("convergences", C.c_int64), ("tests", C.c_int64), ("modifications", C.c_int64),
         ("proposals", C.c_int64), ("disconnected", C.c_int64), ("energy", C.c_double), ("ms_total", C.c_double),
-        ("ms_propose", C.c_double), ("ms_commit", C.c_double), ("ms_clean", C.c_double),
-        ("propose_launches", C.c_int64), ("propose_bytes", C.c_int64), ("ms_device", C.c_double),
+        ("ms_scan", C.c_double), ("ms_evaluate", C.c_double), ("ms_commit", C.c_double), ("ms_clean", C.c_double),
+        ("round_launches", C.c_int64), ("scan_bytes", C.c_int64), ("evaluate_bytes", C.c_int64),
+        ("evaluated", C.c_int64), ("ms_device", C.c_double),
         ("kernel_launches", C.c_int64),
     ]
 

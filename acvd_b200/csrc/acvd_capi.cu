@@ -27,6 +27,24 @@
         ACVD_CUDA(cudaGetLastError());   \
     } while (0)
 
+// ACVD_TRACE=1: wall-clock trace of the host driver's stages on stderr (the reference's ConsoleOutput>1
+// per-loop lines are the analogue, Common/vtkUniformClustering.h:752-760)
+static bool trace_on() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("ACVD_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
+    return on == 1;
+}
+struct TraceScope {
+    const char* name; acvd_ctx* c; std::chrono::steady_clock::time_point t0;
+    TraceScope(acvd_ctx* ctx, const char* n) : name(n), c(ctx) { if (trace_on()) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); } }
+    ~TraceScope() {
+        if (!trace_on()) return;
+        cudaStreamSynchronize(c->stream);
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[acvd trace] %-28s %10.3f ms\n", name, ms);
+    }
+};
+
 static void* cub_temp(acvd_ctx* c, size_t bytes) {
     c->cub_temp.alloc(bytes + 16);
     return c->cub_temp.p;
@@ -72,6 +90,7 @@ extern "C" int acvd_create(acvd_ctx** out, int device) {
         ACVD_CUDA(cudaMallocHost(&c->h_scalars, 8 * sizeof(unsigned long long)));
         c->ctr.alloc(1);
         c->scalars.alloc(8);
+        if (const char* e = getenv("ACVD_COMMIT_PASSES")) c->commit_passes = std::max(1, atoi(e));
     } catch (const CudaError& err) {
         std::string m = std::string("CUDA error in acvd_create: ") + cudaGetErrorString(err.code);
         delete c;
@@ -282,7 +301,12 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
     c->cid.alloc(V);
     c->csize.alloc(K); c->mod_round.alloc(K); c->anchor.alloc(K); c->frozen.alloc(K);
     c->csum.alloc((size_t)K * npad); c->cenergy.alloc(K); c->ccentroid.alloc(3 * (size_t)K);
-    c->best.alloc(K); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->prop_e.alloc(V);
+    c->best.alloc(K); c->modbits.alloc((size_t)(K + 31) / 32 + 1); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->plist_b.alloc(V); c->work.alloc(V);
+    {
+        const size_t n_tiles = ((size_t)V + 31) / 32;
+        c->tile_sig.alloc(n_tiles * kSigSlots); c->tile_active.alloc(n_tiles); c->active_tiles.alloc(n_tiles); c->round_scalars.alloc(2);
+        ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    } c->prop_e.alloc(V);
     ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)V * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->mod_round.p, 0, (size_t)K * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->anchor.p, 0xff, (size_t)K * sizeof(int), c->stream));
@@ -394,6 +418,7 @@ static bool qem_as_iso(const acvd_ctx* c, int constrained, int qlevel) {
 }
 
 static void recompute_statistics(acvd_ctx* c, int constrained, int qlevel, double thr) {
+    TraceScope ts(c, "recompute_statistics");
     const int V = c->V, K = c->K;
     c->sort_k0.alloc(V); c->sort_k1.alloc(V); c->sort_v0.alloc(V); c->sort_v1.alloc(V); c->seg.alloc((size_t)K + 2);
     ACVD_CUDA(cudaMemcpyAsync(c->sort_k0.p, c->cid.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
@@ -435,12 +460,15 @@ extern "C" int acvd_recompute_statistics(acvd_ctx* c, int constrained, int qleve
 }
 
 static int clean_clustering(acvd_ctx* c) {
+    TraceScope ts(c, "clean_clustering");
     const int V = c->V, K = c->K;
     c->label.alloc(V); c->comp_size.alloc(V); c->n_comp.alloc(K); c->winner.alloc(K);
     k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->label.p);
     ACVD_LAUNCH_CHECK();
     int* d_changed = reinterpret_cast<int*>(c->scalars.p);
+    int cc_iters = 0;
     for (int iter = 0; iter < 100000; iter++) {
+        cc_iters++;
         ACVD_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(int), c->stream));
         for (int rep = 0; rep < 4; rep++) {
             k_cc_propagate<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, d_changed);
@@ -465,10 +493,12 @@ static int clean_clustering(acvd_ctx* c) {
     ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     c->stats_valid = false;
+    if (trace_on()) fprintf(stderr, "[acvd trace]   cc iterations x4: %d, disconnected %d, reset %d\n", cc_iters, (int)c->h_scalars[1], (int)c->h_scalars[2]);
     return (int)c->h_scalars[1];
 }
 
 static void fill_holes(acvd_ctx* c) {
+    TraceScope ts(c, "fill_holes");
     const int V = c->V, K = c->K;
     c->null_list.alloc(V);
     ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
@@ -489,6 +519,7 @@ static void fill_holes(acvd_ctx* c) {
         ACVD_CUDA(cudaMemcpyAsync(c->null_list.p, c->sort_k0.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     }
     int64_t remaining = n;
+    if (trace_on()) fprintf(stderr, "[acvd trace]   fill: %d NULL vertices\n", n);
     while (remaining > 0) {
         ACVD_CUDA(cudaMemsetAsync(c->scalars.p + 3, 0, sizeof(unsigned long long), c->stream));
         k_fill_pick<<<grid_for(n), kThreads, 0, c->stream>>>(n, K, c->null_list.p, c->row_ptr.p, c->col.p, c->cid.p, c->pick.p);
@@ -521,7 +552,7 @@ extern "C" int acvd_fill_holes(acvd_ctx* c) {
 
 // ---------------------------------------------------------------------------------------------
 // reassignment rounds
-struct RoundResult { unsigned long long proposals, mods, tests, evaluated, boundary; float ms_propose, ms_commit; };
+struct RoundResult { unsigned long long proposals, mods, tests, evaluated, boundary, active_tiles; float ms_scan, ms_eval, ms_commit; };
 
 static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all) {
     ReassignArgs A;
@@ -529,44 +560,76 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.row_ptr = c->row_ptr.p; A.col = c->col.p; A.cid = c->cid.p;
     A.items = c->items.p; A.csum = c->csum.p; A.cenergy = c->cenergy.p; A.csize = c->csize.p;
     A.mod_round = c->mod_round.p;
+    A.modbits = c->modbits.p;
     A.frozen = c->has_frozen ? c->frozen.p : nullptr;
     A.anchor = c->has_anchor ? c->anchor.p : nullptr;
     A.xyz = c->xyz.p;
     A.best = c->best.p; A.prop_dst = c->prop_dst.p; A.prop_key = c->prop_key.p; A.prop_e = c->prop_e.p;
-    A.plist = c->plist.p; A.ctr = c->ctr.p;
+    A.plist = c->plist_cur ? c->plist_b.p : c->plist.p;
+    A.plist_prev = c->plist_cur ? c->plist.p : c->plist_b.p;
+    A.n_prev_props = c->round_scalars.p + 1;
+    A.tile_sig = c->tile_sig.p; A.tile_active = c->tile_active.p; A.active_tiles = c->active_tiles.p;
+    A.n_active_tiles = c->round_scalars.p;
+    A.work = c->work.p; A.ctr = c->ctr.p;
     A.round = c->round; A.force_all = force_all; A.connexity = connexity; A.cfg = cfg;
     return A;
 }
 
 static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso) {
+    // proposals of the previous round become the carry list (none survive a phase start: everything is dirty)
+    if (force_all) ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p + 1, 0, sizeof(unsigned long long), c->stream));
+    else ACVD_CUDA(cudaMemcpyAsync(c->round_scalars.p + 1, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    c->plist_cur ^= 1;
     ReassignArgs A = make_args(c, cfg, connexity, force_all);
     ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
-    const int gp = grid_for(c->V), gc = kNumSMs * 4;
+    ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, sizeof(unsigned long long), c->stream));
+    const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
+    ACVD_LAUNCH_CHECK();
+    const int n_tiles = (c->V + 31) / 32;
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+    ACVD_LAUNCH_CHECK();
+    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    ACVD_LAUNCH_CHECK();
+    if (!force_all) {
+        k_carry<<<gc, kThreads, 0, c->stream>>>(A);
+        ACVD_LAUNCH_CHECK();
+    }
+    ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
     switch (c->metric) {
-        case M_ISO: k_propose<M_ISO, 4><<<gp, kThreads, 0, c->stream>>>(A); break;
+        case M_ISO: k_evaluate<M_ISO, 4><<<ge, kThreads, 0, c->stream>>>(A); break;
         case M_QEM:
-            if (as_iso) k_propose<M_ISO, 14><<<gp, kThreads, 0, c->stream>>>(A);
-            else k_propose<M_QEM, 14><<<gp, kThreads, 0, c->stream>>>(A);
+            if (as_iso) k_evaluate<M_ISO, 14><<<ge, kThreads, 0, c->stream>>>(A);
+            else k_evaluate<M_QEM, 14><<<ge, kThreads, 0, c->stream>>>(A);
             break;
-        case M_ANISO: k_propose<M_ANISO, 14><<<gp, kThreads, 0, c->stream>>>(A); break;
-        default: k_propose<M_ANISOQ, 22><<<gp, kThreads, 0, c->stream>>>(A); break;
+        case M_ANISO: k_evaluate<M_ANISO, 14><<<ge, kThreads, 0, c->stream>>>(A); break;
+        default: k_evaluate<M_ANISOQ, 22><<<ge, kThreads, 0, c->stream>>>(A); break;
     }
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    switch (c->metric) {
-        case M_ISO: k_commit<M_ISO, M_ISO><<<gc, kThreads, 0, c->stream>>>(A); break;
-        case M_QEM:
-            if (as_iso) k_commit<M_ISO, M_QEM><<<gc, kThreads, 0, c->stream>>>(A);
-            else k_commit<M_QEM, M_QEM><<<gc, kThreads, 0, c->stream>>>(A);
-            break;
-        case M_ANISO: k_commit<M_ANISO, M_ANISO><<<gc, kThreads, 0, c->stream>>>(A); break;
-        default: k_commit<M_ANISOQ, M_ANISOQ><<<gc, kThreads, 0, c->stream>>>(A); break;
+    for (int pass = 0; pass < c->commit_passes; pass++) {
+        if (pass > 0) {
+            ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
+            k_resubmit<<<gc, kThreads, 0, c->stream>>>(A);
+            ACVD_LAUNCH_CHECK();
+        }
+        switch (c->metric) {
+            case M_ISO: k_commit<M_ISO, M_ISO><<<gc, kThreads, 0, c->stream>>>(A); break;
+            case M_QEM:
+                if (as_iso) k_commit<M_ISO, M_QEM><<<gc, kThreads, 0, c->stream>>>(A);
+                else k_commit<M_QEM, M_QEM><<<gc, kThreads, 0, c->stream>>>(A);
+                break;
+            case M_ANISO: k_commit<M_ANISO, M_ANISO><<<gc, kThreads, 0, c->stream>>>(A); break;
+            default: k_commit<M_ANISOQ, M_ANISOQ><<<gc, kThreads, 0, c->stream>>>(A); break;
+        }
+        ACVD_LAUNCH_CHECK();
     }
-    ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
     ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 7, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     c->round++;
 }
 
@@ -574,8 +637,9 @@ static RoundResult finish_round(acvd_ctx* c) {
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     RoundResult r;
     r.proposals = c->h_ctr->proposals; r.mods = c->h_ctr->mods; r.tests = c->h_ctr->tests;
-    r.evaluated = c->h_ctr->evaluated; r.boundary = c->h_ctr->boundary;
-    ACVD_CUDA(cudaEventElapsedTime(&r.ms_propose, c->ev[0], c->ev[1]));
+    r.evaluated = c->h_ctr->evaluated; r.boundary = c->h_ctr->boundary; r.active_tiles = c->h_scalars[7];
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, c->ev[0], c->ev[3]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
     return r;
 }
@@ -590,13 +654,23 @@ static double global_energy(acvd_ctx* c) {
     return (double)s;
 }
 
-// algorithmic bytes of one propose launch (DESIGN.md "bytes model"): frontier scan of every vertex
-// (row_ptr 4 + cid 4 + deg * (col 4 + neighbour cid 4)) + per evaluated vertex the item row, the source
-// cluster row and its (size, energy) + per test the destination row and its energy + proposal write-back
-static int64_t propose_bytes(const acvd_ctx* c, const RoundResult& r, bool as_iso) {
+// algorithmic bytes per launch (DESIGN.md "bytes model"):
+//   scan     tile filter: 32 B signature + 1 B flag per tile (+4 per active tile listed); every vertex of an
+//            active tile: row_ptr 4 + cid 4 + deg * (col 4 + neighbour cid 4) (deg = mesh mean), signature
+//            write-back 32 B per active tile, + 4 per work-list entry written
+//   evaluate per work-list vertex: list entry 4 + its CSR row again (8 + 8 deg) + item row + source cluster
+//            row + (size, energy) 12; per test: destination row + energy 8; per proposal: write-back 28
+//            (dst 4, key 8, energies 16) + 4 list entry
+static int64_t scan_bytes(const acvd_ctx* c, const RoundResult& r) {
+    const int64_t n_tiles = ((int64_t)c->V + 31) / 32;
+    const double deg = c->V ? (double)c->nnz / c->V : 0.0;
+    return 33 * n_tiles + (int64_t)r.active_tiles * (4 + 32 + (int64_t)(32.0 * (8.0 + 8.0 * deg))) + 4 * (int64_t)r.evaluated;
+}
+static int64_t eval_bytes(const acvd_ctx* c, const RoundResult& r, bool as_iso) {
     const int64_t nl = 8 * (int64_t)(as_iso ? 4 : payload_npad(c->metric));
-    return 8 * (int64_t)c->V + 8 * c->nnz + (int64_t)r.evaluated * (2 * nl + 16) + (int64_t)r.tests * (nl + 8) +
-           (int64_t)r.proposals * 28;
+    const double deg = c->V ? (double)c->nnz / c->V : 0.0;
+    return (int64_t)((double)r.evaluated * (12.0 + 8.0 * deg)) + (int64_t)r.evaluated * (2 * nl + 12) +
+           (int64_t)r.tests * (nl + 8) + (int64_t)r.proposals * 32;
 }
 
 extern "C" int acvd_reassign_round(acvd_ctx* c, int constrained, int qlevel, int connexity, int64_t* proposals,
@@ -675,9 +749,13 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         RoundResult r = finish_round(c);
         loops++;
         R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;
-        R.ms_propose += r.ms_propose; R.ms_commit += r.ms_commit;
-        R.propose_launches++; R.propose_bytes += propose_bytes(c, r, as_iso);
+        R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;
+        R.round_launches++; R.scan_bytes += scan_bytes(c, r); R.evaluate_bytes += eval_bytes(c, r, as_iso);
+        R.evaluated += (int64_t)r.evaluated;
         if (p.log_energy) c->energy_log.push_back(global_energy(c));
+        if (trace_on())
+            fprintf(stderr, "[acvd trace] round %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
+                    (long long)loops, nconv, r.active_tiles, r.boundary, r.evaluated, r.tests, r.proposals, r.mods, 1e3 * r.ms_scan, 1e3 * r.ms_eval, 1e3 * r.ms_commit);
         const int64_t mods = (int64_t)r.mods;
         // convergence event (:773-776); a round commits a conflict-free subset, so the analogue of the
         // reference's "modifications in one sweep" is the number of live improving proposals

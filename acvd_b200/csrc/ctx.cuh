@@ -8,7 +8,7 @@
 
 #include "../../include/acvd_b200.h"
 #include "common.cuh"
-#include "reassign.cuh"
+#include "reassign_types.cuh"
 
 using namespace acvd;
 
@@ -37,12 +37,17 @@ struct acvd_ctx {
     bool stats_valid = false;
     // reassignment scratch
     DevBuf<unsigned long long> best, prop_key;
-    DevBuf<int> prop_dst, plist;
+    DevBuf<int> prop_dst, plist, plist_b, work, tile_sig, active_tiles;
+    DevBuf<unsigned char> tile_active;
+    DevBuf<unsigned long long> round_scalars;   // [0] active tiles, [1] proposals of the previous round
+    int plist_cur = 0;
     DevBuf<double2> prop_e;
+    DevBuf<unsigned> modbits;
     DevBuf<RoundCounters> ctr;
+    int commit_passes = 4;            // select+commit passes per round (ACVD_COMMIT_PASSES)
     RoundCounters* h_ctr = nullptr;   // pinned
     int round = 1;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // generic scratch
     DevBuf<char> cub_temp;
     DevBuf<int> sort_k0, sort_k1, sort_v0, sort_v1, seg, label, comp_size, n_comp, null_list, pick;

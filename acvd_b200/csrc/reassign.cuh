@@ -6,8 +6,10 @@
 // Its per-edge candidate set over all boundary edges is exactly {(v, b): v boundary vertex, b a cluster
 // adjacent to v}, so one round here is:
 //
-//   propose : every boundary vertex whose own or adjacent clusters changed since its last evaluation
-//             ("recently modified" rule, :909-920) evaluates all adjacent clusters b:
+//   scan    : a coalesced streaming pass over the CSR finds the boundary vertices whose own or adjacent
+//             clusters changed since their last evaluation ("recently modified" rule, :909-920) and
+//             compacts them into a work list;
+//   evaluate: every work-list vertex evaluates all adjacent clusters b:
 //                 try = E(a - v) + E(b + v)   vs   cur = E(a) + E(b)          (:922-958)
 //             blocked when size(a)==1 or the connexity test fails (:929,:945), or a cluster is frozen
 //             (:914-915).  The best strictly improving candidate becomes the vertex's proposal and is
@@ -19,42 +21,9 @@
 // Vertices in the NULL cluster (id K) adopt an adjacent cluster unconditionally (:881-907).
 #pragma once
 #include "metric.cuh"
+#include "reassign_types.cuh"
 
 namespace acvd {
-
-struct RoundCounters {
-    unsigned long long proposals;   // live proposals submitted this round
-    unsigned long long mods;        // committed moves
-    unsigned long long tests;       // vertex tests (evaluated candidates incl. blocked)
-    unsigned long long evaluated;   // vertices fully evaluated this round (dirty boundary vertices)
-    unsigned long long boundary;    // boundary vertices seen
-    unsigned long long pad[3];
-};
-
-struct ReassignArgs {
-    int V, K;
-    const int* __restrict__ row_ptr;
-    const int* __restrict__ col;
-    int* cid;
-    const double* __restrict__ items;   // V x stride
-    double* csum;                       // K x stride
-    double* cenergy;                    // K
-    int* csize;                         // K
-    int* mod_round;                     // K: last round a cluster was modified
-    const unsigned char* __restrict__ frozen;   // K or null
-    const int* __restrict__ anchor;     // K or null (QEM fixed clusters)
-    const float* __restrict__ xyz;      // V x 3 (anchor coordinates)
-    unsigned long long* best;           // K: min priority key per cluster this round
-    int* prop_dst;                      // V: proposed destination or -1
-    unsigned long long* prop_key;       // V
-    double2* prop_e;                    // V: (E(a - v), E(b + v)) of the proposal
-    int* plist;                         // compact list of proposing vertices this round
-    RoundCounters* ctr;
-    int round;
-    int force_all;                      // SetAllClustersToModified (:717-722)
-    int connexity;
-    EvalCfg cfg;
-};
 
 // Coordinates of the anchor item of cluster c (QEM fixed clusters, vtkQEMetricForClustering.h:270-275), or null.
 template <int EM>
@@ -104,44 +73,249 @@ static __device__ __noinline__ bool connexity_problem(int v, int a, const int* _
     return reach != full;
 }
 
-// EM: metric whose energy is evaluated; STRIDE: doubles per payload row in memory.
-// (QEM's unconstrained phase evaluates the isotropic energy on the first 4 doubles of its rows.)
-template <int EM, int STRIDE>
-__global__ void __launch_bounds__(kThreads) k_propose(ReassignArgs A) {
-    constexpr int NL = MetricTraits<EM>::NPAD;   // doubles loaded per row
-    const int K = A.K;
-    unsigned n_tests = 0, n_eval = 0, n_bnd = 0;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < A.V; v += gridDim.x * blockDim.x) {
-        const int a = A.cid[v];
-        const int beg = A.row_ptr[v], end = A.row_ptr[v + 1];
-        bool boundary = false;
-        const int rm1 = A.round - 1;
-        bool a_dirty = A.force_all || (a < K && A.mod_round[a] >= rm1);
-        bool dirty = a_dirty;
-        for (int e = beg; e < end; e++) {
-            int b = A.cid[A.col[e]];
-            if (b != a) {
-                boundary = true;
-                if (b < K && A.mod_round[b] >= rm1) dirty = true;
+// ---------------------------------------------------------------------------------------------------
+// k_modbits: one bit per cluster, set when the cluster was modified in the previous round (or force_all).
+// K/8 bytes (50 KB at K = 400k): the scan's "recently modified" look-ups hit L1 instead of gathering
+// 4-byte stamps from L2.
+__global__ void __launch_bounds__(kThreads) k_modbits(int K, const int* __restrict__ mod_round, int rm1, int force_all,
+                                                      unsigned* __restrict__ bits) {
+    const int n_words = (K + 31) >> 5;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_words * 32; c += gridDim.x * blockDim.x) {
+        bool m = c < K && (force_all || mod_round[c] >= rm1);
+        unsigned w = __ballot_sync(0xffffffffu, m);
+        if ((threadIdx.x & 31) == 0) bits[c >> 5] = w;
+    }
+}
+
+// k_scan: the frontier scan.  One warp owns 32 consecutive vertices; their CSR rows are contiguous in
+// `col`, so the warp streams row_ptr / cid / col with fully coalesced loads and only the neighbour
+// cluster ids are gathered (mostly L1/L2 hits with a locality-preserving vertex numbering).  Loads are
+// issued kScanUnroll batches deep to keep several requests in flight per warp.  Per entry the owner
+// row follows from a ballot of the row starts (shuffle binary search when the tile has empty rows);
+// boundary / dirty flags are reduced to the owner lanes with ballots and per-row bit ranges (no
+// shared memory, no atomics).  Output: compact work list of boundary vertices that must be
+// (re)evaluated; boundary vertices whose clusters did not change re-submit their stored proposal.
+constexpr int kScanUnroll = 4;
+constexpr int kSigSlots = 8;     // cluster ids remembered per 32-vertex tile (32 bytes)
+
+// k_tile_filter: a tile (32 consecutive vertices) must be re-scanned only if one of the clusters in its
+// signature -- the clusters of its vertices and of their neighbours, recorded by the last scan of the
+// tile -- was modified in the previous round: a vertex's boundary/dirty state and proposal depend on
+// those clusters only, and any move that changes the tile's signature modifies a cluster already in it.
+// Reads 32 B per tile instead of ~1 KB of CSR: tail rounds cost microseconds, not a full sweep.
+__global__ void __launch_bounds__(kThreads) k_tile_filter(int n_tiles, int K, int force_all, const int4* __restrict__ sig,
+                                                          const unsigned* __restrict__ modbits, unsigned char* tile_active,
+                                                          int* active_tiles, unsigned long long* n_active) {
+    const int lane = threadIdx.x & 31;
+    for (int t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; t0 < n_tiles; t0 += gridDim.x * blockDim.x) {
+        const int t = t0 + lane;
+        bool act = false;
+        if (t < n_tiles) {
+            act = force_all != 0;
+            if (!act) {
+                int4 s0 = __ldg(sig + 2 * (int64_t)t), s1 = __ldg(sig + 2 * (int64_t)t + 1);
+                int c[kSigSlots] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                act = c[0] == -2;   // overflowed signature: always rescan
+#pragma unroll
+                for (int k = 0; k < kSigSlots; k++)
+                    act = act || (c[k] >= 0 && c[k] < K && ((modbits[c[k] >> 5] >> (c[k] & 31)) & 1u));
+            }
+            tile_active[t] = act ? 1 : 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(n_active, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (act) active_tiles[base + __popc(m & ((1u << lane) - 1u))] = t;
+        }
+    }
+}
+
+// append value `val` (warp-uniform) to the warp-uniform signature registers if absent
+__device__ __forceinline__ void sig_insert(int (&sg)[kSigSlots], int& n_sig, int val) {
+    bool present = false;
+#pragma unroll
+    for (int k = 0; k < kSigSlots; k++) present |= (k < n_sig && sg[k] == val);
+    if (!present) {
+#pragma unroll
+        for (int k = 0; k < kSigSlots; k++) if (k == n_sig) sg[k] = val;
+        n_sig++;   // beyond kSigSlots: overflow, recorded by the caller
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
+    const int K = A.K, V = A.V;
+    const int lane = threadIdx.x & 31;
+    const unsigned lane_le = 0xffffffffu >> (31 - lane);   // bits 0..lane
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_active = (int)*A.n_active_tiles;           // written by k_tile_filter of this round
+    const unsigned* __restrict__ modbits = A.modbits;
+    unsigned n_bnd = 0;
+    for (int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_active; ti += n_warps) {
+        const int tile = A.active_tiles[ti];
+        const int v = tile * 32 + lane;
+        const bool valid = v < V;
+        const int rp = A.row_ptr[valid ? v : V];
+        const int rpn = valid ? A.row_ptr[v + 1] : rp;
+        const int a = valid ? A.cid[v] : -1;
+        const int beg = __shfl_sync(0xffffffffu, rp, 0);
+        const int end = __shfl_sync(0xffffffffu, rpn, 31);
+        const bool has_empty = __any_sync(0xffffffffu, valid && rp == rpn);
+        bool bnd = false, dirty = false;
+        // signature of the tile: distinct clusters of its vertices ...
+        int sg[kSigSlots];
+#pragma unroll
+        for (int k = 0; k < kSigSlots; k++) sg[k] = -1;
+        int n_sig = 0;
+        for (unsigned lm = __ballot_sync(0xffffffffu, valid); lm;) {
+            const int val = __shfl_sync(0xffffffffu, a, __ffs(lm) - 1);
+            sig_insert(sg, n_sig, val);
+            lm &= ~__ballot_sync(0xffffffffu, a == val);
+        }
+        for (int base0 = beg; base0 < end; base0 += 32 * kScanUnroll) {
+            int b[kScanUnroll];
+#pragma unroll
+            for (int k = 0; k < kScanUnroll; k++) {
+                const int e = base0 + 32 * k + lane;
+                b[k] = (e < end) ? __ldg(A.col + e) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < kScanUnroll; k++) b[k] = (b[k] >= 0) ? A.cid[b[k]] : -1;
+#pragma unroll
+            for (int k = 0; k < kScanUnroll; k++) {
+                const int base = base0 + 32 * k;
+                if (base >= end) break;                       // warp-uniform
+                const int e = base + lane;
+                const bool ok = e < end;
+                int j;
+                if (!has_empty) {
+                    // rows starting at or before `base`, plus row starts strictly inside (base, e]
+                    const int j0 = __popc(__ballot_sync(0xffffffffu, rp <= base)) - 1;
+                    const int off = rp - base;
+                    const unsigned starts = __reduce_or_sync(0xffffffffu, (off > 0 && off < 32) ? (1u << off) : 0u);
+                    j = j0 + __popc(starts & lane_le);
+                } else {
+                    int lo = 0, hi = 31;                      // largest j with row start <= e
+#pragma unroll
+                    for (int it = 0; it < 5; it++) {
+                        int mid = (lo + hi + 1) >> 1;
+                        int r = __shfl_sync(0xffffffffu, rp, mid);
+                        if (r <= e) lo = mid; else hi = mid - 1;
+                    }
+                    j = lo;
+                }
+                const int a_own = __shfl_sync(0xffffffffu, a, j);
+                const int bb = b[k];
+                const bool isb = ok && (bb != a_own);
+                const bool isd = isb && (bb < K) && ((modbits[bb >> 5] >> (bb & 31)) & 1u);
+                const unsigned mb = __ballot_sync(0xffffffffu, isb);
+                const unsigned md = __ballot_sync(0xffffffffu, isd);
+                const int l0 = max(rp - base, 0), h0 = min(rpn - base, 32);
+                if (l0 < h0) {
+                    const unsigned m = (0xffffffffu >> (32 - h0)) & (0xffffffffu << l0);
+                    bnd |= (mb & m) != 0;
+                    dirty |= (md & m) != 0;
+                }
+                // ... and of their neighbours: only a boundary entry whose cluster is not recorded yet adds one
+                // (membership is tested by all lanes at once; the serial loop runs once per new cluster)
+                if (mb) {
+                    bool fresh = isb;
+#pragma unroll
+                    for (int q = 0; q < kSigSlots; q++) fresh = fresh && (sg[q] != bb);
+                    for (unsigned lm = __ballot_sync(0xffffffffu, fresh); lm;) {
+                        const int val = __shfl_sync(0xffffffffu, bb, __ffs(lm) - 1);
+                        sig_insert(sg, n_sig, val);
+                        lm &= ~__ballot_sync(0xffffffffu, bb == val);
+                    }
+                }
             }
         }
-        if (!boundary) {
-            if (a_dirty) A.prop_dst[v] = -1;   // became interior: drop any stale proposal
-            continue;
+        {   // store the signature: lanes 0..7 write one slot each (32 B, coalesced)
+            int mine = -1;
+#pragma unroll
+            for (int k = 0; k < kSigSlots; k++) if (lane == k) mine = sg[k];
+            if (n_sig > kSigSlots && lane == 0) mine = -2;
+            if (lane < kSigSlots) A.tile_sig[(int64_t)tile * kSigSlots + lane] = mine;
         }
-        n_bnd++;
-        if (!dirty) {   // clusters unchanged since last evaluation: the stored proposal is still exact
-            int d = A.prop_dst[v];
+        bnd = bnd && valid;
+        if (bnd) {
+            n_bnd++;
+            dirty = dirty || (a < K && ((modbits[a >> 5] >> (a & 31)) & 1u));
+        }
+        const bool work = bnd && dirty;
+        const unsigned mw = __ballot_sync(0xffffffffu, work);
+        if (mw) {
+            int basew = 0;
+            if (lane == 0) basew = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)__popc(mw));
+            basew = __shfl_sync(0xffffffffu, basew, 0);
+            if (work) A.work[basew + __popc(mw & (lane_le >> 1))] = v;
+        }
+        if (bnd && !dirty) {   // clusters unchanged since the last evaluation: the stored proposal is still exact
+            const int d = A.prop_dst[v];
             if (d >= 0) {
-                unsigned long long key = A.prop_key[v];
+                const unsigned long long key = A.prop_key[v];
                 if (a < K) atomicMin(&A.best[a], key);
                 atomicMin(&A.best[d], key);
                 int slot = (int)atomicAdd(&A.ctr->proposals, 1ull);
                 A.plist[slot] = v;
             }
-            continue;
         }
-        n_eval++;
+    }
+    warp_count_add(&A.ctr->boundary, n_bnd);
+}
+
+// k_carry: live proposals of the previous round whose tile is not re-scanned this round (none of their
+// clusters changed) compete again with their stored key.
+__global__ void __launch_bounds__(kThreads) k_carry(ReassignArgs A) {
+    const int K = A.K;
+    const int n_old = (int)*A.n_prev_props;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_old; i += gridDim.x * blockDim.x) {
+        const int v = A.plist_prev[i];
+        if (A.tile_active[v >> 5]) continue;                  // the scan handles vertices of active tiles
+        const int d = A.prop_dst[v];
+        if (d < 0) continue;                                  // committed last round
+        const int a = A.cid[v];
+        const unsigned long long key = A.prop_key[v];
+        if (a < K) atomicMin(&A.best[a], key);
+        atomicMin(&A.best[d], key);
+        int slot = (int)atomicAdd(&A.ctr->proposals, 1ull);
+        A.plist[slot] = v;
+    }
+}
+
+// k_resubmit: between commit passes of one round.  A proposal whose two clusters were not touched by
+// the commits so far is still exact (same sums, same energies, same ring in its source cluster), so it
+// competes again; repeating select + commit a few times approaches a maximal independent set of moves
+// per round without re-scanning the mesh.
+__global__ void __launch_bounds__(kThreads) k_resubmit(ReassignArgs A) {
+    const int K = A.K;
+    const int n_props = (int)A.ctr->proposals;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
+        const int v = A.plist[i];
+        const int d = A.prop_dst[v];
+        if (d < 0) continue;                                  // committed in an earlier pass
+        const int a = A.cid[v];
+        if (A.mod_round[d] == A.round || (a < K && A.mod_round[a] == A.round)) continue;
+        const unsigned long long key = A.prop_key[v];
+        if (a < K) atomicMin(&A.best[a], key);
+        atomicMin(&A.best[d], key);
+    }
+}
+
+// k_evaluate: one thread per work-list vertex (dense: every lane evaluates a dirty boundary vertex).
+// EM: metric whose energy is evaluated; STRIDE: doubles per payload row in memory.
+// (QEM's unconstrained phase evaluates the isotropic energy on the first 4 doubles of its rows.)
+template <int EM, int STRIDE>
+__global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) {
+    constexpr int NL = MetricTraits<EM>::NPAD;   // doubles loaded per row
+    const int K = A.K;
+    const int n_work = (int)A.ctr->evaluated;    // written by k_scan of this round
+    unsigned n_tests = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
+        const int v = A.work[i];
+        const int a = A.cid[v];
+        const int beg = A.row_ptr[v], end = A.row_ptr[v + 1];
         int best_b = -1;
         double best_delta = 0.0, best_ea = 0.0, best_eb = 0.0;
         unsigned long long key = 0;
@@ -163,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) k_propose(ReassignArgs A) {
                 load_row_ro<NL>(A.items + (int64_t)v * STRIDE, it);
                 load_row<NL>(A.csum + (int64_t)a * STRIDE, s);
 #pragma unroll
-                for (int i = 0; i < NL; i++) s[i] -= it[i];
+                for (int k = 0; k < NL; k++) s[k] -= it[k];
                 ea_new = cluster_energy<EM>(s, A.cfg, nullptr, anchor_point<EM>(A, a, anchor_pt));
             }
             for (int e = beg; e < end; e++) {
@@ -177,7 +351,7 @@ __global__ void __launch_bounds__(kThreads) k_propose(ReassignArgs A) {
                 if (blocked) continue;
                 const double2* ps = reinterpret_cast<const double2*>(A.csum + (int64_t)b * STRIDE);
 #pragma unroll
-                for (int i = 0; i < NL / 2; i++) { double2 u = ps[i]; s[2 * i] = u.x + it[2 * i]; s[2 * i + 1] = u.y + it[2 * i + 1]; }
+                for (int k = 0; k < NL / 2; k++) { double2 u = ps[k]; s[2 * k] = u.x + it[2 * k]; s[2 * k + 1] = u.y + it[2 * k + 1]; }
                 double eb_new = cluster_energy<EM>(s, A.cfg, nullptr, anchor_point<EM>(A, b, anchor_pt));
                 double tr = ea_new + eb_new;
                 double cur = cur_a + A.cenergy[b];
@@ -200,8 +374,6 @@ __global__ void __launch_bounds__(kThreads) k_propose(ReassignArgs A) {
         }
     }
     warp_count_add(&A.ctr->tests, n_tests);
-    warp_count_add(&A.ctr->evaluated, n_eval);
-    warp_count_add(&A.ctr->boundary, n_bnd);
 }
 
 // UM: metric of the stored sums (all UM::NPAD doubles of a row are updated);
@@ -215,6 +387,7 @@ __global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
         const int v = A.plist[i];
         const int d = A.prop_dst[v];
+        if (d < 0) continue;                                  // committed in an earlier pass of this round
         const unsigned long long key = A.prop_key[v];
         const int a = A.cid[v];
         bool win = (A.best[d] == key) && (a >= K || A.best[a] == key);

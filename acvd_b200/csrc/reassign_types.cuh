@@ -1,0 +1,49 @@
+// Argument / counter structs of the reassignment kernels (shared with the host-side context).
+#pragma once
+#include "metric.cuh"
+
+namespace acvd {
+
+struct RoundCounters {
+    unsigned long long proposals;   // live proposals submitted this round
+    unsigned long long mods;        // committed moves
+    unsigned long long tests;       // vertex tests (evaluated candidates incl. blocked)
+    unsigned long long evaluated;   // vertices fully evaluated this round (dirty boundary vertices)
+    unsigned long long boundary;    // boundary vertices seen
+    unsigned long long pad[3];
+};
+
+struct ReassignArgs {
+    int V, K;
+    const int* __restrict__ row_ptr;
+    const int* __restrict__ col;
+    int* cid;
+    const double* __restrict__ items;   // V x stride
+    double* csum;                       // K x stride
+    double* cenergy;                    // K
+    int* csize;                         // K
+    int* mod_round;                     // K: last round a cluster was modified
+    unsigned* modbits;                  // ceil(K/32) words: cluster modified in the previous round
+    const unsigned char* __restrict__ frozen;   // K or null
+    const int* __restrict__ anchor;     // K or null (QEM fixed clusters)
+    const float* __restrict__ xyz;      // V x 3 (anchor coordinates)
+    unsigned long long* best;           // K: min priority key per cluster this round
+    int* prop_dst;                      // V: proposed destination or -1
+    unsigned long long* prop_key;       // V
+    double2* prop_e;                    // V: (E(a - v), E(b + v)) of the proposal
+    int* plist;                         // compact list of proposing vertices this round
+    int* work;                          // compact list of boundary vertices to (re)evaluate this round
+    const int* plist_prev;              // proposing vertices of the previous round
+    const unsigned long long* n_prev_props;   // their count
+    int* tile_sig;                      // n_tiles x 8 cluster-id signature of every 32-vertex tile
+    unsigned char* tile_active;         // n_tiles: tile is re-scanned this round
+    int* active_tiles;                  // compact list of active tiles
+    unsigned long long* n_active_tiles;
+    RoundCounters* ctr;
+    int round;
+    int force_all;                      // SetAllClustersToModified (:717-722)
+    int connexity;
+    EvalCfg cfg;
+};
+
+}  // namespace acvd

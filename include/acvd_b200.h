@@ -113,11 +113,14 @@ typedef struct acvd_report {
     int64_t disconnected;    /* clusters split by the last CleanClustering */
     double energy;           /* ComputeGlobalEnergy (vtkUniformClustering.h:1319-1346) */
     double ms_total;         /* wall time of the call */
-    double ms_propose;       /* device time in the reassignment (propose) kernel */
+    double ms_scan;          /* device time in the frontier-scan kernel (k_scan) */
+    double ms_evaluate;      /* device time in the candidate evaluation kernel (k_evaluate) */
     double ms_commit;        /* device time in conflict resolution + commit */
     double ms_clean;         /* device time in stats / clean / fill */
-    int64_t propose_launches;
-    int64_t propose_bytes;   /* algorithmic bytes moved by the propose kernel (SURVEY §8d model) */
+    int64_t round_launches;  /* launches of each of k_scan / k_evaluate / k_commit */
+    int64_t scan_bytes;      /* algorithmic bytes moved by k_scan (SURVEY §8d model) */
+    int64_t evaluate_bytes;  /* algorithmic bytes moved by k_evaluate */
+    int64_t evaluated;       /* work-list vertices evaluated */
     double ms_device;        /* CUDA-event time of the whole call on the context's stream */
     int64_t kernel_launches; /* kernels this call launched */
 } acvd_report;

@@ -19,8 +19,10 @@ def run(name, p, t, metric, K, uncon, gradation=0.0, ind=None, with_oracle=True)
     cl0 = g.clustering()
     t0 = time.time(); rep = g.minimize(unconstrained_init=uncon); dt = time.time() - t0
     print(f"gpu minimize {dt:.3f}s", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in rep.items()}, flush=True)
-    gbs = rep["propose_bytes"] / (rep["ms_propose"] * 1e-3) / 1e9
-    print(f"propose: {rep['ms_propose']/rep['propose_launches']*1e3:.1f} us/launch, algorithmic {gbs:.1f} GB/s; tests/s={rep['tests']/dt:.3e}")
+    n = rep["round_launches"]
+    print(f"scan: {rep['ms_scan']/n*1e3:.1f} us/launch, {rep['scan_bytes']/(rep['ms_scan']*1e-3)/1e9:.1f} GB/s | "
+          f"evaluate: {rep['ms_evaluate']/n*1e3:.1f} us/launch, {rep['evaluate_bytes']/(rep['ms_evaluate']*1e-3)/1e9:.1f} GB/s | "
+          f"commit {rep['ms_commit']/n*1e3:.1f} us/launch; tests/s={rep['tests']/dt:.3e}")
     if with_oracle:
         o = oracle.Oracle(p, t)
         o.build_metric(metric, gradation, ind)

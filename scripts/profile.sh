@@ -7,6 +7,6 @@ mkdir -p gpurun_out
 BENCH="python bench.py --workload $WL --steps 1 --warmup 0 --no-cpu-baseline --e2e-steps 0"
 # every launch with its device time (cold-cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_${WL}_${TAG}.csv $BENCH > gpurun_out/launches_${WL}_${TAG}.log 2>&1
-# the reassignment kernel, 3 launches in the middle of the first phase
-ncu --set full --clock-control none --import-source on -k regex:k_propose -s 10 -c 3 -f -o gpurun_out/prof_propose_${WL}_${TAG} $BENCH > gpurun_out/prof_propose_${WL}_${TAG}.log 2>&1
+# the reassignment kernels, a few launches in the first phase
+ncu --set full --clock-control none --import-source on -k regex:"k_scan|k_evaluate" -s 20 -c 4 -f -o gpurun_out/prof_reassign_${WL}_${TAG} $BENCH > gpurun_out/prof_reassign_${WL}_${TAG}.log 2>&1
 ls -la gpurun_out
