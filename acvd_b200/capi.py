@@ -29,6 +29,7 @@ class Params(C.Structure):
         ("unconstrained_init", C.c_int32), ("quadrics_level", C.c_int32), ("connexity", C.c_int32),
         ("max_loops", C.c_int32), ("max_convergences", C.c_int32), ("early_stop_div", C.c_int32),
         ("log_energy", C.c_int32), ("rounds_per_sync", C.c_int32), ("sv_threshold", C.c_double),
+        ("bulk_rounds", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -39,7 +40,7 @@ class Report(C.Structure):
         ("ms_scan", C.c_double), ("ms_evaluate", C.c_double), ("ms_commit", C.c_double), ("ms_clean", C.c_double),
         ("round_launches", C.c_int64), ("scan_bytes", C.c_int64), ("evaluate_bytes", C.c_int64),
         ("evaluated", C.c_int64), ("ms_device", C.c_double),
-        ("kernel_launches", C.c_int64),
+        ("kernel_launches", C.c_int64), ("bulk_rounds", C.c_int64),
     ]
 
     def asdict(self):

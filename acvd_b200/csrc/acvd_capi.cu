@@ -301,6 +301,7 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
     c->cid.alloc(V);
     c->csize.alloc(K); c->mod_round.alloc(K); c->anchor.alloc(K); c->frozen.alloc(K);
     c->csum.alloc((size_t)K * npad); c->cenergy.alloc(K); c->ccentroid.alloc(3 * (size_t)K);
+    c->isum.alloc(4 * (size_t)K); c->bulk_cen.alloc(3 * (size_t)K); c->leave_cnt.alloc(K); c->join_cnt.alloc(K);
     c->best.alloc(K); c->modbits.alloc((size_t)(K + 31) / 32 + 1); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->plist_b.alloc(V); c->work.alloc(V);
     {
         const size_t n_tiles = ((size_t)V + 31) / 32;
@@ -571,7 +572,7 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.tile_sig = c->tile_sig.p; A.tile_active = c->tile_active.p; A.active_tiles = c->active_tiles.p;
     A.n_active_tiles = c->round_scalars.p;
     A.work = c->work.p; A.ctr = c->ctr.p;
-    A.round = c->round; A.force_all = force_all; A.connexity = connexity; A.cfg = cfg;
+    A.round = c->round; A.force_all = force_all; A.bulk = 0; A.connexity = connexity; A.cfg = cfg;
     return A;
 }
 
@@ -633,6 +634,73 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
     c->round++;
 }
 
+// fixed-point scale of the bulk rounds: a power of two such that no cluster sum can overflow 2^62
+static void ensure_fx_scale(acvd_ctx* c) {
+    if (c->fx_scale > 0) return;
+    const int V = c->V, stride = payload_npad(c->metric);
+    DevBuf<double> bound, total;
+    bound.alloc(V); total.alloc(1);
+    k_item_bound<<<grid_for(V), kThreads, 0, c->stream>>>(V, stride, c->items.p, bound.p);
+    ACVD_LAUNCH_CHECK();
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceReduce::Sum(nullptr, tb, bound.p, total.p, V, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceReduce::Sum(t, tb, bound.p, total.p, V, c->stream));
+    double T = 0;
+    ACVD_CUDA(cudaMemcpyAsync(&T, total.p, sizeof T, cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    if (!(T > 0) || !std::isfinite(T)) { c->fx_scale = -1; return; }   // degenerate weights: bulk rounds off
+    int e = 0;
+    std::frexp(T, &e);                      // T = m * 2^e, m in [0.5, 1)
+    c->fx_scale = std::ldexp(1.0, 61 - e);  // T * scale < 2^61
+}
+
+static BulkArgs make_bulk_args(acvd_ctx* c) {
+    BulkArgs B;
+    B.isum = c->isum.p; B.ccen = c->bulk_cen.p; B.leave_cnt = c->leave_cnt.p; B.join_cnt = c->join_cnt.p;
+    B.scale = c->fx_scale;
+    return B;
+}
+
+static void bulk_init(acvd_ctx* c) {
+    k_bulk_init<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, payload_npad(c->metric), c->csum.p, make_bulk_args(c));
+    ACVD_LAUNCH_CHECK();
+}
+
+// one bulk (Lloyd-criterion) round: scan -> evaluate against the centroids -> commit all -> refresh centroids
+static void launch_bulk_round(acvd_ctx* c, int force_all) {
+    EvalCfg cfg = make_cfg(0, 0, 0);
+    c->plist_cur = 0;
+    ReassignArgs A = make_args(c, cfg, 0, force_all);
+    A.bulk = 1;
+    BulkArgs B = make_bulk_args(c);
+    ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
+    ACVD_LAUNCH_CHECK();
+    const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    const int n_tiles = (c->V + 31) / 32;
+    ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+    ACVD_LAUNCH_CHECK();
+    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    k_bulk_commit<<<gc, kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric));
+    ACVD_LAUNCH_CHECK();
+    k_bulk_refresh<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->csize.p, B);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 7, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    c->round++;
+    c->stats_valid = false;
+}
+
 static RoundResult finish_round(acvd_ctx* c) {
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     RoundResult r;
@@ -671,6 +739,13 @@ static int64_t eval_bytes(const acvd_ctx* c, const RoundResult& r, bool as_iso) 
     const double deg = c->V ? (double)c->nnz / c->V : 0.0;
     return (int64_t)((double)r.evaluated * (12.0 + 8.0 * deg)) + (int64_t)r.evaluated * (2 * nl + 12) +
            (int64_t)r.tests * (nl + 8) + (int64_t)r.proposals * 32;
+}
+
+// bulk evaluate: list entry 4 + CSR row (8 + 8 deg) + point 12 + own centroid 24 + size 4 per work-list vertex;
+// 24 (centroid) per test; 8 per proposal written + commit: item 32 + 2 x 32 fixed-point sums
+static int64_t bulk_eval_bytes(const acvd_ctx* c, const RoundResult& r) {
+    const double deg = c->V ? (double)c->nnz / c->V : 0.0;
+    return (int64_t)((double)r.evaluated * (12.0 + 8.0 * deg + 40.0)) + (int64_t)r.tests * 24 + (int64_t)r.proposals * 8;
 }
 
 extern "C" int acvd_reassign_round(acvd_ctx* c, int constrained, int qlevel, int connexity, int64_t* proposals,
@@ -741,9 +816,39 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         for (int i = 0; i < c->K; i++) if (!fr[i]) early_items += sz[i];
     }
     int64_t loops = 0;
+    const int bulk_cap = p.bulk_rounds < 0 ? 0 : (p.bulk_rounds == 0 ? 1000 : p.bulk_rounds);
     while (true) {
         EvalCfg cfg = make_cfg(constrained, qlevel, thr);
         const bool as_iso = qem_as_iso(c, constrained, qlevel);
+        // ---- bulk (Lloyd-criterion) rounds open the phases that end by early convergence
+        if (force_all && bulk_cap > 0 && nconv <= 1 && !connexity && !c->has_frozen && !c->has_anchor &&
+            (c->metric == M_ISO || as_iso)) {
+            ensure_fx_scale(c);
+            if (c->fx_scale > 0) {
+                bulk_init(c);
+                int fa = 1;
+                for (int b = 0; b < bulk_cap && loops < p.max_loops; b++) {
+                    launch_bulk_round(c, fa);
+                    fa = 0;
+                    RoundResult r = finish_round(c);
+                    loops++;
+                    R.rounds++; R.bulk_rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods;
+                    R.proposals += (int64_t)r.proposals; R.evaluated += (int64_t)r.evaluated;
+                    R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;
+                    R.round_launches++; R.scan_bytes += scan_bytes(c, r); R.evaluate_bytes += bulk_eval_bytes(c, r);
+                    if (p.log_energy) {   // exact energy of the current clustering (test/trace path only)
+                        recompute_statistics(c, constrained, qlevel, thr);
+                        c->energy_log.push_back(global_energy(c));
+                    }
+                    if (trace_on())
+                        fprintf(stderr, "[acvd trace] bulk  %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
+                                (long long)loops, nconv, r.active_tiles, r.boundary, r.evaluated, r.tests, r.proposals, r.mods,
+                                1e3 * r.ms_scan, 1e3 * r.ms_eval, 1e3 * r.ms_commit);
+                    if ((int64_t)r.mods <= early_items / p.early_stop_div) break;
+                }
+                timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
+            }
+        }
         launch_round(c, cfg, connexity, force_all, as_iso);
         force_all = 0;
         RoundResult r = finish_round(c);

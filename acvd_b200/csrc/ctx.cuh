@@ -41,6 +41,11 @@ struct acvd_ctx {
     DevBuf<unsigned char> tile_active;
     DevBuf<unsigned long long> round_scalars;   // [0] active tiles, [1] proposals of the previous round
     int plist_cur = 0;
+    // bulk (Lloyd-criterion) rounds
+    DevBuf<long long> isum;
+    DevBuf<double> bulk_cen;
+    DevBuf<int> leave_cnt, join_cnt;
+    double fx_scale = 0.0;
     DevBuf<double2> prop_e;
     DevBuf<unsigned> modbits;
     DevBuf<RoundCounters> ctr;

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
             basew = __shfl_sync(0xffffffffu, basew, 0);
             if (work) A.work[basew + __popc(mw & (lane_le >> 1))] = v;
         }
-        if (bnd && !dirty) {   // clusters unchanged since the last evaluation: the stored proposal is still exact
+        if (bnd && !dirty && !A.bulk) {   // clusters unchanged since the last evaluation: the stored proposal is still exact
             const int d = A.prop_dst[v];
             if (d >= 0) {
                 const unsigned long long key = A.prop_key[v];
@@ -421,6 +421,131 @@ __global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
         n_mods++;
     }
     warp_count_add(&A.ctr->mods, n_mods);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bulk rounds (Lloyd criterion) for the phases that the reference ends by "early convergence"
+// (Common/vtkUniformClustering.h:773-776) and whose energy is the centroid energy E = sum w |p - c|^2
+// (isotropic metric; QEM while unconstrained, vtkQEMetricForClustering.h:277-280).
+//
+// A move v: a -> b with |p_v - c_b|^2 < |p_v - c_a|^2 is a strictly improving candidate of the
+// reference's test (its delta-E is w [W_b/(W_b+w) d_b^2 - W_a/(W_a-w) d_a^2] < 0), and for fixed centroids
+// every such move lowers sum w |p - c|^2 independently of the others; recomputing the centroids lowers
+// it again.  So all of them commit in the same round, with no per-cluster exclusivity.  The moves the
+// reference accepts beyond this criterion (a thin band near the bisectors) are left to the exact rounds
+// that follow in the same phase.  Sums are kept in 64-bit fixed point while in bulk mode: integer atomics
+// commute, so the result does not depend on the order of the adds; exact double statistics are
+// recomputed from the clustering before the exact rounds resume.
+struct BulkArgs {
+    long long* isum;            // K x 4 fixed-point (S, W)
+    double* ccen;               // K x 3 centroids
+    int* leave_cnt;             // K: vertices that want to leave the cluster this round
+    int* join_cnt;              // K: vertices that joined the cluster this round
+    double scale;               // fixed-point scale (power of two)
+};
+
+__global__ void __launch_bounds__(kThreads) k_bulk_init(int K, int stride, const double* __restrict__ csum, BulkArgs B) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x) {
+        const double* s = csum + (int64_t)c * stride;
+#pragma unroll
+        for (int k = 0; k < 4; k++) B.isum[4 * (int64_t)c + k] = __double2ll_rn(s[k] * B.scale);
+        B.ccen[3 * c] = s[0] / s[3]; B.ccen[3 * c + 1] = s[1] / s[3]; B.ccen[3 * c + 2] = s[2] / s[3];
+        B.leave_cnt[c] = 0; B.join_cnt[c] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, BulkArgs B) {
+    const int K = A.K;
+    const int n_work = (int)A.ctr->evaluated;
+    unsigned n_tests = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
+        const int v = A.work[i];
+        const int a = A.cid[v];
+        const int beg = A.row_ptr[v], end = A.row_ptr[v + 1];
+        int best_b = -1;
+        if (a >= K) {
+            for (int e = beg; e < end && best_b < 0; e++) {
+                int b = A.cid[A.col[e]];
+                if (b < K) best_b = b;
+            }
+        } else {
+            const double px = A.xyz[3 * (int64_t)v], py = A.xyz[3 * (int64_t)v + 1], pz = A.xyz[3 * (int64_t)v + 2];
+            const bool blocked = A.csize[a] == 1;
+            double dx = px - B.ccen[3 * a], dy = py - B.ccen[3 * a + 1], dz = pz - B.ccen[3 * a + 2];
+            double best_d = dx * dx + dy * dy + dz * dz;
+            for (int e = beg; e < end; e++) {
+                int b = A.cid[A.col[e]];
+                if (b == a || b >= K) continue;
+                bool seen = false;
+                for (int e2 = beg; e2 < e; e2++) seen |= (A.cid[A.col[e2]] == b);
+                if (seen) continue;
+                n_tests++;
+                if (blocked) continue;
+                dx = px - B.ccen[3 * b]; dy = py - B.ccen[3 * b + 1]; dz = pz - B.ccen[3 * b + 2];
+                double d = dx * dx + dy * dy + dz * dz;
+                if (d < best_d) { best_d = d; best_b = b; }
+            }
+        }
+        A.prop_dst[v] = best_b;
+        if (best_b >= 0) {
+            if (a < K) atomicAdd(&B.leave_cnt[a], 1);
+            int slot = (int)atomicAdd(&A.ctr->proposals, 1ull);
+            A.plist[slot] = v;
+        }
+    }
+    warp_count_add(&A.ctr->tests, n_tests);
+}
+
+// Applies every proposal unless its source cluster would be emptied (then all of that cluster's leavers
+// wait: the decision depends only on totals, so it is deterministic).
+__global__ void __launch_bounds__(kThreads) k_bulk_commit(ReassignArgs A, BulkArgs B, int stride) {
+    const int K = A.K;
+    const int n_props = (int)A.ctr->proposals;
+    unsigned n_mods = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
+        const int v = A.plist[i];
+        const int d = A.prop_dst[v];
+        const int a = A.cid[v];
+        if (a < K && B.leave_cnt[a] >= A.csize[a]) continue;
+        const double* it = A.items + (int64_t)v * stride;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            long long f = __double2ll_rn(__ldg(it + k) * B.scale);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)d + k]), (unsigned long long)f);
+            if (a < K) atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)a + k]), (unsigned long long)(-f));
+        }
+        atomicAdd(&B.join_cnt[d], 1);
+        A.mod_round[d] = A.round;
+        if (a < K) A.mod_round[a] = A.round;
+        A.cid[v] = d;
+        n_mods++;
+    }
+    warp_count_add(&A.ctr->mods, n_mods);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bulk_refresh(int K, int* csize, BulkArgs B) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x) {
+        const int lv = B.leave_cnt[c], jn = B.join_cnt[c];
+        if ((lv | jn) == 0) continue;
+        const int sz = csize[c];
+        const int left = (lv < sz) ? lv : 0;
+        if (left | jn) {
+            csize[c] = sz - left + jn;
+            const double w = (double)B.isum[4 * (int64_t)c + 3];
+            B.ccen[3 * c] = (double)B.isum[4 * (int64_t)c] / w;
+            B.ccen[3 * c + 1] = (double)B.isum[4 * (int64_t)c + 1] / w;
+            B.ccen[3 * c + 2] = (double)B.isum[4 * (int64_t)c + 2] / w;
+        }
+        B.leave_cnt[c] = 0; B.join_cnt[c] = 0;
+    }
+}
+
+// per-vertex bound used to pick the fixed-point scale: max(|S_x|, |S_y|, |S_z|, W)
+__global__ void __launch_bounds__(kThreads) k_item_bound(int V, int stride, const double* __restrict__ items, double* out) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const double* it = items + (int64_t)v * stride;
+        out[v] = fmax(fmax(fabs(it[0]), fabs(it[1])), fmax(fabs(it[2]), fabs(it[3])));
+    }
 }
 
 }  // namespace acvd

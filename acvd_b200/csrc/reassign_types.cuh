@@ -42,6 +42,7 @@ struct ReassignArgs {
     RoundCounters* ctr;
     int round;
     int force_all;                      // SetAllClustersToModified (:717-722)
+    int bulk;                           // bulk (Lloyd-criterion) round: no stored proposals
     int connexity;
     EvalCfg cfg;
 };

@@ -102,6 +102,8 @@ typedef struct acvd_params {
     int32_t log_energy;           /* keep a per-round global-energy trace (energy.txt analogue) */
     int32_t rounds_per_sync;      /* rounds between host polls of the counters, <=0 -> 1 */
     double sv_threshold;          /* <=0 -> 1e-3 (Common/vtkQuadricTools.h:36) */
+    int32_t bulk_rounds;          /* early phases: 0 -> bulk Lloyd-criterion rounds on (cap 1000), <0 -> off, >0 -> cap */
+    int32_t reserved;
 } acvd_params;
 
 typedef struct acvd_report {
@@ -123,6 +125,7 @@ typedef struct acvd_report {
     int64_t evaluated;       /* work-list vertices evaluated */
     double ms_device;        /* CUDA-event time of the whole call on the context's stream */
     int64_t kernel_launches; /* kernels this call launched */
+    int64_t bulk_rounds;     /* rounds run with the bulk (Lloyd-criterion) commit */
 } acvd_report;
 
 /* MinimizeEnergy (Common/vtkUniformClustering.h:725-830) with ProcessOneLoop (:833-995) replaced by

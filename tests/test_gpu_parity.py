@@ -210,6 +210,33 @@ def test_energy_monotone_per_phase(oracle_mod, gpu_ctx_factory, torus):
         e_prev = e
 
 
+@pytest.mark.parametrize("metric,uncon", [("iso", 0), ("qem", 1)])
+def test_bulk_rounds_energy_monotone_and_same_fixed_point(oracle_mod, gpu_ctx_factory, torus, metric, uncon):
+    """Bulk (Lloyd-criterion) rounds only ever lower the energy, and with or without them the
+    minimisation ends in a state the sequential oracle cannot improve, at the same energy within 1 %."""
+    p, t, ind = torus
+    K = 500
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K, 1.5, ind)
+    cl0 = o.initial_sampling()
+    res = {}
+    for bulk in (0, -1):
+        g.set_clustering(cl0)
+        rep = g.minimize(unconstrained_init=uncon, log_energy=1, bulk_rounds=bulk)
+        log = g.energy_log()
+        nb = rep["bulk_rounds"]
+        assert (nb > 0) == (bulk == 0)
+        if nb:
+            e = log[:nb]
+            assert np.all(np.diff(e) <= 1e-12 * np.abs(e[:-1]))
+        res[bulk] = rep["energy"]
+        assert g.clean_clustering() == 0
+    assert abs(res[0] - res[-1]) <= 0.01 * abs(res[-1])
+    o.set_params(unconstrained_init=uncon)
+    o.minimize()
+    o.recompute_statistics()
+    assert abs(res[0] - o.global_energy()) <= 0.01 * abs(o.global_energy())
+
+
 def test_round_trip_determinism(gpu_ctx_factory, sphere):
     p, t = sphere
     res = []
