@@ -1,4 +1,4 @@
-"""In-tree build of the CUDA library (sm_100a) and, for tests, of the CPU oracle.
+"""In-tree build of the CUDA library (sm_100a).
 
 ``python -m acvd_b200.build`` compiles ``acvd_b200/libacvd_b200.so`` with nvcc; nvcc cross-compiles
 without a GPU, and the built ``.so`` travels to the GPU box with the repository snapshot.
@@ -42,7 +42,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB]
     cmd += [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd += ["-lnccl"]
+    cmd += ["-ldl"]   # NCCL is resolved with dlopen at run time (csrc/nccl_dyn.hpp)
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

@@ -1,0 +1,288 @@
+"""CPU tests (no GPU): pins for the oracle (SURVEY §8c known-answer tests), mesh generators, and the
+C ABI library surface.  The reference ships no golden vectors for this path, so these pins are ours;
+the committed fixtures under tests/golden/ freeze the oracle's outputs for regression."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from acvd_b200 import meshgen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ---------------------------------------------------------------- §8c (5): std::mt19937 seed 0
+def test_mt19937_first_outputs(oracle_mod):
+    assert list(oracle_mod.mt19937_first(3)) == [2357136044, 2546248239, 3071714933]
+
+
+# ---------------------------------------------------------------- §8c (1): quadrics / representative point
+def test_triangle_quadric_known_answer(oracle_mod):
+    c = 2.5
+    q = oracle_mod.triangle_quadric((0, 0, c), (1, 0, c), (0, 1, c))
+    # n = (0,0,1) (|n| = 2 * area = 1), d = -c  ->  Q9 = [0,0,0,0,0,0,0,1,-c], q33 = c^2
+    assert np.allclose(q, [0, 0, 0, 0, 0, 0, 0, 1, -c, c * c], atol=1e-15)
+
+
+def _plane_quadric(normal, d):
+    v = np.append(np.asarray(normal, float), d)
+    m = np.outer(v, v)
+    return np.array([m[0, 0], m[0, 1], m[0, 2], m[0, 3], m[1, 1], m[1, 2], m[1, 3], m[2, 2], m[2, 3]])
+
+
+def test_representative_point_three_planes(oracle_mod):
+    q = _plane_quadric((1, 0, 0), -3) + _plane_quadric((0, 1, 0), 1) + _plane_quadric((0, 0, 1), -2)
+    p, rd = oracle_mod.representative_point(q, [0.3, 0.2, 0.1])
+    assert rd == 0 and np.allclose(p, [3, -1, 2], atol=1e-12)
+
+
+def test_representative_point_rank_deficient(oracle_mod):
+    # one plane: deficiency 2, the point only moves along the normal
+    q = _plane_quadric((0, 0, 1), -2)
+    p, rd = oracle_mod.representative_point(q, [0.5, 0.25, 0.0])
+    assert rd == 2 and np.allclose(p, [0.5, 0.25, 2.0], atol=1e-12)
+    # two planes: deficiency 1, the free direction (y) is untouched
+    q = _plane_quadric((1, 0, 0), -3) + _plane_quadric((0, 0, 1), -2)
+    p, rd = oracle_mod.representative_point(q, [0.0, 7.0, 0.0])
+    assert rd == 1 and np.allclose(p, [3, 7, 2], atol=1e-12)
+
+
+def test_representative_point_level_and_threshold(oracle_mod):
+    q = 100 * _plane_quadric((1, 0, 0), -3) + _plane_quadric((0, 1, 0), 1) + 1e-5 * _plane_quadric((0, 0, 1), -2)
+    # singular values 100, 1, 1e-5: the last one is below 1e-3 of the largest -> dropped
+    p, rd = oracle_mod.representative_point(q, [0, 0, 0])
+    assert rd == 1 and np.allclose(p, [3, -1, 0], atol=1e-9)
+    # MaxNumberOfUsedSingularValues = 1 keeps only the largest (vtkQuadricTools.cxx:130-147)
+    p, rd = oracle_mod.representative_point(q, [0, 0, 0], level=1)
+    assert rd == 2 and np.allclose(p, [3, 0, 0], atol=1e-9)
+    # an all-zero quadric is fully deficient and leaves the point alone
+    p, rd = oracle_mod.representative_point(np.zeros(9), [1, 2, 3])
+    assert rd == 3 and np.allclose(p, [1, 2, 3])
+
+
+# ---------------------------------------------------------------- §8c (3): icosphere counts and edge order
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_icosphere_counts_and_first_seen_edges(oracle_mod, n):
+    p, t = meshgen.geodesic_icosphere(n)
+    V = 10 * n * n + 2
+    o = oracle_mod.Oracle(p, t)
+    assert p.shape[0] == V and t.shape[0] == 2 * V - 4 and o.E == 3 * V - 6
+    a, b = o.edges()
+    # edge ids are first-seen order over the faces (vtkSurfaceBase.cxx:1446-1451)
+    seen, order = set(), []
+    for f in t:
+        for x, y in ((f[0], f[1]), (f[1], f[2]), (f[2], f[0])):
+            k = (min(x, y), max(x, y))
+            if k not in seen:
+                seen.add(k)
+                order.append((x, y))
+    assert [(int(x), int(y)) for x, y in zip(a, b)] == [(int(x), int(y)) for x, y in order]
+    # vertex areas sum to the mesh area
+    tri = p[t].astype(np.float64)
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1).sum()
+    assert abs(o.vertex_areas().sum() - area) < 1e-12 * area
+
+
+def test_ring_order_follows_edge_creation(oracle_mod):
+    p, t = meshgen.geodesic_icosphere(2)
+    o = oracle_mod.Oracle(p, t)
+    a, b = o.edges()
+    rp, col = o.csr()
+    for v in range(p.shape[0]):
+        expect = [int(b[e]) if a[e] == v else int(a[e]) for e in range(o.E) if a[e] == v or b[e] == v]
+        assert list(col[rp[v]:rp[v + 1]]) == expect
+
+
+# ---------------------------------------------------------------- §8c (2): energy identity
+def test_iso_energy_identity(oracle_mod):
+    p, t = meshgen.geodesic_icosphere(8)
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric("iso")
+    o.set_num_clusters(20)
+    o.initial_sampling()
+    o.fill_holes()                       # the sampling may leave NULL (id K) vertices
+    cl = o.clustering()
+    o.recompute_statistics()
+    sums, cen, en, sz = o.cluster_stats()
+    it = o.items()
+    w = it[:, 3]
+    assert np.allclose(en, -(sums[:, :3] ** 2).sum(axis=1) / sums[:, 3], rtol=1e-14)
+    true = oracle_mod.true_energy(p, w, cl, cen)
+    const = float(np.sum(w * (p.astype(np.float64) ** 2).sum(axis=1)))
+    assert abs(true - (const + o.global_energy())) < 1e-12 * const
+    assert np.array_equal(sz, np.bincount(cl, minlength=20))
+
+
+# ---------------------------------------------------------------- §8c (4): invariants of MinimizeEnergy
+@pytest.mark.parametrize("metric,uncon", [("iso", 0), ("qem", 1), ("qem", 0), ("anisoq", 0), ("aniso", 0)])
+def test_minimize_invariants(oracle_mod, metric, uncon):
+    p, t = meshgen.geodesic_icosphere(12)
+    V, K = p.shape[0], 40
+    rng = np.random.default_rng(1)
+    pd = None
+    if metric.startswith("aniso"):
+        # tangent-ish principal directions scaled by sqrt(|kappa|) = 1 on the unit sphere
+        n = p.astype(np.float64)
+        e1 = np.cross(n, [0, 0, 1.0]) + 1e-3
+        e1 /= np.linalg.norm(e1, axis=1, keepdims=True)
+        e2 = np.cross(n, e1)
+        pd = np.concatenate([e1, e2], axis=1).astype(np.float32)
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric(metric, 0.0, None, pd)
+    o.set_num_clusters(K)
+    o.set_params(unconstrained_init=uncon, log_energy=1)
+    o.initial_sampling()
+    o.minimize()
+    cl = o.clustering()
+    assert cl.min() >= 0 and cl.max() < K
+    sz = np.bincount(cl, minlength=K)
+    assert sz.min() >= 1 and sz.sum() == V
+    assert o.clean_clustering() == 0                       # every cluster connected
+    log = o.energy_log()
+    if metric == "iso":
+        assert np.all(np.diff(log) <= 1e-12)               # energy non-increasing loop to loop
+    # a further loop on the converged state changes nothing
+    o.set_connexity(1)
+    o.prime()
+    assert o.process_one_loop() == 0
+    rep = o.report()
+    assert rep["loops"] == len(log) + 1 and rep["convergences"] >= 1 and rep["tests"] > 0
+
+
+def test_threaded_restatement_reaches_same_quality(oracle_mod):
+    p, t = meshgen.geodesic_icosphere(24)
+    K = 120
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric("qem")
+    o.set_num_clusters(K)
+    cl0 = o.initial_sampling().copy()
+    o.set_params(unconstrained_init=1)
+    o.minimize()
+    o.recompute_statistics()
+    e_seq = o.global_energy()
+    o2 = oracle_mod.Oracle(p, t)
+    o2.build_metric("qem")
+    o2.set_num_clusters(K)
+    o2.set_clustering(cl0)
+    o2.set_params(unconstrained_init=1)
+    o2.minimize_threaded(3)
+    o2.recompute_statistics()
+    cl = o2.clustering()
+    assert cl.min() >= 0 and cl.max() < K and np.bincount(cl, minlength=K).min() >= 1
+    assert o2.clean_clustering() == 0
+    assert abs(o2.global_energy() - e_seq) <= 0.01 * abs(e_seq)
+
+
+def test_connexity_predicate(oracle_mod):
+    # a strip of a torus grid: removing the middle vertex of a 1-wide bridge disconnects its ring
+    p, t = meshgen.torus_grid(12, 8)
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric("iso")
+    o.set_num_clusters(2)
+    nv = 8
+    cl = np.ones(p.shape[0], dtype=np.int32)
+    bridge = [3 * nv + 2, 4 * nv + 2, 5 * nv + 2]          # three consecutive vertices along the major circle
+    cl[bridge] = 0
+    o.set_clustering(cl)
+    o.set_connexity(1)
+    assert o.connexity_problem(bridge[1], 0) == 1          # middle: its two same-cluster neighbours are not adjacent
+    assert o.connexity_problem(bridge[0], 0) == 0          # end: one same-cluster neighbour
+    o.set_connexity(0)
+    assert o.connexity_problem(bridge[1], 0) == 0
+
+
+def test_clean_clustering_keeps_largest_component_and_item0_quirk(oracle_mod):
+    p, t = meshgen.torus_grid(20, 10)
+    nv = 10
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric("iso")
+    o.set_num_clusters(2)
+    cl = np.ones(p.shape[0], dtype=np.int32)
+    big = [5 * nv + j for j in range(4)] + [6 * nv + j for j in range(4)]
+    small = [12 * nv + 5, 12 * nv + 6]
+    cl[big] = 0
+    cl[small] = 0
+    o.set_clustering(cl)
+    assert o.clean_clustering() == 1
+    out = o.clustering()
+    assert all(out[v] == 0 for v in big) and all(out[v] == 2 for v in small)   # small component -> NULL id K
+    o.fill_holes()
+    assert o.clustering().max() == 1
+    # quirk (vtkUniformClustering.h:463-467): the component discovered at item 0 is never recorded
+    cl = np.ones(p.shape[0], dtype=np.int32)
+    cl[0] = 0
+    cl[big] = 0
+    o.set_clustering(cl)
+    assert o.clean_clustering() == 0
+    assert o.clustering()[0] == 0
+
+
+# ---------------------------------------------------------------- golden fixtures (oracle regression pins)
+def _golden_case():
+    p, t = meshgen.geodesic_icosphere(6)       # V = 362
+    return p, t, 12
+
+
+def test_golden_fixture_matches(oracle_mod):
+    path = os.path.join(GOLD, "oracle_ico6_k12.json")
+    gold = json.load(open(path))
+    p, t, K = _golden_case()
+    for metric, uncon in (("iso", 0), ("qem", 1)):
+        o = oracle_mod.Oracle(p, t)
+        o.build_metric(metric)
+        o.set_num_clusters(K)
+        o.set_params(unconstrained_init=uncon)
+        cl0 = o.initial_sampling().copy()
+        o.minimize()
+        o.recompute_statistics()
+        g = gold[metric]
+        assert cl0.tolist() == g["initial_sampling"]
+        assert o.clustering().tolist() == g["clustering"]
+        assert abs(o.global_energy() - g["energy"]) <= 1e-12 * abs(g["energy"])
+        assert o.dual_triangles().tolist() == g["dual_triangles"]
+        assert o.report()["loops"] == g["loops"]
+
+
+# ---------------------------------------------------------------- C ABI surface (no compute without a GPU)
+def test_capi_exports_every_declared_symbol(capi_mod):
+    hdr = open(os.path.join(ROOT, "include", "acvd_b200.h")).read()
+    declared = set(re.findall(r"\b(acvd_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"acvd_ctx", "acvd_params", "acvd_report"}
+    lib = ctypes.CDLL(capi_mod.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    bound = {name for name, _, _ in capi_mod.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    assert lib.acvd_abi_version() == 1
+    assert [lib.acvd_payload_size(m) for m in range(4)] == [4, 13, 13, 22]
+
+
+def test_capi_struct_layout_matches_header(capi_mod):
+    # field order of the ctypes mirrors == declaration order in the header
+    hdr = open(os.path.join(ROOT, "include", "acvd_b200.h")).read()
+    for cname, cls in (("acvd_params", capi_mod.Params), ("acvd_report", capi_mod.Report)):
+        body = re.search(r"typedef struct " + cname + r" \{(.*?)\} " + cname + ";", hdr, re.S).group(1)
+        fields = re.findall(r"^\s*(?:int32_t|int64_t|double)\s+([a-z_0-9]+);", body, re.M)
+        assert fields == [f for f, _ in cls._fields_]
+
+
+def test_product_fails_loudly_without_gpu(capi_mod):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi_mod.AcvdError) as e:
+        capi_mod.Context(0)
+    assert e.value.code == -2 and "no CPU path" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    # the oracle is test infrastructure: nothing under acvd_b200/ may reference it
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "acvd_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp", ".cxx")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower().replace("# oracle", ""), os.path.join(dirpath, f)
