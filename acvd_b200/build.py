@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]
-SOURCES = ["acvd_capi.cu", "acvd_dist.cu"]
+SOURCES = ["acvd_capi.cu"]
 
 
 def _newest_source_mtime() -> float:

@@ -107,6 +107,8 @@ extern "C" int acvd_destroy(acvd_ctx* c) {
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    if (c->comm && nccl().load()) nccl().CommDestroy(c->comm);
     delete c;
     return ACVD_OK;
 }
@@ -590,7 +592,7 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
     ACVD_LAUNCH_CHECK();
     const int n_tiles = (c->V + 31) / 32;
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
+    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
                                                                 c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
     ACVD_LAUNCH_CHECK();
     k_scan<<<gs, kThreads, 0, c->stream>>>(A);
@@ -681,13 +683,13 @@ static void launch_bulk_round(acvd_ctx* c, int force_all) {
     const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
     const int n_tiles = (c->V + 31) / 32;
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
+    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
                                                                 c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
     ACVD_LAUNCH_CHECK();
     k_scan<<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B);
+    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 1);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     k_bulk_commit<<<gc, kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric));
@@ -711,6 +713,8 @@ static RoundResult finish_round(acvd_ctx* c) {
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
     return r;
 }
+
+#include "dist.cuh"
 
 static double global_energy(acvd_ctx* c) {
     // ComputeGlobalEnergy sums in long double on the host (:1319-1346); K doubles is a small copy
@@ -828,9 +832,10 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                 bulk_init(c);
                 int fa = 1;
                 for (int b = 0; b < bulk_cap && loops < p.max_loops; b++) {
-                    launch_bulk_round(c, fa);
+                    RoundResult r;
+                    if (c->world > 1) r = run_bulk_round_dist(c, fa);
+                    else { launch_bulk_round(c, fa); r = finish_round(c); }
                     fa = 0;
-                    RoundResult r = finish_round(c);
                     loops++;
                     R.rounds++; R.bulk_rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods;
                     R.proposals += (int64_t)r.proposals; R.evaluated += (int64_t)r.evaluated;
@@ -844,14 +849,15 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                         fprintf(stderr, "[acvd trace] bulk  %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
                                 (long long)loops, nconv, r.active_tiles, r.boundary, r.evaluated, r.tests, r.proposals, r.mods,
                                 1e3 * r.ms_scan, 1e3 * r.ms_eval, 1e3 * r.ms_commit);
-                    if ((int64_t)r.mods <= early_items / p.early_stop_div) break;
+                    if ((int64_t)r.proposals <= early_items / p.early_stop_div) break;
                 }
                 timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
             }
         }
-        launch_round(c, cfg, connexity, force_all, as_iso);
+        RoundResult r;
+        if (c->world > 1) r = run_round_dist(c, cfg, connexity, force_all, as_iso);
+        else { launch_round(c, cfg, connexity, force_all, as_iso); r = finish_round(c); }
         force_all = 0;
-        RoundResult r = finish_round(c);
         loops++;
         R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;
         R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;

@@ -8,9 +8,17 @@
 
 #include "../../include/acvd_b200.h"
 #include "common.cuh"
+#include "nccl_dyn.hpp"
 #include "reassign_types.cuh"
 
 using namespace acvd;
+
+struct NcclError { ncclResult_t code; const char* what; };
+#define ACVD_NCCL(expr)                                              \
+    do {                                                             \
+        ncclResult_t _r = (expr);                                    \
+        if (_r != ncclSuccess) throw NcclError{_r, #expr};           \
+    } while (0)
 
 struct acvd_ctx {
     int device = 0;
@@ -63,6 +71,9 @@ struct acvd_ctx {
     // multi-GPU (acvd_dist.cu)
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    DevBuf<char> moves_local, moves_all;      // move records of this rank / of all ranks
+    DevBuf<unsigned long long> hdr_local, hdr_all, n_moves;
+    unsigned long long* h_hdr = nullptr;      // pinned: world x 8
 };
 
 inline std::string g_create_error;

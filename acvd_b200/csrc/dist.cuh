@@ -1,0 +1,201 @@
+// Multi-GPU plumbing and round drivers (included by acvd_capi.cu so the kernels are shared).
+// One process per GPU; NCCL over NVLink 5 / NVSwitch, resolved at run time (nccl_dyn.hpp).
+#pragma once
+#include <cstring>
+
+#include "ctx.cuh"
+#include "nccl_dyn.hpp"
+
+static_assert(sizeof(ncclUniqueId) <= ACVD_NCCL_ID_BYTES, "ACVD_NCCL_ID_BYTES too small");
+
+extern "C" int acvd_dist_unique_id(void* id_out) {
+    if (!id_out) return ACVD_EINVAL;
+    if (!nccl().load()) return ACVD_ENCCL;
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return ACVD_ENCCL;
+    memset(id_out, 0, ACVD_NCCL_ID_BYTES);
+    memcpy(id_out, &id, sizeof id);
+    return ACVD_OK;
+}
+
+extern "C" int acvd_dist_init(acvd_ctx* c, int rank, int world, const void* id_bytes) {
+    if (!c || !id_bytes || world < 1 || rank < 0 || rank >= world) return fail(c, ACVD_EINVAL, "acvd_dist_init: bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, ACVD_ECUDA, "acvd_dist_init: cudaSetDevice failed");
+    if (!nccl().load()) return fail(c, ACVD_ENCCL, "acvd_dist_init: " + nccl().error);
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    if (c->comm) { nccl().CommDestroy(c->comm); c->comm = nullptr; }
+    ncclResult_t r = nccl().CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) return fail(c, ACVD_ENCCL, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
+    c->rank = rank;
+    c->world = world;
+    if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    if (cudaMallocHost(&c->h_hdr, (size_t)world * 8 * sizeof(unsigned long long)) != cudaSuccess)
+        return fail(c, ACVD_ECUDA, "acvd_dist_init: pinned allocation failed");
+    try {
+        c->hdr_local.alloc(8); c->hdr_all.alloc((size_t)world * 8); c->n_moves.alloc(1);
+    } catch (const CudaError&) { return fail(c, ACVD_ECUDA, "acvd_dist_init: device allocation failed"); }
+    return ACVD_OK;
+}
+
+// tile range owned by this rank
+static void dist_tile_range(const acvd_ctx* c, int& t0, int& t1) {
+    const int64_t n_tiles = ((int64_t)c->V + 31) / 32;
+    t0 = (int)(n_tiles * c->rank / c->world);
+    t1 = (int)(n_tiles * (c->rank + 1) / c->world);
+}
+
+// All-gather of variable-length records: the 64-byte headers first (they carry the local count and the
+// round's counters, so this is also the one host synchronisation of the round), then one broadcast per
+// rank, grouped.  Returns the total record count; RoundResult gets the counters summed over ranks.
+static int64_t dist_gather_moves(acvd_ctx* c, size_t rec_bytes, RoundResult& r) {
+    const int W = c->world;
+    k_pack_header<<<1, 32, 0, c->stream>>>(c->ctr.p, c->round_scalars.p, c->n_moves.p, c->hdr_local.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_NCCL(nccl().AllGather(c->hdr_local.p, c->hdr_all.p, 8, ncclUint64, c->comm, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_hdr, c->hdr_all.p, (size_t)W * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t total = 0;
+    r.proposals = r.tests = r.evaluated = r.boundary = r.active_tiles = 0;
+    for (int i = 0; i < W; i++) {
+        const unsigned long long* h = c->h_hdr + 8 * i;
+        total += (int64_t)h[0];
+        r.proposals += h[1]; r.tests += h[2]; r.evaluated += h[3]; r.boundary += h[4]; r.active_tiles += h[5];
+    }
+    if (total == 0) return 0;
+    c->moves_all.alloc((size_t)total * rec_bytes);
+    ACVD_NCCL(nccl().GroupStart());
+    int64_t off = 0;
+    for (int i = 0; i < W; i++) {
+        const int64_t n = (int64_t)c->h_hdr[8 * i];
+        if (n > 0)
+            ACVD_NCCL(nccl().Broadcast(c->moves_local.p, c->moves_all.p + off * rec_bytes, (size_t)n * rec_bytes, ncclChar, i, c->comm, c->stream));
+        off += n;
+    }
+    ACVD_NCCL(nccl().GroupEnd());
+    return total;
+}
+
+// exact round on `world` GPUs
+static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso) {
+    if (force_all) ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p + 1, 0, sizeof(unsigned long long), c->stream));
+    else ACVD_CUDA(cudaMemcpyAsync(c->round_scalars.p + 1, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    c->plist_cur ^= 1;
+    ReassignArgs A = make_args(c, cfg, connexity, force_all);
+    ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, sizeof(unsigned long long), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->n_moves.p, 0, sizeof(unsigned long long), c->stream));
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
+    ACVD_LAUNCH_CHECK();
+    int t0, t1;
+    dist_tile_range(c, t0, t1);
+    const int own_tiles = t1 - t0;
+    const int gs = grid_for((int64_t)own_tiles * 32, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                  c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+    ACVD_LAUNCH_CHECK();
+    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    ACVD_LAUNCH_CHECK();
+    if (!force_all) {
+        k_carry<<<gc, kThreads, 0, c->stream>>>(A);
+        ACVD_LAUNCH_CHECK();
+    }
+    ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    switch (c->metric) {
+        case M_ISO: k_evaluate<M_ISO, 4><<<ge, kThreads, 0, c->stream>>>(A); break;
+        case M_QEM:
+            if (as_iso) k_evaluate<M_ISO, 14><<<ge, kThreads, 0, c->stream>>>(A);
+            else k_evaluate<M_QEM, 14><<<ge, kThreads, 0, c->stream>>>(A);
+            break;
+        case M_ANISO: k_evaluate<M_ANISO, 14><<<ge, kThreads, 0, c->stream>>>(A); break;
+        default: k_evaluate<M_ANISOQ, 22><<<ge, kThreads, 0, c->stream>>>(A); break;
+    }
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    // 1. conflict resolution across ranks: the minimum key per cluster
+    ACVD_NCCL(nccl().AllReduce(c->best.p, c->best.p, (size_t)c->K, ncclUint64, ncclMin, c->comm, c->stream));
+    // 2. winners of this rank -> all ranks
+    c->moves_local.alloc(((size_t)c->K / 2 + 64) * sizeof(MoveRec));
+    k_select_winners<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<MoveRec*>(c->moves_local.p), c->n_moves.p);
+    ACVD_LAUNCH_CHECK();
+    RoundResult r;
+    memset(&r, 0, sizeof r);
+    const int64_t total = dist_gather_moves(c, sizeof(MoveRec), r);
+    if (total > 0) {
+        const MoveRec* mv = reinterpret_cast<const MoveRec*>(c->moves_all.p);
+        switch (c->metric) {
+            case M_ISO: k_apply_moves<M_ISO, M_ISO><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total); break;
+            case M_QEM:
+                if (as_iso) k_apply_moves<M_ISO, M_QEM><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total);
+                else k_apply_moves<M_QEM, M_QEM><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total);
+                break;
+            case M_ANISO: k_apply_moves<M_ANISO, M_ANISO><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total); break;
+            default: k_apply_moves<M_ANISOQ, M_ANISOQ><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total); break;
+        }
+        ACVD_LAUNCH_CHECK();
+    }
+    ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    ACVD_CUDA(cudaEventSynchronize(c->ev[2]));
+    r.mods = (unsigned long long)total;
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, c->ev[0], c->ev[3]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
+    c->round++;
+    return r;
+}
+
+// bulk (Lloyd-criterion) round on `world` GPUs: local scan + evaluate, all-gather of the (vertex, destination)
+// pairs, then every rank counts leavers and applies all moves (integer sums: order-independent)
+static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all) {
+    EvalCfg cfg = make_cfg(0, 0, 0);
+    c->plist_cur = 0;
+    ReassignArgs A = make_args(c, cfg, 0, force_all);
+    A.bulk = 1;
+    BulkArgs B = make_bulk_args(c);
+    ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
+    ACVD_LAUNCH_CHECK();
+    int t0, t1;
+    dist_tile_range(c, t0, t1);
+    const int own_tiles = t1 - t0;
+    const int gs = grid_for((int64_t)own_tiles * 32, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                  c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+    ACVD_LAUNCH_CHECK();
+    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 0);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    c->moves_local.alloc(((size_t)(own_tiles) * 32 + 64) * sizeof(int2));
+    k_pack_bulk_moves<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<int2*>(c->moves_local.p));
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(c->n_moves.p, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    RoundResult r;
+    memset(&r, 0, sizeof r);
+    const int64_t total = dist_gather_moves(c, sizeof(int2), r);
+    if (total > 0) {
+        const int2* mv = reinterpret_cast<const int2*>(c->moves_all.p);
+        k_bulk_count<<<gc, kThreads, 0, c->stream>>>(c->K, c->cid.p, mv, (int)total, c->leave_cnt.p);
+        ACVD_LAUNCH_CHECK();
+        k_bulk_apply<<<gc, kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric), mv, (int)total);
+        ACVD_LAUNCH_CHECK();
+        k_bulk_refresh<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->csize.p, B);
+        ACVD_LAUNCH_CHECK();
+    }
+    ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    r.mods = c->h_ctr->mods;   // accepted moves (identical on every rank)
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, c->ev[0], c->ev[3]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
+    c->round++;
+    c->stats_valid = false;
+    return r;
+}

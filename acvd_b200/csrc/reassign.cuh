@@ -103,11 +103,12 @@ constexpr int kSigSlots = 8;     // cluster ids remembered per 32-vertex tile (3
 // tile -- was modified in the previous round: a vertex's boundary/dirty state and proposal depend on
 // those clusters only, and any move that changes the tile's signature modifies a cluster already in it.
 // Reads 32 B per tile instead of ~1 KB of CSR: tail rounds cost microseconds, not a full sweep.
-__global__ void __launch_bounds__(kThreads) k_tile_filter(int n_tiles, int K, int force_all, const int4* __restrict__ sig,
+// [tile_begin, n_tiles) is the tile range owned by this rank (the whole mesh on one GPU).
+__global__ void __launch_bounds__(kThreads) k_tile_filter(int tile_begin, int n_tiles, int K, int force_all, const int4* __restrict__ sig,
                                                           const unsigned* __restrict__ modbits, unsigned char* tile_active,
                                                           int* active_tiles, unsigned long long* n_active) {
     const int lane = threadIdx.x & 31;
-    for (int t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; t0 < n_tiles; t0 += gridDim.x * blockDim.x) {
+    for (int t0 = tile_begin + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); t0 < n_tiles; t0 += gridDim.x * blockDim.x) {
         const int t = t0 + lane;
         bool act = false;
         if (t < n_tiles) {
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_init(int K, int stride, const
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, BulkArgs B) {
+__global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, BulkArgs B, int count_leave) {
     const int K = A.K;
     const int n_work = (int)A.ctr->evaluated;
     unsigned n_tests = 0;
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, Bulk
         }
         A.prop_dst[v] = best_b;
         if (best_b >= 0) {
-            if (a < K) atomicAdd(&B.leave_cnt[a], 1);
+            if (a < K && count_leave) atomicAdd(&B.leave_cnt[a], 1);
             int slot = (int)atomicAdd(&A.ctr->proposals, 1ull);
             A.plist[slot] = v;
         }
@@ -545,6 +546,115 @@ __global__ void __launch_bounds__(kThreads) k_item_bound(int V, int stride, cons
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         const double* it = items + (int64_t)v * stride;
         out[v] = fmax(fmax(fabs(it[0]), fabs(it[1])), fmax(fabs(it[2]), fabs(it[3])));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-GPU rounds (one process per GPU).  Every rank holds the whole clustering state (cluster ids,
+// per-cluster sums/energies/sizes) and owns a contiguous range of 32-vertex tiles: it scans and evaluates
+// only its own range.  Per round two exchanges go over NCCL (NVLink 5 / NVSwitch):
+//   1. conflict resolution: min-allreduce of the per-cluster priority keys;
+//   2. the winners (vertex, destination, the two new energies) are all-gathered -- this *is* the halo
+//      exchange of boundary cluster ids, in delta form -- and every rank applies every move to its replica.
+// Because all ranks apply the same moves with the same arithmetic, the replicas stay bit-identical and
+// the result is identical to the single-GPU run.
+struct MoveRec { int v, d; double ea, eb; };
+
+__global__ void __launch_bounds__(kThreads) k_select_winners(ReassignArgs A, MoveRec* moves, unsigned long long* n_moves) {
+    const int K = A.K;
+    const int n_props = (int)A.ctr->proposals;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
+        const int v = A.plist[i];
+        const int d = A.prop_dst[v];
+        if (d < 0) continue;
+        const unsigned long long key = A.prop_key[v];
+        const int a = A.cid[v];
+        if ((A.best[d] == key) && (a >= K || A.best[a] == key)) {
+            const double2 pe = A.prop_e[v];
+            const int slot = (int)atomicAdd(n_moves, 1ull);
+            moves[slot] = MoveRec{v, d, pe.x, pe.y};
+        }
+    }
+}
+
+template <int EM, int UM>
+__global__ void __launch_bounds__(kThreads) k_apply_moves(ReassignArgs A, const MoveRec* __restrict__ moves, int n_moves) {
+    constexpr int NU = MetricTraits<UM>::NPAD;
+    const int K = A.K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_moves; i += gridDim.x * blockDim.x) {
+        const MoveRec m = moves[i];
+        const int v = m.v, d = m.d;
+        const int a = A.cid[v];
+        double it[NU], s[NU];
+        load_row_ro<NU>(A.items + (int64_t)v * NU, it);
+        load_row<NU>(A.csum + (int64_t)d * NU, s);
+#pragma unroll
+        for (int k = 0; k < NU; k++) s[k] += it[k];
+        store_row<NU>(A.csum + (int64_t)d * NU, s);
+        if (a >= K) {
+            double anchor_pt[3];
+            A.cenergy[d] = cluster_energy<EM>(s, A.cfg, nullptr, anchor_point<EM>(A, d, anchor_pt));
+        } else {
+            A.cenergy[d] = m.eb;
+            load_row<NU>(A.csum + (int64_t)a * NU, s);
+#pragma unroll
+            for (int k = 0; k < NU; k++) s[k] -= it[k];
+            store_row<NU>(A.csum + (int64_t)a * NU, s);
+            A.cenergy[a] = m.ea;
+            A.csize[a] -= 1;
+            A.mod_round[a] = A.round;
+        }
+        A.csize[d] += 1;
+        A.mod_round[d] = A.round;
+        A.cid[v] = d;
+        A.prop_dst[v] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_pack_bulk_moves(ReassignArgs A, int2* moves) {
+    const int n = (int)A.ctr->proposals;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = A.plist[i];
+        moves[i] = make_int2(v, A.prop_dst[v]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bulk_count(int K, const int* __restrict__ cid, const int2* __restrict__ moves, int n, int* leave_cnt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int a = cid[moves[i].x];
+        if (a < K) atomicAdd(&leave_cnt[a], 1);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bulk_apply(ReassignArgs A, BulkArgs B, int stride, const int2* __restrict__ moves, int n) {
+    const int K = A.K;
+    unsigned n_mods = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = moves[i].x, d = moves[i].y;
+        const int a = A.cid[v];
+        if (a < K && B.leave_cnt[a] >= A.csize[a]) continue;
+        const double* it = A.items + (int64_t)v * stride;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            long long f = __double2ll_rn(__ldg(it + k) * B.scale);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)d + k]), (unsigned long long)f);
+            if (a < K) atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)a + k]), (unsigned long long)(-f));
+        }
+        atomicAdd(&B.join_cnt[d], 1);
+        A.mod_round[d] = A.round;
+        if (a < K) A.mod_round[a] = A.round;
+        A.cid[v] = d;
+        n_mods++;
+    }
+    warp_count_add(&A.ctr->mods, n_mods);
+}
+
+// header exchanged with the moves: [0] local move count, [1] proposals, [2] tests, [3] evaluated, [4] boundary, [5] active tiles
+__global__ void k_pack_header(const RoundCounters* ctr, const unsigned long long* round_scalars, const unsigned long long* n_moves,
+                              unsigned long long* hdr) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        hdr[0] = *n_moves; hdr[1] = ctr->proposals; hdr[2] = ctr->tests; hdr[3] = ctr->evaluated; hdr[4] = ctr->boundary;
+        hdr[5] = round_scalars[0]; hdr[6] = 0; hdr[7] = 0;
     }
 }
 
