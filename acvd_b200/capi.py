@@ -29,7 +29,7 @@ class Params(C.Structure):
         ("unconstrained_init", C.c_int32), ("quadrics_level", C.c_int32), ("connexity", C.c_int32),
         ("max_loops", C.c_int32), ("max_convergences", C.c_int32), ("early_stop_div", C.c_int32),
         ("log_energy", C.c_int32), ("rounds_per_sync", C.c_int32), ("sv_threshold", C.c_double),
-        ("bulk_rounds", C.c_int32), ("reserved", C.c_int32),
+        ("bulk_rounds", C.c_int32), ("commit_passes", C.c_int32),
     ]
 
 

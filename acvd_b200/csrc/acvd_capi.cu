@@ -90,7 +90,6 @@ extern "C" int acvd_create(acvd_ctx** out, int device) {
         ACVD_CUDA(cudaMallocHost(&c->h_scalars, 8 * sizeof(unsigned long long)));
         c->ctr.alloc(1);
         c->scalars.alloc(8);
-        if (const char* e = getenv("ACVD_COMMIT_PASSES")) c->commit_passes = std::max(1, atoi(e));
     } catch (const CudaError& err) {
         std::string m = std::string("CUDA error in acvd_create: ") + cudaGetErrorString(err.code);
         delete c;
@@ -821,6 +820,8 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     }
     int64_t loops = 0;
     const int bulk_cap = p.bulk_rounds < 0 ? 0 : (p.bulk_rounds == 0 ? 1000 : p.bulk_rounds);
+    const int env_passes = getenv("ACVD_COMMIT_PASSES") ? std::max(1, atoi(getenv("ACVD_COMMIT_PASSES"))) : 0;
+    c->commit_passes = p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : (c->world > 1 ? 1 : 4));
     while (true) {
         EvalCfg cfg = make_cfg(constrained, qlevel, thr);
         const bool as_iso = qem_as_iso(c, constrained, qlevel);

@@ -114,27 +114,41 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
     }
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    // 1. conflict resolution across ranks: the minimum key per cluster
-    ACVD_NCCL(nccl().AllReduce(c->best.p, c->best.p, (size_t)c->K, ncclUint64, ncclMin, c->comm, c->stream));
-    // 2. winners of this rank -> all ranks
     c->moves_local.alloc(((size_t)c->K / 2 + 64) * sizeof(MoveRec));
-    k_select_winners<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<MoveRec*>(c->moves_local.p), c->n_moves.p);
-    ACVD_LAUNCH_CHECK();
     RoundResult r;
     memset(&r, 0, sizeof r);
-    const int64_t total = dist_gather_moves(c, sizeof(MoveRec), r);
-    if (total > 0) {
-        const MoveRec* mv = reinterpret_cast<const MoveRec*>(c->moves_all.p);
-        switch (c->metric) {
-            case M_ISO: k_apply_moves<M_ISO, M_ISO><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total); break;
-            case M_QEM:
-                if (as_iso) k_apply_moves<M_ISO, M_QEM><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total);
-                else k_apply_moves<M_QEM, M_QEM><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total);
-                break;
-            case M_ANISO: k_apply_moves<M_ANISO, M_ANISO><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total); break;
-            default: k_apply_moves<M_ANISOQ, M_ANISOQ><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)total); break;
+    int64_t total = 0;
+    for (int pass = 0; pass < c->commit_passes; pass++) {
+        if (pass > 0) {
+            ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
+            ACVD_CUDA(cudaMemsetAsync(c->n_moves.p, 0, sizeof(unsigned long long), c->stream));
+            k_resubmit<<<gc, kThreads, 0, c->stream>>>(A);
+            ACVD_LAUNCH_CHECK();
         }
+        // 1. conflict resolution across ranks: the minimum key per cluster
+        ACVD_NCCL(nccl().AllReduce(c->best.p, c->best.p, (size_t)c->K, ncclUint64, ncclMin, c->comm, c->stream));
+        // 2. winners of this rank -> all ranks
+        k_select_winners<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<MoveRec*>(c->moves_local.p), c->n_moves.p);
         ACVD_LAUNCH_CHECK();
+        RoundResult rp;
+        memset(&rp, 0, sizeof rp);
+        const int64_t n = dist_gather_moves(c, sizeof(MoveRec), rp);
+        if (pass == 0) r = rp;
+        total += n;
+        if (n > 0) {
+            const MoveRec* mv = reinterpret_cast<const MoveRec*>(c->moves_all.p);
+            switch (c->metric) {
+                case M_ISO: k_apply_moves<M_ISO, M_ISO><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)n); break;
+                case M_QEM:
+                    if (as_iso) k_apply_moves<M_ISO, M_QEM><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)n);
+                    else k_apply_moves<M_QEM, M_QEM><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)n);
+                    break;
+                case M_ANISO: k_apply_moves<M_ANISO, M_ANISO><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)n); break;
+                default: k_apply_moves<M_ANISOQ, M_ANISOQ><<<gc, kThreads, 0, c->stream>>>(A, mv, (int)n); break;
+            }
+            ACVD_LAUNCH_CHECK();
+        }
+        if (n == 0) break;   // nothing won: later passes cannot win either
     }
     ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
     ACVD_CUDA(cudaEventSynchronize(c->ev[2]));

@@ -9,6 +9,8 @@
 // C ABI of include/acvd_b200.h, at the three points where the reference calls its engine
 // (ProcessClustering :897, MinimizeEnergy in the -m loop :943, ReComputeStatistics :930).
 #pragma once
+#include <cstring>
+#include <iostream>
 #include <string>
 #include <vector>
 
@@ -56,7 +58,7 @@ public:
     void SetMaxNumberOfConvergences(int v) { MaxNumberOfConvergences = v; }
     void SetNumberOfThreads(int) {}                            // P variants only: the GPU engine ignores it
     void SetPoolingRatio(int) {}
-    void SetInputDensityFile(const char*) { std::cout_warning("custom density volumes (-cd) are not supported by this build"); }
+    void SetInputDensityFile(const char*);                     // -cd: custom density volumes are not supported by this build
     void SetMaxCustomDensity(double) {}
     void SetMinCustomDensity(double) {}
     void SetCustomDensityMultiplicationFactor(double) {}

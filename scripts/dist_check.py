@@ -34,9 +34,12 @@ def main():
         g.set_num_clusters(w["K"])
         g.initial_sampling()
         g.save_clustering()
+        passes = int(os.environ.get("DIST_CHECK_PASSES", "1"))
+        g.minimize(unconstrained_init=uncon, commit_passes=passes)     # warm-up (NCCL channels, allocations)
+        g.restore_clustering()
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
-        rep = g.minimize(unconstrained_init=uncon)
+        rep = g.minimize(unconstrained_init=uncon, commit_passes=passes)
         torch.cuda.synchronize(); dist.barrier()
         dt = time.perf_counter() - t0
         cl = g.clustering()
@@ -51,8 +54,11 @@ def main():
             s.build_items(w["metric"], w["gradation"], w["indicator"])
             s.set_num_clusters(w["K"])
             s.initial_sampling()
+            s.save_clustering()
+            s.minimize(unconstrained_init=uncon, commit_passes=passes)
+            s.restore_clustering()
             t0 = time.perf_counter()
-            rep1 = s.minimize(unconstrained_init=uncon)
+            rep1 = s.minimize(unconstrained_init=uncon, commit_passes=passes)
             dt1 = time.perf_counter() - t0
             cl1 = s.clustering()
             identical = bool(np.array_equal(cl, cl1))
