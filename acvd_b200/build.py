@@ -47,5 +47,31 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(CSRC, "host")
+BIN = os.path.join(HERE, "bin")
+CLIS = ["ACVD", "ACVDQ", "AnisotropicRemeshingQ"]
+
+
+def build_host(force: bool = False) -> list:
+    """Host C++ front-ends (VTK-free vtkSurface + remeshing classes + the three CLIs), linked against
+    libacvd_b200.so through its C ABI only."""
+    os.makedirs(BIN, exist_ok=True)
+    build_library()
+    srcs = [os.path.join(HOST, "vtkSurface.cpp"), os.path.join(HOST, "vtkDiscreteRemeshing.cpp")]
+    newest = max(os.path.getmtime(os.path.join(dp, f)) for dp, _, fs in os.walk(HOST) for f in fs)
+    newest = max(newest, os.path.getmtime(os.path.join(ROOT, "include", "acvd_b200.h")))
+    out = []
+    for cli in CLIS:
+        exe = os.path.join(BIN, cli)
+        out.append(exe)
+        if not force and os.path.exists(exe) and os.path.getmtime(exe) >= newest:
+            continue
+        cmd = ["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(HOST, "Examples", cli + ".cxx")] + srcs
+        cmd += ["-L" + HERE, "-lacvd_b200", "-Wl,-rpath,$ORIGIN/.."]
+        subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))
