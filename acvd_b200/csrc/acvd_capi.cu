@@ -157,6 +157,21 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
         build_rows(c, uniq.p, nu, c->row_ptr, c->col.p);
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
     }
+    // --- ELL copy for the frontier scan (width 6 when no vertex has more neighbours, else 8 + CSR overflow)
+    {
+        int* d_max = reinterpret_cast<int*>(c->scalars.p);
+        ACVD_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), c->stream));
+        k_max_degree<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->row_ptr.p, d_max);
+        ACVD_LAUNCH_CHECK();
+        int max_deg = 0;
+        ACVD_CUDA(cudaMemcpyAsync(&max_deg, d_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        c->ell_w = max_deg <= 6 ? 6 : 8;
+        c->vpad = (((int64_t)V + 31) / 32) * 32;
+        c->ell.alloc((size_t)c->ell_w * c->vpad);
+        k_build_ell<<<grid_for(c->vpad), kThreads, 0, c->stream>>>(V, c->vpad, c->ell_w, c->row_ptr.p, c->col.p, c->ell.p);
+        ACVD_LAUNCH_CHECK();
+    }
     // --- vertex -> face incidence (ascending face id per vertex)
     {
         int64_t n = 3 * (int64_t)F;
@@ -559,7 +574,7 @@ struct RoundResult { unsigned long long proposals, mods, tests, evaluated, bound
 static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all) {
     ReassignArgs A;
     A.V = c->V; A.K = c->K;
-    A.row_ptr = c->row_ptr.p; A.col = c->col.p; A.cid = c->cid.p;
+    A.row_ptr = c->row_ptr.p; A.col = c->col.p; A.ell = c->ell.p; A.vpad = c->vpad; A.cid = c->cid.p;
     A.items = c->items.p; A.csum = c->csum.p; A.cenergy = c->cenergy.p; A.csize = c->csize.p;
     A.mod_round = c->mod_round.p;
     A.modbits = c->modbits.p;
@@ -594,7 +609,7 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
     k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
                                                                 c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
     ACVD_LAUNCH_CHECK();
-    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     if (!force_all) {
         k_carry<<<gc, kThreads, 0, c->stream>>>(A);
@@ -685,7 +700,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all) {
     k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
                                                                 c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
     ACVD_LAUNCH_CHECK();
-    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
     k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 1);

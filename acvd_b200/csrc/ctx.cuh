@@ -28,7 +28,9 @@ struct acvd_ctx {
     int V = 0, F = 0;
     int64_t nnz = 0;   // 2E
     DevBuf<float> xyz;
-    DevBuf<int> tri, row_ptr, col, vf_ptr;
+    DevBuf<int> tri, row_ptr, col, vf_ptr, ell;
+    int ell_w = 0;                    // ELL width (6 or 8)
+    int64_t vpad = 0;
     DevBuf<unsigned long long> vf_keys;
     // items
     int metric = -1;

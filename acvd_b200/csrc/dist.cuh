@@ -96,7 +96,7 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
     k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
                                                                   c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
     ACVD_LAUNCH_CHECK();
-    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     if (!force_all) {
         k_carry<<<gc, kThreads, 0, c->stream>>>(A);
@@ -180,7 +180,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all) {
     k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
                                                                   c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
     ACVD_LAUNCH_CHECK();
-    k_scan<<<gs, kThreads, 0, c->stream>>>(A);
+    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
     k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 0);

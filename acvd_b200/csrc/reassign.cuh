@@ -87,15 +87,10 @@ __global__ void __launch_bounds__(kThreads) k_modbits(int K, const int* __restri
     }
 }
 
-// k_scan: the frontier scan.  One warp owns 32 consecutive vertices; their CSR rows are contiguous in
-// `col`, so the warp streams row_ptr / cid / col with fully coalesced loads and only the neighbour
-// cluster ids are gathered (mostly L1/L2 hits with a locality-preserving vertex numbering).  Loads are
-// issued kScanUnroll batches deep to keep several requests in flight per warp.  Per entry the owner
-// row follows from a ballot of the row starts (shuffle binary search when the tile has empty rows);
-// boundary / dirty flags are reduced to the owner lanes with ballots and per-row bit ranges (no
-// shared memory, no atomics).  Output: compact work list of boundary vertices that must be
-// (re)evaluated; boundary vertices whose clusters did not change re-submit their stored proposal.
-constexpr int kScanUnroll = 4;
+// The frontier scan works on tiles of 32 consecutive vertices (one warp each): k_tile_filter picks the tiles that
+// must be looked at, k_scan<W> classifies their vertices (boundary? dirty?), emits the compact work list of
+// boundary vertices that must be (re)evaluated, lets the other boundary vertices re-submit their stored
+// proposal, and records the tile's cluster signature.
 constexpr int kSigSlots = 8;     // cluster ids remembered per 32-vertex tile (32 bytes)
 
 // k_tile_filter: a tile (32 consecutive vertices) must be re-scanned only if one of the clusters in its
@@ -145,25 +140,32 @@ __device__ __forceinline__ void sig_insert(int (&sg)[kSigSlots], int& n_sig, int
     }
 }
 
+// k_scan<W>: one thread per vertex of an active tile, neighbours from the ELL copy of the adjacency (W columns,
+// column-major: every load of a warp is one coalesced line; all W loads and the W gathers of neighbour cluster ids
+// are independent, so they are in flight together).  Rows longer than W finish from the CSR (rare).
+template <int W>
 __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
     const int K = A.K, V = A.V;
     const int lane = threadIdx.x & 31;
-    const unsigned lane_le = 0xffffffffu >> (31 - lane);   // bits 0..lane
+    const unsigned lane_lt = (1u << lane) - 1u;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_active = (int)*A.n_active_tiles;           // written by k_tile_filter of this round
     const unsigned* __restrict__ modbits = A.modbits;
+    const int* __restrict__ ell = A.ell;
+    const int64_t vpad = A.vpad;
     unsigned n_bnd = 0;
     for (int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_active; ti += n_warps) {
         const int tile = A.active_tiles[ti];
         const int v = tile * 32 + lane;
         const bool valid = v < V;
-        const int rp = A.row_ptr[valid ? v : V];
-        const int rpn = valid ? A.row_ptr[v + 1] : rp;
         const int a = valid ? A.cid[v] : -1;
-        const int beg = __shfl_sync(0xffffffffu, rp, 0);
-        const int end = __shfl_sync(0xffffffffu, rpn, 31);
-        const bool has_empty = __any_sync(0xffffffffu, valid && rp == rpn);
-        bool bnd = false, dirty = false;
+        int nb[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);      // v < vpad always
+        const bool overflow = nb[W - 1] == -2;
+        if (overflow) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
+#pragma unroll
+        for (int k = 0; k < W; k++) nb[k] = nb[k] >= 0 ? A.cid[nb[k]] : a;            // neighbour cluster ids (a = no neighbour)
         // signature of the tile: distinct clusters of its vertices ...
         int sg[kSigSlots];
 #pragma unroll
@@ -174,63 +176,30 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
             sig_insert(sg, n_sig, val);
             lm &= ~__ballot_sync(0xffffffffu, a == val);
         }
-        for (int base0 = beg; base0 < end; base0 += 32 * kScanUnroll) {
-            int b[kScanUnroll];
+        bool bnd = false, dirty = false;
+        auto visit = [&](int bb) {
+            const bool isb = bb != a;
+            bnd |= isb;
+            if (isb && bb < K) dirty |= (modbits[bb >> 5] >> (bb & 31)) & 1u;
+            // ... and of their neighbours: only a foreign cluster that is not recorded yet adds one (membership is
+            // tested by all lanes at once; the serial loop runs once per new cluster)
+            if (__any_sync(0xffffffffu, isb)) {
+                bool fresh = isb;
 #pragma unroll
-            for (int k = 0; k < kScanUnroll; k++) {
-                const int e = base0 + 32 * k + lane;
-                b[k] = (e < end) ? __ldg(A.col + e) : -1;
-            }
-#pragma unroll
-            for (int k = 0; k < kScanUnroll; k++) b[k] = (b[k] >= 0) ? A.cid[b[k]] : -1;
-#pragma unroll
-            for (int k = 0; k < kScanUnroll; k++) {
-                const int base = base0 + 32 * k;
-                if (base >= end) break;                       // warp-uniform
-                const int e = base + lane;
-                const bool ok = e < end;
-                int j;
-                if (!has_empty) {
-                    // rows starting at or before `base`, plus row starts strictly inside (base, e]
-                    const int j0 = __popc(__ballot_sync(0xffffffffu, rp <= base)) - 1;
-                    const int off = rp - base;
-                    const unsigned starts = __reduce_or_sync(0xffffffffu, (off > 0 && off < 32) ? (1u << off) : 0u);
-                    j = j0 + __popc(starts & lane_le);
-                } else {
-                    int lo = 0, hi = 31;                      // largest j with row start <= e
-#pragma unroll
-                    for (int it = 0; it < 5; it++) {
-                        int mid = (lo + hi + 1) >> 1;
-                        int r = __shfl_sync(0xffffffffu, rp, mid);
-                        if (r <= e) lo = mid; else hi = mid - 1;
-                    }
-                    j = lo;
-                }
-                const int a_own = __shfl_sync(0xffffffffu, a, j);
-                const int bb = b[k];
-                const bool isb = ok && (bb != a_own);
-                const bool isd = isb && (bb < K) && ((modbits[bb >> 5] >> (bb & 31)) & 1u);
-                const unsigned mb = __ballot_sync(0xffffffffu, isb);
-                const unsigned md = __ballot_sync(0xffffffffu, isd);
-                const int l0 = max(rp - base, 0), h0 = min(rpn - base, 32);
-                if (l0 < h0) {
-                    const unsigned m = (0xffffffffu >> (32 - h0)) & (0xffffffffu << l0);
-                    bnd |= (mb & m) != 0;
-                    dirty |= (md & m) != 0;
-                }
-                // ... and of their neighbours: only a boundary entry whose cluster is not recorded yet adds one
-                // (membership is tested by all lanes at once; the serial loop runs once per new cluster)
-                if (mb) {
-                    bool fresh = isb;
-#pragma unroll
-                    for (int q = 0; q < kSigSlots; q++) fresh = fresh && (sg[q] != bb);
-                    for (unsigned lm = __ballot_sync(0xffffffffu, fresh); lm;) {
-                        const int val = __shfl_sync(0xffffffffu, bb, __ffs(lm) - 1);
-                        sig_insert(sg, n_sig, val);
-                        lm &= ~__ballot_sync(0xffffffffu, bb == val);
-                    }
+                for (int q = 0; q < kSigSlots; q++) fresh = fresh && (sg[q] != bb);
+                for (unsigned lm = __ballot_sync(0xffffffffu, fresh); lm;) {
+                    const int val = __shfl_sync(0xffffffffu, bb, __ffs(lm) - 1);
+                    sig_insert(sg, n_sig, val);
+                    lm &= ~__ballot_sync(0xffffffffu, bb == val);
                 }
             }
+        };
+#pragma unroll
+        for (int k = 0; k < W; k++) visit(nb[k]);
+        if (__any_sync(0xffffffffu, overflow)) {            // finish long rows from the CSR, warp-uniformly
+            const int e0 = overflow ? A.row_ptr[v] + W : 0, e1 = overflow ? A.row_ptr[v + 1] : 0;
+            const int steps = __reduce_max_sync(0xffffffffu, e1 - e0);
+            for (int s = 0; s < steps; s++) visit((e0 + s < e1) ? A.cid[A.col[e0 + s]] : a);
         }
         {   // store the signature: lanes 0..7 write one slot each (32 B, coalesced)
             int mine = -1;
@@ -250,7 +219,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
             int basew = 0;
             if (lane == 0) basew = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)__popc(mw));
             basew = __shfl_sync(0xffffffffu, basew, 0);
-            if (work) A.work[basew + __popc(mw & (lane_le >> 1))] = v;
+            if (work) A.work[basew + __popc(mw & lane_lt)] = v;
         }
         if (bnd && !dirty && !A.bulk) {   // clusters unchanged since the last evaluation: the stored proposal is still exact
             const int d = A.prop_dst[v];

@@ -17,6 +17,8 @@ struct ReassignArgs {
     int V, K;
     const int* __restrict__ row_ptr;
     const int* __restrict__ col;
+    const int* __restrict__ ell;        // column-major padded adjacency (W columns of vpad entries)
+    long long vpad;
     int* cid;
     const double* __restrict__ items;   // V x stride
     double* csum;                       // K x stride

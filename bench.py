@@ -175,6 +175,10 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------------
 def main():
+    # stdout carries exactly one JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
