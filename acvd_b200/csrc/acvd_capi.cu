@@ -317,11 +317,12 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
     c->cid.alloc(V);
     c->csize.alloc(K); c->mod_round.alloc(K); c->anchor.alloc(K); c->frozen.alloc(K);
     c->csum.alloc((size_t)K * npad); c->cenergy.alloc(K); c->ccentroid.alloc(3 * (size_t)K);
-    c->isum.alloc(4 * (size_t)K); c->bulk_cen.alloc(3 * (size_t)K); c->leave_cnt.alloc(K); c->join_cnt.alloc(K);
+    c->isum.alloc(4 * (size_t)K); c->bulk_cen.alloc(4 * (size_t)K); c->bulk_energy.alloc(K); c->bulk_energy_sum.alloc(1); c->leave_cnt.alloc(K); c->join_cnt.alloc(K);
     c->best.alloc(K); c->modbits.alloc((size_t)(K + 31) / 32 + 1); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->plist_b.alloc(V); c->work.alloc(V);
     {
         const size_t n_tiles = ((size_t)V + 31) / 32;
-        c->tile_sig.alloc(n_tiles * kSigSlots); c->tile_active.alloc(n_tiles); c->active_tiles.alloc(n_tiles); c->round_scalars.alloc(2);
+        c->tile_sig.alloc(n_tiles * kSigSlots); c->tile_active.alloc(n_tiles); c->tile_stale.alloc(n_tiles);
+        ACVD_CUDA(cudaMemsetAsync(c->tile_stale.p, 1, n_tiles, c->stream)); c->active_tiles.alloc(n_tiles); c->round_scalars.alloc(2);
         ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
     } c->prop_e.alloc(V);
     ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)V * sizeof(int), c->stream));
@@ -585,7 +586,7 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.plist = c->plist_cur ? c->plist_b.p : c->plist.p;
     A.plist_prev = c->plist_cur ? c->plist.p : c->plist_b.p;
     A.n_prev_props = c->round_scalars.p + 1;
-    A.tile_sig = c->tile_sig.p; A.tile_active = c->tile_active.p; A.active_tiles = c->active_tiles.p;
+    A.tile_sig = c->tile_sig.p; A.tile_active = c->tile_active.p; A.tile_stale = c->tile_stale.p; A.active_tiles = c->active_tiles.p;
     A.n_active_tiles = c->round_scalars.p;
     A.work = c->work.p; A.ctr = c->ctr.p;
     A.round = c->round; A.force_all = force_all; A.bulk = 0; A.connexity = connexity; A.cfg = cfg;
@@ -673,7 +674,7 @@ static void ensure_fx_scale(acvd_ctx* c) {
 
 static BulkArgs make_bulk_args(acvd_ctx* c) {
     BulkArgs B;
-    B.isum = c->isum.p; B.ccen = c->bulk_cen.p; B.leave_cnt = c->leave_cnt.p; B.join_cnt = c->join_cnt.p;
+    B.isum = c->isum.p; B.ccen = c->bulk_cen.p; B.cen_energy = c->bulk_energy.p; B.leave_cnt = c->leave_cnt.p; B.join_cnt = c->join_cnt.p;
     B.scale = c->fx_scale;
     return B;
 }
@@ -683,8 +684,20 @@ static void bulk_init(acvd_ctx* c) {
     ACVD_LAUNCH_CHECK();
 }
 
+// deterministic sum of the per-cluster centroid energies kept by the bulk rounds
+static double bulk_energy(acvd_ctx* c) {
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceReduce::Sum(nullptr, tb, c->bulk_energy.p, c->bulk_energy_sum.p, c->K, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceReduce::Sum(t, tb, c->bulk_energy.p, c->bulk_energy_sum.p, c->K, c->stream));
+    double e = 0;
+    ACVD_CUDA(cudaMemcpyAsync(&e, c->bulk_energy_sum.p, sizeof e, cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    return e;
+}
+
 // one bulk (Lloyd-criterion) round: scan -> evaluate against the centroids -> commit all -> refresh centroids
-static void launch_bulk_round(acvd_ctx* c, int force_all) {
+static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     EvalCfg cfg = make_cfg(0, 0, 0);
     c->plist_cur = 0;
     ReassignArgs A = make_args(c, cfg, 0, force_all);
@@ -703,7 +716,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all) {
     if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 1);
+    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 1, stage, payload_npad(c->metric));
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     k_bulk_commit<<<gc, kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric));
@@ -847,10 +860,14 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
             if (c->fx_scale > 0) {
                 bulk_init(c);
                 int fa = 1;
+                // stage 0: Lloyd criterion (monotone by construction); stage 1: the reference's delta-E criterion on
+                // the thin band of moves stage 0 leaves, guarded by the energy of the fixed-point sums
+                int stage = 0;
+                double e_prev = 0;
                 for (int b = 0; b < bulk_cap && loops < p.max_loops; b++) {
                     RoundResult r;
-                    if (c->world > 1) r = run_bulk_round_dist(c, fa);
-                    else { launch_bulk_round(c, fa); r = finish_round(c); }
+                    if (c->world > 1) r = run_bulk_round_dist(c, fa, stage);
+                    else { launch_bulk_round(c, fa, stage); r = finish_round(c); }
                     fa = 0;
                     loops++;
                     R.rounds++; R.bulk_rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods;
@@ -865,7 +882,14 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                         fprintf(stderr, "[acvd trace] bulk  %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
                                 (long long)loops, nconv, r.active_tiles, r.boundary, r.evaluated, r.tests, r.proposals, r.mods,
                                 1e3 * r.ms_scan, 1e3 * r.ms_eval, 1e3 * r.ms_commit);
-                    if ((int64_t)r.proposals <= early_items / p.early_stop_div) break;
+                    const bool dry = (int64_t)r.proposals <= early_items / p.early_stop_div;
+                    if (stage == 0) {
+                        if (dry) { stage = 1; fa = 1; e_prev = bulk_energy(c); }
+                    } else {
+                        const double e = bulk_energy(c);
+                        if (dry || e > e_prev) break;
+                        e_prev = e;
+                    }
                 }
                 timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
             }

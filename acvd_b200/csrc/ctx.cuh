@@ -48,12 +48,12 @@ struct acvd_ctx {
     // reassignment scratch
     DevBuf<unsigned long long> best, prop_key;
     DevBuf<int> prop_dst, plist, plist_b, work, tile_sig, active_tiles;
-    DevBuf<unsigned char> tile_active;
+    DevBuf<unsigned char> tile_active, tile_stale;
     DevBuf<unsigned long long> round_scalars;   // [0] active tiles, [1] proposals of the previous round
     int plist_cur = 0;
     // bulk (Lloyd-criterion) rounds
     DevBuf<long long> isum;
-    DevBuf<double> bulk_cen;
+    DevBuf<double> bulk_cen, bulk_energy, bulk_energy_sum;
     DevBuf<int> leave_cnt, join_cnt;
     double fx_scale = 0.0;
     DevBuf<double2> prop_e;

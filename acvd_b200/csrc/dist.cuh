@@ -162,7 +162,7 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
 
 // bulk (Lloyd-criterion) round on `world` GPUs: local scan + evaluate, all-gather of the (vertex, destination)
 // pairs, then every rank counts leavers and applies all moves (integer sums: order-independent)
-static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all) {
+static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     EvalCfg cfg = make_cfg(0, 0, 0);
     c->plist_cur = 0;
     ReassignArgs A = make_args(c, cfg, 0, force_all);
@@ -183,7 +183,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all) {
     if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 0);
+    k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 0, stage, payload_npad(c->metric));
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->moves_local.alloc(((size_t)(own_tiles) * 32 + 64) * sizeof(int2));

@@ -25,6 +25,12 @@
 
 namespace acvd {
 
+// A vertex that changes cluster changes the signature of its own tile and of its neighbours' tiles.
+__device__ __forceinline__ void mark_tiles_stale(const ReassignArgs& A, int v) {
+    A.tile_stale[v >> 5] = 1;
+    for (int e = A.row_ptr[v]; e < A.row_ptr[v + 1]; e++) A.tile_stale[A.col[e] >> 5] = 1;
+}
+
 // Coordinates of the anchor item of cluster c (QEM fixed clusters, vtkQEMetricForClustering.h:270-275), or null.
 template <int EM>
 __device__ __forceinline__ const double* anchor_point(const ReassignArgs& A, int c, double* buf) {
@@ -128,26 +134,35 @@ __global__ void __launch_bounds__(kThreads) k_tile_filter(int tile_begin, int n_
     }
 }
 
-// append value `val` (warp-uniform) to the warp-uniform signature registers if absent
-__device__ __forceinline__ void sig_insert(int (&sg)[kSigSlots], int& n_sig, int val) {
-    bool present = false;
-#pragma unroll
-    for (int k = 0; k < kSigSlots; k++) present |= (k < n_sig && sg[k] == val);
-    if (!present) {
-#pragma unroll
-        for (int k = 0; k < kSigSlots; k++) if (k == n_sig) sg[k] = val;
-        n_sig++;   // beyond kSigSlots: overflow, recorded by the caller
+constexpr int kSigHash = 16;     // slots of the per-warp hash set the signature is collected in
+
+// insert `val` into the warp's open-addressing hash set (shared memory, -1 = empty); lanes insert in parallel
+__device__ __forceinline__ void sig_hash_insert(int* set, int val, bool& overflow) {
+    unsigned h = ((unsigned)val * 2654435761u) >> 28;
+#pragma unroll 1
+    for (int probe = 0; probe < kSigHash; probe++) {
+        const int slot = (h + probe) & (kSigHash - 1);
+        int old = reinterpret_cast<volatile int*>(set)[slot];          // usually already there: no atomic
+        if (old == val) return;
+        if (old == -1) old = atomicCAS(&set[slot], -1, val);
+        if (old == -1 || old == val) return;
     }
+    overflow = true;
 }
 
 // k_scan<W>: one thread per vertex of an active tile, neighbours from the ELL copy of the adjacency (W columns,
 // column-major: every load of a warp is one coalesced line; all W loads and the W gathers of neighbour cluster ids
 // are independent, so they are in flight together).  Rows longer than W finish from the CSR (rare).
+// The tile signature (distinct clusters of the tile's vertices and of their neighbours) is collected in a 16-slot
+// hash set per warp in shared memory: every lane inserts its foreign neighbour clusters with atomicCAS, in
+// parallel, so the cost does not depend on how many clusters meet in the tile.
 template <int W>
 __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
+    __shared__ int s_sig[kThreads / 32][kSigHash];
     const int K = A.K, V = A.V;
     const int lane = threadIdx.x & 31;
     const unsigned lane_lt = (1u << lane) - 1u;
+    int* set = s_sig[threadIdx.x >> 5];
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_active = (int)*A.n_active_tiles;           // written by k_tile_filter of this round
     const unsigned* __restrict__ modbits = A.modbits;
@@ -162,51 +177,50 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
         int nb[W];
 #pragma unroll
         for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);      // v < vpad always
-        const bool overflow = nb[W - 1] == -2;
-        if (overflow) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
+        const bool overflow_row = nb[W - 1] == -2;
+        if (overflow_row) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
 #pragma unroll
         for (int k = 0; k < W; k++) nb[k] = nb[k] >= 0 ? A.cid[nb[k]] : a;            // neighbour cluster ids (a = no neighbour)
-        // signature of the tile: distinct clusters of its vertices ...
-        int sg[kSigSlots];
-#pragma unroll
-        for (int k = 0; k < kSigSlots; k++) sg[k] = -1;
-        int n_sig = 0;
-        for (unsigned lm = __ballot_sync(0xffffffffu, valid); lm;) {
-            const int val = __shfl_sync(0xffffffffu, a, __ffs(lm) - 1);
-            sig_insert(sg, n_sig, val);
-            lm &= ~__ballot_sync(0xffffffffu, a == val);
+        // the signature is rebuilt only when a vertex in / next to the tile moved since it was recorded
+        const bool rebuild = A.force_all || A.tile_stale[tile];
+        bool sig_overflow = false;
+        if (rebuild) {
+            if (lane < kSigHash) set[lane] = -1;
+            __syncwarp();
+            // own clusters: one lane per run of equal ids inserts
+            const int prev = __shfl_up_sync(0xffffffffu, a, 1);
+            if (valid && (lane == 0 || prev != a)) sig_hash_insert(set, a, sig_overflow);
         }
         bool bnd = false, dirty = false;
+        int last = a;
         auto visit = [&](int bb) {
             const bool isb = bb != a;
             bnd |= isb;
-            if (isb && bb < K) dirty |= (modbits[bb >> 5] >> (bb & 31)) & 1u;
-            // ... and of their neighbours: only a foreign cluster that is not recorded yet adds one (membership is
-            // tested by all lanes at once; the serial loop runs once per new cluster)
-            if (__any_sync(0xffffffffu, isb)) {
-                bool fresh = isb;
-#pragma unroll
-                for (int q = 0; q < kSigSlots; q++) fresh = fresh && (sg[q] != bb);
-                for (unsigned lm = __ballot_sync(0xffffffffu, fresh); lm;) {
-                    const int val = __shfl_sync(0xffffffffu, bb, __ffs(lm) - 1);
-                    sig_insert(sg, n_sig, val);
-                    lm &= ~__ballot_sync(0xffffffffu, bb == val);
-                }
+            if (isb) {
+                if (bb < K) dirty |= (modbits[bb >> 5] >> (bb & 31)) & 1u;
+                if (rebuild && bb != last) { sig_hash_insert(set, bb, sig_overflow); last = bb; }
             }
         };
 #pragma unroll
         for (int k = 0; k < W; k++) visit(nb[k]);
-        if (__any_sync(0xffffffffu, overflow)) {            // finish long rows from the CSR, warp-uniformly
-            const int e0 = overflow ? A.row_ptr[v] + W : 0, e1 = overflow ? A.row_ptr[v + 1] : 0;
+        if (__any_sync(0xffffffffu, overflow_row)) {        // finish long rows from the CSR, warp-uniformly
+            const int e0 = overflow_row ? A.row_ptr[v] + W : 0, e1 = overflow_row ? A.row_ptr[v + 1] : 0;
             const int steps = __reduce_max_sync(0xffffffffu, e1 - e0);
             for (int s = 0; s < steps; s++) visit((e0 + s < e1) ? A.cid[A.col[e0 + s]] : a);
         }
-        {   // store the signature: lanes 0..7 write one slot each (32 B, coalesced)
-            int mine = -1;
-#pragma unroll
-            for (int k = 0; k < kSigSlots; k++) if (lane == k) mine = sg[k];
-            if (n_sig > kSigSlots && lane == 0) mine = -2;
-            if (lane < kSigSlots) A.tile_sig[(int64_t)tile * kSigSlots + lane] = mine;
+        __syncwarp();
+        if (rebuild) {   // compact the hash set into the 8-slot signature (32 B, coalesced); more than 8 clusters: overflow mark
+            const int mine = lane < kSigHash ? set[lane] : -1;
+            const unsigned full = __ballot_sync(0xffffffffu, mine != -1);
+            const bool ovf = __any_sync(0xffffffffu, sig_overflow) || __popc(full) > kSigSlots;
+            const int rank = __popc(full & lane_lt);
+            int* sig = A.tile_sig + (int64_t)tile * kSigSlots;
+            if (lane < kSigSlots) sig[lane] = -1;
+            __syncwarp();
+            if (mine != -1 && rank < kSigSlots) sig[rank] = mine;
+            __syncwarp();
+            if (ovf && lane == 0) sig[0] = -2;
+            if (lane == 0) A.tile_stale[tile] = 0;
         }
         bnd = bnd && valid;
         if (bnd) {
@@ -388,6 +402,7 @@ __global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
         A.mod_round[d] = A.round;
         A.cid[v] = d;
         A.prop_dst[v] = -1;
+        mark_tiles_stale(A, v);
         n_mods++;
     }
     warp_count_add(&A.ctr->mods, n_mods);
@@ -408,7 +423,8 @@ __global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
 // recomputed from the clustering before the exact rounds resume.
 struct BulkArgs {
     long long* isum;            // K x 4 fixed-point (S, W)
-    double* ccen;               // K x 3 centroids
+    double* ccen;               // K x 4: centroid and total weight
+    double* cen_energy;         // K: -|S|^2 / W of the fixed-point sums (energy guard of the second bulk stage)
     int* leave_cnt;             // K: vertices that want to leave the cluster this round
     int* join_cnt;              // K: vertices that joined the cluster this round
     double scale;               // fixed-point scale (power of two)
@@ -419,12 +435,16 @@ __global__ void __launch_bounds__(kThreads) k_bulk_init(int K, int stride, const
         const double* s = csum + (int64_t)c * stride;
 #pragma unroll
         for (int k = 0; k < 4; k++) B.isum[4 * (int64_t)c + k] = __double2ll_rn(s[k] * B.scale);
-        B.ccen[3 * c] = s[0] / s[3]; B.ccen[3 * c + 1] = s[1] / s[3]; B.ccen[3 * c + 2] = s[2] / s[3];
+        B.ccen[4 * c] = s[0] / s[3]; B.ccen[4 * c + 1] = s[1] / s[3]; B.ccen[4 * c + 2] = s[2] / s[3]; B.ccen[4 * c + 3] = s[3];
+        B.cen_energy[c] = -(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) / s[3];
         B.leave_cnt[c] = 0; B.join_cnt[c] = 0;
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, BulkArgs B, int count_leave) {
+// stage 0 (Lloyd criterion): move to the adjacent cluster whose centroid is strictly closer than the own one.
+// stage 1 (exact criterion, for the thin band of moves the first stage leaves): delta-E of the reference's test
+// against the round-start sums, w [W_b/(W_b+w) d_b^2 - W_a/(W_a-w) d_a^2] < 0, best candidate.
+__global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, BulkArgs B, int count_leave, int stage, int stride) {
     const int K = A.K;
     const int n_work = (int)A.ctr->evaluated;
     unsigned n_tests = 0;
@@ -441,8 +461,14 @@ __global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, Bulk
         } else {
             const double px = A.xyz[3 * (int64_t)v], py = A.xyz[3 * (int64_t)v + 1], pz = A.xyz[3 * (int64_t)v + 2];
             const bool blocked = A.csize[a] == 1;
-            double dx = px - B.ccen[3 * a], dy = py - B.ccen[3 * a + 1], dz = pz - B.ccen[3 * a + 2];
-            double best_d = dx * dx + dy * dy + dz * dz;
+            const double4 ca = *reinterpret_cast<const double4*>(B.ccen + 4 * (int64_t)a);
+            double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
+            const double da = dx * dx + dy * dy + dz * dz;
+            double w = 0.0, best = da;
+            if (stage == 1) {
+                w = __ldg(A.items + (int64_t)v * stride + 3);
+                best = ca.w / (ca.w - w) * da;          // what leaving the own cluster gains (per unit weight)
+            }
             for (int e = beg; e < end; e++) {
                 int b = A.cid[A.col[e]];
                 if (b == a || b >= K) continue;
@@ -451,9 +477,11 @@ __global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, Bulk
                 if (seen) continue;
                 n_tests++;
                 if (blocked) continue;
-                dx = px - B.ccen[3 * b]; dy = py - B.ccen[3 * b + 1]; dz = pz - B.ccen[3 * b + 2];
+                const double4 cb = *reinterpret_cast<const double4*>(B.ccen + 4 * (int64_t)b);
+                dx = px - cb.x; dy = py - cb.y; dz = pz - cb.z;
                 double d = dx * dx + dy * dy + dz * dz;
-                if (d < best_d) { best_d = d; best_b = b; }
+                if (stage == 1) d = cb.w / (cb.w + w) * d;  // what joining b costs (per unit weight)
+                if (d < best) { best = d; best_b = b; }
             }
         }
         A.prop_dst[v] = best_b;
@@ -488,6 +516,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_commit(ReassignArgs A, BulkAr
         A.mod_round[d] = A.round;
         if (a < K) A.mod_round[a] = A.round;
         A.cid[v] = d;
+        mark_tiles_stale(A, v);
         n_mods++;
     }
     warp_count_add(&A.ctr->mods, n_mods);
@@ -501,10 +530,11 @@ __global__ void __launch_bounds__(kThreads) k_bulk_refresh(int K, int* csize, Bu
         const int left = (lv < sz) ? lv : 0;
         if (left | jn) {
             csize[c] = sz - left + jn;
-            const double w = (double)B.isum[4 * (int64_t)c + 3];
-            B.ccen[3 * c] = (double)B.isum[4 * (int64_t)c] / w;
-            B.ccen[3 * c + 1] = (double)B.isum[4 * (int64_t)c + 1] / w;
-            B.ccen[3 * c + 2] = (double)B.isum[4 * (int64_t)c + 2] / w;
+            const double inv = 1.0 / B.scale;
+            const double sx = (double)B.isum[4 * (int64_t)c] * inv, sy = (double)B.isum[4 * (int64_t)c + 1] * inv;
+            const double sz = (double)B.isum[4 * (int64_t)c + 2] * inv, w = (double)B.isum[4 * (int64_t)c + 3] * inv;
+            B.ccen[4 * c] = sx / w; B.ccen[4 * c + 1] = sy / w; B.ccen[4 * c + 2] = sz / w; B.ccen[4 * c + 3] = w;
+            B.cen_energy[c] = -(sx * sx + sy * sy + sz * sz) / w;
         }
         B.leave_cnt[c] = 0; B.join_cnt[c] = 0;
     }
@@ -577,6 +607,7 @@ __global__ void __launch_bounds__(kThreads) k_apply_moves(ReassignArgs A, const 
         A.mod_round[d] = A.round;
         A.cid[v] = d;
         A.prop_dst[v] = -1;
+        mark_tiles_stale(A, v);
     }
 }
 
@@ -613,6 +644,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_apply(ReassignArgs A, BulkArg
         A.mod_round[d] = A.round;
         if (a < K) A.mod_round[a] = A.round;
         A.cid[v] = d;
+        mark_tiles_stale(A, v);
         n_mods++;
     }
     warp_count_add(&A.ctr->mods, n_mods);

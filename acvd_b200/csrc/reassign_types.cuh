@@ -39,6 +39,7 @@ struct ReassignArgs {
     const unsigned long long* n_prev_props;   // their count
     int* tile_sig;                      // n_tiles x 8 cluster-id signature of every 32-vertex tile
     unsigned char* tile_active;         // n_tiles: tile is re-scanned this round
+    unsigned char* tile_stale;          // n_tiles: a vertex in / next to the tile moved since its signature was built
     int* active_tiles;                  // compact list of active tiles
     unsigned long long* n_active_tiles;
     RoundCounters* ctr;
