@@ -590,6 +590,8 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.n_active_tiles = c->round_scalars.p;
     A.work = c->work.p; A.ctr = c->ctr.p;
     A.round = c->round; A.force_all = force_all; A.bulk = 0; A.connexity = connexity; A.cfg = cfg;
+    A.bulk_stage = 0; A.bulk_count_leave = 0; A.bulk_cen = c->bulk_cen.p; A.bulk_leave = c->leave_cnt.p;
+    A.item_stride = payload_npad(c->metric);
     return A;
 }
 
@@ -701,13 +703,13 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     EvalCfg cfg = make_cfg(0, 0, 0);
     c->plist_cur = 0;
     ReassignArgs A = make_args(c, cfg, 0, force_all);
-    A.bulk = 1;
+    A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 1;
     BulkArgs B = make_bulk_args(c);
     ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
     ACVD_LAUNCH_CHECK();
-    const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 2, gc = kNumSMs * 4;
     const int n_tiles = (c->V + 31) / 32;
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
     k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
@@ -734,7 +736,7 @@ static RoundResult finish_round(acvd_ctx* c) {
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     RoundResult r;
     r.proposals = c->h_ctr->proposals; r.mods = c->h_ctr->mods; r.tests = c->h_ctr->tests;
-    r.evaluated = c->h_ctr->evaluated; r.boundary = c->h_ctr->boundary; r.active_tiles = c->h_scalars[7];
+    r.evaluated = c->h_ctr->evaluated + c->h_ctr->pad[0]; r.boundary = c->h_ctr->boundary; r.active_tiles = c->h_scalars[7];
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, c->ev[0], c->ev[3]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
@@ -774,9 +776,11 @@ static int64_t eval_bytes(const acvd_ctx* c, const RoundResult& r, bool as_iso) 
 
 // bulk evaluate: list entry 4 + CSR row (8 + 8 deg) + point 12 + own centroid 24 + size 4 per work-list vertex;
 // 24 (centroid) per test; 8 per proposal written + commit: item 32 + 2 x 32 fixed-point sums
+// (bulk rounds take the decision inside k_scan: per decided vertex position 12 + own centroid 32 + size 4,
+//  32 per test, 8 per proposal written; these bytes are added to the scan's)
 static int64_t bulk_eval_bytes(const acvd_ctx* c, const RoundResult& r) {
-    const double deg = c->V ? (double)c->nnz / c->V : 0.0;
-    return (int64_t)((double)r.evaluated * (12.0 + 8.0 * deg + 40.0)) + (int64_t)r.tests * 24 + (int64_t)r.proposals * 8;
+    (void)c;
+    return (int64_t)r.evaluated * 48 + (int64_t)r.tests * 32 + (int64_t)r.proposals * 8;
 }
 
 extern "C" int acvd_reassign_round(acvd_ctx* c, int constrained, int qlevel, int connexity, int64_t* proposals,
@@ -873,7 +877,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                     R.rounds++; R.bulk_rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods;
                     R.proposals += (int64_t)r.proposals; R.evaluated += (int64_t)r.evaluated;
                     R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;
-                    R.round_launches++; R.scan_bytes += scan_bytes(c, r); R.evaluate_bytes += bulk_eval_bytes(c, r);
+                    R.round_launches++; R.scan_bytes += scan_bytes(c, r) + bulk_eval_bytes(c, r);
                     if (p.log_energy) {   // exact energy of the current clustering (test/trace path only)
                         recompute_statistics(c, constrained, qlevel, thr);
                         c->energy_log.push_back(global_energy(c));

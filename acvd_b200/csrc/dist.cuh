@@ -166,7 +166,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     EvalCfg cfg = make_cfg(0, 0, 0);
     c->plist_cur = 0;
     ReassignArgs A = make_args(c, cfg, 0, force_all);
-    A.bulk = 1;
+    A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 0;
     BulkArgs B = make_bulk_args(c);
     ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
     const unsigned* __restrict__ modbits = A.modbits;
     const int* __restrict__ ell = A.ell;
     const int64_t vpad = A.vpad;
-    unsigned n_bnd = 0;
+    unsigned n_bnd = 0, n_fused = 0, n_tests = 0;
     for (int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_active; ti += n_warps) {
         const int tile = A.active_tiles[ti];
         const int v = tile * 32 + lane;
@@ -227,7 +227,56 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
             n_bnd++;
             dirty = dirty || (a < K && ((modbits[a >> 5] >> (a & 31)) & 1u));
         }
-        const bool work = bnd && dirty;
+        bool work = bnd && dirty;
+        if (A.bulk) {
+            // bulk rounds: the decision needs only the neighbour cluster ids already in registers, the vertex
+            // position (coalesced) and the centroids of the few clusters involved -- taken here, no second pass.
+            // Rows longer than W (rare) go through the work list to k_bulk_evaluate.
+            const bool fused = work && !overflow_row;
+            int best_b = -1;
+            if (fused) {
+                n_fused++;
+                if (a >= K) {
+#pragma unroll
+                    for (int k = W - 1; k >= 0; k--) if (nb[k] < K) best_b = nb[k];     // first assigned neighbour cluster
+                } else {
+                    const double px = A.xyz[3 * (int64_t)v], py = A.xyz[3 * (int64_t)v + 1], pz = A.xyz[3 * (int64_t)v + 2];
+                    const bool blocked = A.csize[a] == 1;
+                    const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)a);
+                    double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
+                    double best = dx * dx + dy * dy + dz * dz, w = 0.0;
+                    if (A.bulk_stage == 1) {
+                        w = __ldg(A.items + (int64_t)v * A.item_stride + 3);
+                        best = ca.w / (ca.w - w) * best;
+                    }
+#pragma unroll
+                    for (int k = 0; k < W; k++) {
+                        const int b = nb[k];
+                        bool fresh = b != a && b < K;
+#pragma unroll
+                        for (int q = 0; q < k; q++) fresh = fresh && (nb[q] != b);
+                        if (!fresh) continue;
+                        n_tests++;
+                        if (blocked) continue;
+                        const double4 cb = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)b);
+                        dx = px - cb.x; dy = py - cb.y; dz = pz - cb.z;
+                        double d = dx * dx + dy * dy + dz * dz;
+                        if (A.bulk_stage == 1) d = cb.w / (cb.w + w) * d;
+                        if (d < best) { best = d; best_b = b; }
+                    }
+                }
+                A.prop_dst[v] = best_b;
+                if (best_b >= 0 && a < K && A.bulk_count_leave) atomicAdd(&A.bulk_leave[a], 1);
+            }
+            const unsigned mp = __ballot_sync(0xffffffffu, fused && best_b >= 0);
+            if (mp) {
+                int basep = 0;
+                if (lane == 0) basep = (int)atomicAdd(&A.ctr->proposals, (unsigned long long)__popc(mp));
+                basep = __shfl_sync(0xffffffffu, basep, 0);
+                if (fused && best_b >= 0) A.plist[basep + __popc(mp & lane_lt)] = v;
+            }
+            work = work && overflow_row;
+        }
         const unsigned mw = __ballot_sync(0xffffffffu, work);
         if (mw) {
             int basew = 0;
@@ -247,6 +296,10 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
         }
     }
     warp_count_add(&A.ctr->boundary, n_bnd);
+    if (A.bulk) {
+        warp_count_add(&A.ctr->pad[0], n_fused);   // vertices decided inside the scan
+        warp_count_add(&A.ctr->tests, n_tests);
+    }
 }
 
 // k_carry: live proposals of the previous round whose tile is not re-scanned this round (none of their
@@ -654,7 +707,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_apply(ReassignArgs A, BulkArg
 __global__ void k_pack_header(const RoundCounters* ctr, const unsigned long long* round_scalars, const unsigned long long* n_moves,
                               unsigned long long* hdr) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        hdr[0] = *n_moves; hdr[1] = ctr->proposals; hdr[2] = ctr->tests; hdr[3] = ctr->evaluated; hdr[4] = ctr->boundary;
+        hdr[0] = *n_moves; hdr[1] = ctr->proposals; hdr[2] = ctr->tests; hdr[3] = ctr->evaluated + ctr->pad[0]; hdr[4] = ctr->boundary;
         hdr[5] = round_scalars[0]; hdr[6] = 0; hdr[7] = 0;
     }
 }

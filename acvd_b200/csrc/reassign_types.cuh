@@ -45,7 +45,12 @@ struct ReassignArgs {
     RoundCounters* ctr;
     int round;
     int force_all;                      // SetAllClustersToModified (:717-722)
-    int bulk;                           // bulk (Lloyd-criterion) round: no stored proposals
+    int bulk;                           // bulk round: no stored proposals; the decision is taken inside k_scan
+    int bulk_stage;                     // 0: Lloyd criterion, 1: delta-E criterion against the round-start sums
+    int bulk_count_leave;               // count leavers per cluster here (single GPU) or after the all-gather
+    const double* bulk_cen;             // K x 4 centroid + weight
+    int* bulk_leave;                    // K
+    int item_stride;                    // doubles per item row
     int connexity;
     EvalCfg cfg;
 };
