@@ -483,20 +483,13 @@ static int clean_clustering(acvd_ctx* c) {
     c->label.alloc(V); c->comp_size.alloc(V); c->n_comp.alloc(K); c->winner.alloc(K);
     k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->label.p);
     ACVD_LAUNCH_CHECK();
-    int* d_changed = reinterpret_cast<int*>(c->scalars.p);
-    int cc_iters = 0;
-    for (int iter = 0; iter < 100000; iter++) {
-        cc_iters++;
-        ACVD_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(int), c->stream));
-        for (int rep = 0; rep < 4; rep++) {
-            k_cc_propagate<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, d_changed);
-            ACVD_LAUNCH_CHECK();
-        }
-        int changed = 0;
-        ACVD_CUDA(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        ACVD_CUDA(cudaStreamSynchronize(c->stream));
-        if (!changed) break;
-    }
+    if (c->ell_w == 6)
+        k_cc_hook<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
+    else
+        k_cc_hook<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
+    ACVD_LAUNCH_CHECK();
+    k_cc_flatten<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->label.p);
+    ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaMemsetAsync(c->comp_size.p, 0, (size_t)V * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->n_comp.p, 0, (size_t)K * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->winner.p, 0, (size_t)K * sizeof(unsigned long long), c->stream));
@@ -511,7 +504,7 @@ static int clean_clustering(acvd_ctx* c) {
     ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     c->stats_valid = false;
-    if (trace_on()) fprintf(stderr, "[acvd trace]   cc iterations x4: %d, disconnected %d, reset %d\n", cc_iters, (int)c->h_scalars[1], (int)c->h_scalars[2]);
+    if (trace_on()) fprintf(stderr, "[acvd trace]   disconnected %d, reset %d\n", (int)c->h_scalars[1], (int)c->h_scalars[2]);
     return (int)c->h_scalars[1];
 }
 
@@ -853,7 +846,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     int64_t loops = 0;
     const int bulk_cap = p.bulk_rounds < 0 ? 0 : (p.bulk_rounds == 0 ? 1000 : p.bulk_rounds);
     const int env_passes = getenv("ACVD_COMMIT_PASSES") ? std::max(1, atoi(getenv("ACVD_COMMIT_PASSES"))) : 0;
-    c->commit_passes = p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : (c->world > 1 ? 1 : 4));
+    c->commit_passes = p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : (c->world > 1 ? 1 : 2));
     while (true) {
         EvalCfg cfg = make_cfg(constrained, qlevel, thr);
         const bool as_iso = qem_as_iso(c, constrained, qlevel);

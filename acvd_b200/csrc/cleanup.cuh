@@ -65,24 +65,66 @@ __global__ void __launch_bounds__(kThreads) k_cluster_stats(int K, const int* __
 }
 
 // ---------------- connected components of every cluster (label = min vertex id of the component) ----------------
-__global__ void k_cc_propagate(int V, int K, const int* __restrict__ row_ptr, const int* __restrict__ col,
-                               const int* __restrict__ cid, int* label, int* changed) {
-    bool any = false;
+// Connected components of every cluster by hooking (union-find on the GPU): label[] is a parent array
+// initialised to the identity; every same-cluster edge (u < v) joins the two trees by atomically hooking
+// the larger root under the smaller one, so a component's root is its minimum vertex id -- which is also the
+// vertex at which the reference's index-ordered BFS discovers the component (:428-437).  One pass over the
+// edges (k_cc_hook) and one flattening pass (k_cc_flatten) replace ~16 label-propagation sweeps.
+__device__ __forceinline__ int cc_find(const int* label, int x) {
+    int p = __ldcg(label + x);
+    while (p != x) { x = p; p = __ldcg(label + x); }
+    return x;
+}
+// find with path halving; the shortcut is written with atomicMin so parents only ever decrease
+__device__ __forceinline__ int cc_find_compress(int* label, int x) {
+    while (true) {
+        const int p = __ldcg(label + x);
+        if (p == x) return x;
+        const int gp = __ldcg(label + p);
+        if (gp == p) return p;
+        atomicMin(label + x, gp);
+        x = gp;
+    }
+}
+
+__device__ __forceinline__ void cc_union(int* label, int u, int v) {
+    int ru = cc_find_compress(label, u), rv = cc_find_compress(label, v);
+    while (ru != rv) {
+        const int hi = max(ru, rv), lo = min(ru, rv);
+        const int old = atomicMin(label + hi, lo);
+        if (old == hi) return;          // hi was still a root: hooked
+        // somebody re-parented hi meanwhile: continue from the trees as they are now
+        ru = cc_find_compress(label, old);
+        rv = cc_find_compress(label, lo);
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_cc_hook(int V, int K, int64_t vpad, const int* __restrict__ ell,
+                                                      const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                                      const int* __restrict__ cid, int* label) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         const int c = cid[v];
         if (c >= K) continue;
-        int m = label[v];
-        const int m0 = m;
-        for (int e = row_ptr[v]; e < row_ptr[v + 1]; e++) {
-            int u = col[e];
-            if (cid[u] == c) { int lu = label[u]; if (lu < m) m = lu; }
+        int nb[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);
+        const bool overflow = nb[W - 1] == -2;
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            const int u = nb[k];
+            if (u >= 0 && u < v && cid[u] == c) cc_union(label, u, v);
         }
-        // pointer jumping: labels only ever name vertices of the same component
-        int j = label[m];
-        while (j < m) { m = j; j = label[m]; }
-        if (m < m0) { atomicMin(&label[v], m); any = true; }
+        if (overflow)
+            for (int e = row_ptr[v] + W - 1; e < row_ptr[v + 1]; e++) {
+                const int u = col[e];
+                if (u < v && cid[u] == c) cc_union(label, u, v);
+            }
     }
-    if (__syncthreads_or(any) && threadIdx.x == 0) *changed = 1;
+}
+
+__global__ void __launch_bounds__(kThreads) k_cc_flatten(int V, int* label) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) label[v] = cc_find(label, v);
 }
 
 __global__ void k_cc_sizes(int V, int K, const int* __restrict__ cid, const int* __restrict__ label, int* comp_size,

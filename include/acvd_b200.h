@@ -103,7 +103,7 @@ typedef struct acvd_params {
     int32_t rounds_per_sync;      /* rounds between host polls of the counters, <=0 -> 1 */
     double sv_threshold;          /* <=0 -> 1e-3 (Common/vtkQuadricTools.h:36) */
     int32_t bulk_rounds;          /* early phases: 0 -> bulk Lloyd-criterion rounds on (cap 1000), <0 -> off, >0 -> cap */
-    int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 4 on one GPU, 1 across GPUs */
+    int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 2 on one GPU, 1 across GPUs */
 } acvd_params;
 
 typedef struct acvd_report {
