@@ -585,7 +585,29 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.round = c->round; A.force_all = force_all; A.bulk = 0; A.connexity = connexity; A.cfg = cfg;
     A.bulk_stage = 0; A.bulk_count_leave = 0; A.bulk_cen = c->bulk_cen.p; A.bulk_leave = c->leave_cnt.p;
     A.item_stride = payload_npad(c->metric);
+    A.all_tiles = 0; A.tile_begin = 0; A.tile_end = (c->V + 31) / 32; A.sig_mode = 0;
     return A;
+}
+
+// Scan mode of a round.  Dense rounds (the previous round found most tiles active, or a phase starts) scan the
+// whole tile range and leave the signatures alone; the first sparse round after them rebuilds every signature
+// while scanning everything; after that the tile filter is used.  Returns true when k_tile_filter must run.
+static bool plan_scan(acvd_ctx* c, ReassignArgs& A, int force_all, int t0, int t1) {
+    A.tile_begin = t0; A.tile_end = t1;
+    const bool dense = force_all || c->dense_next;
+    c->last_tile_count = t1 - t0;
+    if (dense) { A.all_tiles = 1; A.sig_mode = 1; c->sig_valid = false; c->last_all_tiles = 1; return false; }
+    if (!c->sig_valid) { A.all_tiles = 1; A.sig_mode = 2; c->sig_valid = true; c->last_all_tiles = 1; return false; }
+    A.all_tiles = 0; A.sig_mode = 0; c->last_all_tiles = 0;
+    return true;
+}
+// after the round: decide the next round's mode from how much of the mesh was active (counters summed over ranks,
+// so every rank takes the same decision)
+static void update_density(acvd_ctx* c, RoundResult& r) {
+    if (c->last_all_tiles) {
+        r.active_tiles = (unsigned long long)(((int64_t)c->V + 31) / 32);
+        c->dense_next = r.boundary > 0 && (double)r.evaluated > 0.5 * (double)r.boundary;
+    } else c->dense_next = (double)r.active_tiles > 0.6 * (double)(((int64_t)c->V + 31) / 32);
 }
 
 static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso) {
@@ -601,13 +623,16 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
     ACVD_LAUNCH_CHECK();
     const int n_tiles = (c->V + 31) / 32;
+    const bool filtered = plan_scan(c, A, force_all, 0, n_tiles);
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
-                                                                c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
-    ACVD_LAUNCH_CHECK();
+    if (filtered) {
+        k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, 0, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                    c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+        ACVD_LAUNCH_CHECK();
+    }
     if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
-    if (!force_all) {
+    if (filtered) {   // live proposals in tiles that were not scanned compete again
         k_carry<<<gc, kThreads, 0, c->stream>>>(A);
         ACVD_LAUNCH_CHECK();
     }
@@ -704,10 +729,13 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     ACVD_LAUNCH_CHECK();
     const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 2, gc = kNumSMs * 4;
     const int n_tiles = (c->V + 31) / 32;
+    const bool filtered = plan_scan(c, A, force_all, 0, n_tiles);
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
-                                                                c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
-    ACVD_LAUNCH_CHECK();
+    if (filtered) {
+        k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, 0, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                    c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+        ACVD_LAUNCH_CHECK();
+    }
     if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
@@ -733,6 +761,7 @@ static RoundResult finish_round(acvd_ctx* c) {
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, c->ev[0], c->ev[3]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
+    update_density(c, r);
     return r;
 }
 

@@ -51,6 +51,9 @@ struct acvd_ctx {
     DevBuf<unsigned char> tile_active, tile_stale;
     DevBuf<unsigned long long> round_scalars;   // [0] active tiles, [1] proposals of the previous round
     int plist_cur = 0;
+    bool sig_valid = false;           // tile signatures describe the current clustering
+    bool dense_next = true;           // next round scans all tiles (activity was high)
+    int last_all_tiles = 0, last_tile_count = 0;
     // bulk (Lloyd-criterion) rounds
     DevBuf<long long> isum;
     DevBuf<double> bulk_cen, bulk_energy, bulk_energy_sum;

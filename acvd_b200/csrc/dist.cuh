@@ -92,13 +92,16 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
     dist_tile_range(c, t0, t1);
     const int own_tiles = t1 - t0;
     const int gs = grid_for((int64_t)own_tiles * 32, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    const bool filtered = plan_scan(c, A, force_all, t0, t1);
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
-                                                                  c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
-    ACVD_LAUNCH_CHECK();
+    if (filtered) {
+        k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, 0, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                      c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+        ACVD_LAUNCH_CHECK();
+    }
     if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
-    if (!force_all) {
+    if (filtered) {
         k_carry<<<gc, kThreads, 0, c->stream>>>(A);
         ACVD_LAUNCH_CHECK();
     }
@@ -157,6 +160,7 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
     c->round++;
+    update_density(c, r);
     return r;
 }
 
@@ -176,10 +180,13 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     dist_tile_range(c, t0, t1);
     const int own_tiles = t1 - t0;
     const int gs = grid_for((int64_t)own_tiles * 32, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    const bool filtered = plan_scan(c, A, force_all, t0, t1);
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, force_all, reinterpret_cast<const int4*>(c->tile_sig.p),
-                                                                  c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
-    ACVD_LAUNCH_CHECK();
+    if (filtered) {
+        k_tile_filter<<<grid_for(own_tiles), kThreads, 0, c->stream>>>(t0, t1, c->K, 0, reinterpret_cast<const int4*>(c->tile_sig.p),
+                                                                      c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
+        ACVD_LAUNCH_CHECK();
+    }
     if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
@@ -211,5 +218,6 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
     c->round++;
     c->stats_valid = false;
+    update_density(c, r);
     return r;
 }

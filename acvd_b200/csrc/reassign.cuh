@@ -164,13 +164,14 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
     const unsigned lane_lt = (1u << lane) - 1u;
     int* set = s_sig[threadIdx.x >> 5];
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int n_active = (int)*A.n_active_tiles;           // written by k_tile_filter of this round
+    // dense rounds scan the rank's whole tile range; otherwise the list written by k_tile_filter of this round
+    const int n_active = A.all_tiles ? (A.tile_end - A.tile_begin) : (int)*A.n_active_tiles;
     const unsigned* __restrict__ modbits = A.modbits;
     const int* __restrict__ ell = A.ell;
     const int64_t vpad = A.vpad;
     unsigned n_bnd = 0, n_fused = 0, n_tests = 0;
     for (int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_active; ti += n_warps) {
-        const int tile = A.active_tiles[ti];
+        const int tile = A.all_tiles ? (A.tile_begin + ti) : A.active_tiles[ti];
         const int v = tile * 32 + lane;
         const bool valid = v < V;
         const int a = valid ? A.cid[v] : -1;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
 #pragma unroll
         for (int k = 0; k < W; k++) nb[k] = nb[k] >= 0 ? A.cid[nb[k]] : a;            // neighbour cluster ids (a = no neighbour)
         // the signature is rebuilt only when a vertex in / next to the tile moved since it was recorded
-        const bool rebuild = A.force_all || A.tile_stale[tile];
+        const bool rebuild = A.sig_mode == 2 || (A.sig_mode == 0 && (A.force_all || A.tile_stale[tile]));
         bool sig_overflow = false;
         if (rebuild) {
             if (lane < kSigHash) set[lane] = -1;

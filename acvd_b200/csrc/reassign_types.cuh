@@ -51,6 +51,9 @@ struct ReassignArgs {
     const double* bulk_cen;             // K x 4 centroid + weight
     int* bulk_leave;                    // K
     int item_stride;                    // doubles per item row
+    int all_tiles;                      // dense round: scan tiles [tile_begin, tile_end) directly, no filter / list
+    int tile_begin, tile_end;
+    int sig_mode;                       // 0: rebuild stale signatures, 1: leave signatures alone, 2: rebuild all
     int connexity;
     EvalCfg cfg;
 };
