@@ -19,6 +19,10 @@
 #include "metric.cuh"
 #include "reassign.cuh"
 
+// blocks per SM requested for the scan grid (grid-stride; more blocks than resident ones balance the tail)
+static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("ACVD_SCAN_BPS")) : 8; return v; }
+#define ACVD_SCAN_BPS scan_bps()
+
 // every launch site of our own kernels has the context in scope as `c`: count them for the report
 #undef ACVD_LAUNCH_CHECK
 #define ACVD_LAUNCH_CHECK()              \
@@ -589,6 +593,14 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     return A;
 }
 
+static void launch_scan(acvd_ctx* c, const ReassignArgs& A, int grid) {
+    if (A.bulk) {
+        if (c->ell_w == 6) k_scan<6, true><<<grid, kThreads, 0, c->stream>>>(A); else k_scan<8, true><<<grid, kThreads, 0, c->stream>>>(A);
+    } else {
+        if (c->ell_w == 6) k_scan<6, false><<<grid, kThreads, 0, c->stream>>>(A); else k_scan<8, false><<<grid, kThreads, 0, c->stream>>>(A);
+    }
+}
+
 // Scan mode of a round.  Dense rounds (the previous round found most tiles active, or a phase starts) scan the
 // whole tile range and leave the signatures alone; the first sparse round after them rebuilds every signature
 // while scanning everything; after that the tile filter is used.  Returns true when k_tile_filter must run.
@@ -619,7 +631,7 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
     ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, sizeof(unsigned long long), c->stream));
-    const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 8, gc = kNumSMs * 4;
+    const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 8, gc = kNumSMs * 4;
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
     ACVD_LAUNCH_CHECK();
     const int n_tiles = (c->V + 31) / 32;
@@ -630,7 +642,7 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
                                                                     c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
         ACVD_LAUNCH_CHECK();
     }
-    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
+    launch_scan(c, A, gs);
     ACVD_LAUNCH_CHECK();
     if (filtered) {   // live proposals in tiles that were not scanned compete again
         k_carry<<<gc, kThreads, 0, c->stream>>>(A);
@@ -727,7 +739,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
     ACVD_LAUNCH_CHECK();
-    const int gs = grid_for((int64_t)c->V, kThreads, 8), ge = kNumSMs * 2, gc = kNumSMs * 4;
+    const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 2, gc = kNumSMs * 4;
     const int n_tiles = (c->V + 31) / 32;
     const bool filtered = plan_scan(c, A, force_all, 0, n_tiles);
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -736,7 +748,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
                                                                     c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
         ACVD_LAUNCH_CHECK();
     }
-    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
+    launch_scan(c, A, gs);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
     k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 1, stage, payload_npad(c->metric));

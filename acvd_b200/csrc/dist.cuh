@@ -99,7 +99,7 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
                                                                       c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
         ACVD_LAUNCH_CHECK();
     }
-    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
+    launch_scan(c, A, gs);
     ACVD_LAUNCH_CHECK();
     if (filtered) {
         k_carry<<<gc, kThreads, 0, c->stream>>>(A);
@@ -187,7 +187,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
                                                                       c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
         ACVD_LAUNCH_CHECK();
     }
-    if (c->ell_w == 6) k_scan<6><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8><<<gs, kThreads, 0, c->stream>>>(A);
+    launch_scan(c, A, gs);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
     k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 0, stage, payload_npad(c->metric));

@@ -156,7 +156,8 @@ __device__ __forceinline__ void sig_hash_insert(int* set, int val, bool& overflo
 // The tile signature (distinct clusters of the tile's vertices and of their neighbours) is collected in a 16-slot
 // hash set per warp in shared memory: every lane inserts its foreign neighbour clusters with atomicCAS, in
 // parallel, so the cost does not depend on how many clusters meet in the tile.
-template <int W>
+// BULK selects at compile time whether the bulk decision is taken in here (keeps the exact-round variant lean).
+template <int W, bool BULK>
 __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
     __shared__ int s_sig[kThreads / 32][kSigHash];
     const int K = A.K, V = A.V;
@@ -170,7 +171,16 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
     const int* __restrict__ ell = A.ell;
     const int64_t vpad = A.vpad;
     unsigned n_bnd = 0, n_fused = 0, n_tests = 0;
-    for (int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_active; ti += n_warps) {
+    // dense rounds: every block streams through one contiguous chunk of tiles, so the cluster ids of the mesh
+    // rows above / below (needed again a row later) are still in this SM's L1; list rounds: grid-stride
+    int ti_begin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, ti_end = n_active, ti_step = n_warps;
+    if (A.all_tiles) {
+        const int chunk = (n_active + gridDim.x - 1) / gridDim.x;
+        ti_begin = blockIdx.x * chunk + (threadIdx.x >> 5);
+        ti_end = min(n_active, (int)(blockIdx.x + 1) * chunk);
+        ti_step = blockDim.x >> 5;
+    }
+    for (int ti = ti_begin; ti < ti_end; ti += ti_step) {
         const int tile = A.all_tiles ? (A.tile_begin + ti) : A.active_tiles[ti];
         const int v = tile * 32 + lane;
         const bool valid = v < V;
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
             dirty = dirty || (a < K && ((modbits[a >> 5] >> (a & 31)) & 1u));
         }
         bool work = bnd && dirty;
-        if (A.bulk) {
+        if (BULK) {
             // bulk rounds: the decision needs only the neighbour cluster ids already in registers, the vertex
             // position (coalesced) and the centroids of the few clusters involved -- taken here, no second pass.
             // Rows longer than W (rare) go through the work list to k_bulk_evaluate.
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
             basew = __shfl_sync(0xffffffffu, basew, 0);
             if (work) A.work[basew + __popc(mw & lane_lt)] = v;
         }
-        if (bnd && !dirty && !A.bulk) {   // clusters unchanged since the last evaluation: the stored proposal is still exact
+        if (!BULK && bnd && !dirty) {   // clusters unchanged since the last evaluation: the stored proposal is still exact
             const int d = A.prop_dst[v];
             if (d >= 0) {
                 const unsigned long long key = A.prop_key[v];
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
         }
     }
     warp_count_add(&A.ctr->boundary, n_bnd);
-    if (A.bulk) {
+    if (BULK) {
         warp_count_add(&A.ctr->pad[0], n_fused);   // vertices decided inside the scan
         warp_count_add(&A.ctr->tests, n_tests);
     }
