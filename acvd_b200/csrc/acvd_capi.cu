@@ -33,6 +33,8 @@ static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("AC
 
 // ACVD_TRACE=1: wall-clock trace of the host driver's stages on stderr (the reference's ConsoleOutput>1
 // per-loop lines are the analogue, Common/vtkUniformClustering.h:752-760)
+constexpr int64_t kReplicatedTailProposals = 4096;
+
 static bool trace_on() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("ACVD_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
@@ -873,6 +875,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     // prime: FillHoles, ReComputeStatistics, SetAllClustersToModified (:727-730)
     timed_clean([&] { fill_holes(c); recompute_statistics(c, constrained, qlevel, thr); });
     int force_all = 1;
+    bool reeval_all = false;   // first replicated round of a multi-GPU tail
     int nconv = 0;
     // earlyStopItems = items of non-frozen clusters (:733-736)
     int64_t early_items = c->V;
@@ -932,9 +935,21 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                 timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
             }
         }
+        // Across GPUs the work of a round is split and two exchanges keep the replicas in step.  Once a phase is in
+        // its long tail (a few thousand live proposals or fewer) the exchanges cost more than the work: every rank
+        // then runs the remaining rounds of the phase redundantly on its own replica -- same deterministic code on
+        // the same state, so the replicas stay identical without any communication.  The first such round
+        // re-evaluates every boundary vertex, because stored proposals are only known to the rank that owns them.
         RoundResult r;
-        if (c->world > 1) r = run_round_dist(c, cfg, connexity, force_all, as_iso);
-        else { launch_round(c, cfg, connexity, force_all, as_iso); r = finish_round(c); }
+        if (force_all) c->replicated_tail = false;
+        if (c->world > 1 && !c->replicated_tail) {
+            r = run_round_dist(c, cfg, connexity, force_all, as_iso);
+            if ((int64_t)r.proposals <= kReplicatedTailProposals && r.mods > 0) { c->replicated_tail = true; reeval_all = true; }
+        } else {
+            launch_round(c, cfg, connexity, (force_all || reeval_all) ? 1 : 0, as_iso);
+            r = finish_round(c);
+            reeval_all = false;
+        }
         force_all = 0;
         loops++;
         R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;

@@ -76,6 +76,7 @@ struct acvd_ctx {
     // multi-GPU (acvd_dist.cu)
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    bool replicated_tail = false;             // multi-GPU: the tail of a phase runs redundantly on every rank, no exchange
     DevBuf<char> moves_local, moves_all;      // move records of this rank / of all ranks
     DevBuf<unsigned long long> hdr_local, hdr_all, n_moves;
     unsigned long long* h_hdr = nullptr;      // pinned: world x 8
