@@ -184,6 +184,41 @@ def ridged_ellipsoid(n: int = 316, axes=(1.0, 0.6, 0.4), ridge: float = 0.03, fr
     return pts.astype(dtype), tris
 
 
+def subdivide(points, triangles):
+    """One 1->4 midpoint subdivision (old points first, then one midpoint per edge)."""
+    p = np.asarray(points, dtype=np.float64)
+    t = np.asarray(triangles, dtype=np.int64)
+    V = p.shape[0]
+    e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
+    key = np.minimum(e[:, 0], e[:, 1]) * V + np.maximum(e[:, 0], e[:, 1])
+    uniq, inv = np.unique(key, return_inverse=True)
+    mid = 0.5 * (p[uniq // V] + p[uniq % V])
+    m = (V + inv).reshape(3, -1).T          # midpoints of (v0v1, v1v2, v2v0) per face
+    a, b, c = t[:, 0], t[:, 1], t[:, 2]
+    m01, m12, m20 = m[:, 0], m[:, 1], m[:, 2]
+    nt = np.concatenate([np.stack([a, m01, m20], 1), np.stack([m01, b, m12], 1), np.stack([m12, c, m20], 1),
+                         np.stack([m01, m12, m20], 1)])
+    return np.concatenate([p, mid]).astype(np.float32), nt.astype(np.int32)
+
+
+def bipyramid(n: int = 24, levels: int = 4):
+    """Closed surface with two vertices of valence ``n`` (the apexes) -- exercises adjacency rows longer than
+    the ELL width -- subdivided ``levels`` times (the apex valence is preserved by midpoint subdivision)."""
+    ang = np.arange(n) * (2 * np.pi / n)
+    ring = np.stack([np.cos(ang), np.sin(ang), 0 * ang], axis=1)
+    pts = np.concatenate([ring, [[0, 0, 0.8]], [[0, 0, -0.8]]])
+    top, bot = n, n + 1
+    tris = []
+    for i in range(n):
+        j = (i + 1) % n
+        tris.append([i, j, top])
+        tris.append([j, i, bot])
+    p, t = pts.astype(np.float32), np.asarray(tris, dtype=np.int32)
+    for _ in range(levels):
+        p, t = subdivide(p, t)
+    return p, t
+
+
 def workload(name: str):
     """Named workloads used by bench.py and the tests."""
     if name == "C1":

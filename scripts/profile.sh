@@ -6,8 +6,8 @@ WL=${1:-C2}; TAG=${2:-r01}
 mkdir -p gpurun_out
 BENCH="python bench.py --workload $WL --steps 1 --warmup 0 --no-cpu-baseline --e2e-steps 0"
 # every launch with its device time (cold-cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_${WL}_${TAG}.csv $BENCH > gpurun_out/launches_${WL}_${TAG}.log 2>&1
-# the reassignment kernels: early bulk rounds and early exact rounds
-ncu --set full --clock-control none --import-source on -k regex:"k_scan|k_bulk_evaluate|k_tile_filter" -s 9 -c 6 -f -o gpurun_out/prof_bulk_${WL}_${TAG} $BENCH > gpurun_out/prof_bulk_${WL}_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_scan|k_evaluate|k_commit" -s 130 -c 8 -f -o gpurun_out/prof_exact_${WL}_${TAG} $BENCH > gpurun_out/prof_exact_${WL}_${TAG}.log 2>&1
-ls -la gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_${WL}_${TAG}.csv $BENCH > gpurun_out/launches_${WL}_${TAG}.log 2>&1
+# dense bulk rounds: the fused scan (k_scan<6,true>); first exact rounds: k_scan<6,false>, k_evaluate, k_commit
+ncu --set full --clock-control none --import-source on -k regex:"k_scan" -s 4 -c 2 -f -o gpurun_out/prof_bulkscan_${WL}_${TAG} $BENCH > gpurun_out/prof_bulkscan_${WL}_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_evaluate|k_scan<\(int\)6, \(bool\)0>" -s 2 -c 4 -f -o gpurun_out/prof_exact_${WL}_${TAG} $BENCH > gpurun_out/prof_exact_${WL}_${TAG}.log 2>&1
+ls -la gpurun_out | tail -8

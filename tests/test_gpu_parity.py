@@ -30,6 +30,11 @@ def torus():
     return p, t, meshgen.torus_curvature_indicator(160, 100)
 
 
+@pytest.fixture(scope="module")
+def spindle():
+    return meshgen.bipyramid(24, 4)      # V = 6 146, two vertices of valence 24 (> ELL width)
+
+
 def make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K, gradation=0.0, cw=None, pd=None):
     o = oracle_mod.Oracle(p, t)
     o.build_metric(metric, gradation, cw, pd)
@@ -239,6 +244,48 @@ def test_bulk_rounds_energy_monotone_and_same_fixed_point(oracle_mod, gpu_ctx_fa
     o.minimize()
     o.recompute_statistics()
     assert abs(res[0] - o.global_energy()) <= 0.01 * abs(o.global_energy())
+
+
+@pytest.mark.parametrize("metric,uncon", [("iso", 0), ("qem", 1)])
+def test_high_valence_rows(oracle_mod, gpu_ctx_factory, spindle, metric, uncon):
+    """Adjacency rows longer than the ELL width take the CSR overflow paths (scan, bulk decision, components)."""
+    p, t = spindle
+    K = 150
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K)
+    rp, col = g.csr()
+    assert (np.diff(rp) > 8).sum() == 2 and np.diff(rp).max() == 24
+    rpo, colo = o.csr()
+    assert np.array_equal(rp, rpo) and np.array_equal(col, np.concatenate([np.sort(colo[rpo[v]:rpo[v + 1]]) for v in range(p.shape[0])]))
+    g.set_items(metric, o.items())
+    cl0 = o.initial_sampling().copy()
+    # bit-exact stages at the same clustering, including the clean-up of broken clusters around the apexes
+    cl = cl0.copy()
+    cl[cl == K] = 0
+    apex = int(np.argmax(np.diff(rp)))
+    cl[col[rp[apex]:rp[apex + 1]][::2]] = (cl[apex] + 1) % K     # every other neighbour of the apex -> foreign cluster
+    o.set_clustering(cl)
+    g.set_clustering(cl)
+    assert np.array_equal(g.boundary_flags(), o.boundary_flags())
+    assert o.clean_clustering() == g.clean_clustering()
+    assert np.array_equal(o.clustering(), g.clustering())
+    # full minimisation from the same start
+    o.set_clustering(cl0)
+    g.set_clustering(cl0)
+    o.set_params(unconstrained_init=uncon)
+    o.minimize()
+    o.recompute_statistics()
+    rep = g.minimize(unconstrained_init=uncon)
+    cg = g.clustering()
+    assert cg.min() >= 0 and cg.max() < K and np.bincount(cg, minlength=K).min() >= 1
+    assert g.clean_clustering() == 0
+    assert abs(rep["energy"] - o.global_energy()) <= 0.01 * abs(o.global_energy())
+    o2 = oracle_mod.Oracle(p, t)
+    o2.build_metric(metric)
+    o2.set_num_clusters(K)
+    o2.set_clustering(cg)
+    o2.set_connexity(1)
+    o2.prime()
+    assert o2.process_one_loop() == 0
 
 
 def test_round_trip_determinism(gpu_ctx_factory, sphere):
