@@ -18,6 +18,7 @@
 #include "mesh.cuh"
 #include "metric.cuh"
 #include "reassign.cuh"
+#include "scan_dense.cuh"
 
 // blocks per SM requested for the scan grid (grid-stride; more blocks than resident ones balance the tail)
 static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("ACVD_SCAN_BPS")) : 8; return v; }
@@ -131,7 +132,8 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     if (V <= 0 || F <= 0 || !xyz || !tri) throw std::runtime_error("acvd_set_mesh: bad arguments");
     c->V = V; c->F = F;
     c->have_items = false; c->stats_valid = false;
-    c->xyz.alloc(3 * (size_t)V);
+    c->vpad = (((int64_t)V + 31) / 32) * 32;      // per-vertex streams are padded to whole 32-vertex tiles (TMA copies whole tiles)
+    c->xyz.alloc(3 * (size_t)c->vpad);
     c->tri.alloc(3 * (size_t)F);
     ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -173,7 +175,6 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
         ACVD_CUDA(cudaMemcpyAsync(&max_deg, d_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
         c->ell_w = max_deg <= 6 ? 6 : 8;
-        c->vpad = (((int64_t)V + 31) / 32) * 32;
         c->ell.alloc((size_t)c->ell_w * c->vpad);
         k_build_ell<<<grid_for(c->vpad), kThreads, 0, c->stream>>>(V, c->vpad, c->ell_w, c->row_ptr.p, c->col.p, c->ell.p);
         ACVD_LAUNCH_CHECK();
@@ -235,7 +236,7 @@ extern "C" int acvd_build_items(acvd_ctx* c, int metric, double gradation, const
     if (!custom && ((metric == M_QEM && gradation > 0) || (aniso && gradation != 0)))
         throw std::runtime_error("acvd_build_items: gradation needs custom_weights (curvature indicator)");
     c->metric = metric;
-    c->weight.alloc(V);
+    c->weight.alloc((size_t)c->vpad);
     c->items.alloc((size_t)V * payload_npad(metric));
     compute_areas(c);
     DevBuf<double> d_custom, d_sum;
@@ -277,7 +278,7 @@ extern "C" int acvd_set_items(acvd_ctx* c, int metric, const double* payload) {
     const int V = c->V, np = payload_np(metric), npad = payload_npad(metric);
     c->metric = metric;
     c->items.alloc((size_t)V * npad);
-    c->weight.alloc(V);
+    c->weight.alloc((size_t)c->vpad);
     DevBuf<double> tmp;
     tmp.alloc((size_t)V * np);
     ACVD_CUDA(cudaMemcpyAsync(tmp.p, payload, (size_t)V * np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -320,14 +321,15 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
     if (!c->have_items) throw std::runtime_error("acvd_set_num_clusters: build or set the items first");
     const int V = c->V, npad = payload_npad(c->metric);
     c->K = K;
-    c->cid.alloc(V);
+    c->cid.alloc((size_t)c->vpad);
     c->csize.alloc(K); c->mod_round.alloc(K); c->anchor.alloc(K); c->frozen.alloc(K);
     c->csum.alloc((size_t)K * npad); c->cenergy.alloc(K); c->ccentroid.alloc(3 * (size_t)K);
     c->isum.alloc(4 * (size_t)K); c->bulk_cen.alloc(4 * (size_t)K); c->bulk_energy.alloc(K); c->bulk_energy_sum.alloc(1); c->leave_cnt.alloc(K); c->join_cnt.alloc(K);
     c->best.alloc(K); c->modbits.alloc((size_t)(K + 31) / 32 + 1); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->plist_b.alloc(V); c->work.alloc(V);
     {
         const size_t n_tiles = ((size_t)V + 31) / 32;
-        c->tile_sig.alloc(n_tiles * kSigSlots); c->tile_active.alloc(n_tiles); c->tile_stale.alloc(n_tiles);
+        c->tile_sig.alloc(n_tiles * kSigSlots); c->tile_active.alloc(n_tiles); c->tile_stale.alloc(n_tiles); c->prop_mask.alloc(n_tiles);
+        ACVD_CUDA(cudaMemsetAsync(c->prop_mask.p, 0, n_tiles * sizeof(unsigned), c->stream));
         ACVD_CUDA(cudaMemsetAsync(c->tile_stale.p, 1, n_tiles, c->stream)); c->active_tiles.alloc(n_tiles); c->round_scalars.alloc(2);
         ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
     } c->prop_e.alloc(V);
@@ -582,6 +584,7 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.anchor = c->has_anchor ? c->anchor.p : nullptr;
     A.xyz = c->xyz.p;
     A.best = c->best.p; A.prop_dst = c->prop_dst.p; A.prop_key = c->prop_key.p; A.prop_e = c->prop_e.p;
+    A.prop_mask = c->prop_mask.p; A.weight = c->weight.p;
     A.plist = c->plist_cur ? c->plist_b.p : c->plist.p;
     A.plist_prev = c->plist_cur ? c->plist.p : c->plist_b.p;
     A.n_prev_props = c->round_scalars.p + 1;
@@ -595,7 +598,24 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     return A;
 }
 
+// dense bulk rounds: the TMA-staged streaming scan (scan_dense.cuh), one wave of 4 blocks per SM
+template <int W>
+static void launch_scan_bulk_dense(acvd_ctx* c, const ReassignArgs& A) {
+    static bool configured = false;
+    if (!configured) {
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W)));
+        configured = true;
+    }
+    const int n_tiles = A.tile_end - A.tile_begin;
+    const int grid = std::max(1, std::min(kNumSMs * 4, (n_tiles + kDenseConsumers - 1) / kDenseConsumers));
+    k_scan_bulk_dense<W><<<grid, kDenseThreads, dense_smem_bytes(W), c->stream>>>(A);
+}
+
 static void launch_scan(acvd_ctx* c, const ReassignArgs& A, int grid) {
+    if (A.bulk && A.all_tiles && A.sig_mode == 1 && !getenv("ACVD_NO_DENSE_SCAN")) {
+        if (c->ell_w == 6) launch_scan_bulk_dense<6>(c, A); else launch_scan_bulk_dense<8>(c, A);
+        return;
+    }
     if (A.bulk) {
         if (c->ell_w == 6) k_scan<6, true><<<grid, kThreads, 0, c->stream>>>(A); else k_scan<8, true><<<grid, kThreads, 0, c->stream>>>(A);
     } else {
@@ -741,7 +761,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
     ACVD_LAUNCH_CHECK();
-    const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 2, gc = kNumSMs * 4;
+    const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 2;
     const int n_tiles = (c->V + 31) / 32;
     const bool filtered = plan_scan(c, A, force_all, 0, n_tiles);
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -756,7 +776,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 1, stage, payload_npad(c->metric));
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    k_bulk_commit<<<gc, kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric));
+    k_bulk_commit<<<grid_for((int64_t)c->V), kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric));
     ACVD_LAUNCH_CHECK();
     k_bulk_refresh<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->csize.p, B);
     ACVD_LAUNCH_CHECK();

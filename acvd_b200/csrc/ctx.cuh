@@ -49,6 +49,7 @@ struct acvd_ctx {
     DevBuf<unsigned long long> best, prop_key;
     DevBuf<int> prop_dst, plist, plist_b, work, tile_sig, active_tiles;
     DevBuf<unsigned char> tile_active, tile_stale;
+    DevBuf<unsigned> prop_mask;                 // bulk rounds: proposing vertices, one bit per vertex
     DevBuf<unsigned long long> round_scalars;   // [0] active tiles, [1] proposals of the previous round
     int plist_cur = 0;
     bool sig_valid = false;           // tile signatures describe the current clustering

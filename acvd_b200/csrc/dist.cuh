@@ -194,9 +194,9 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->moves_local.alloc(((size_t)(own_tiles) * 32 + 64) * sizeof(int2));
-    k_pack_bulk_moves<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<int2*>(c->moves_local.p));
+    ACVD_CUDA(cudaMemsetAsync(c->n_moves.p, 0, sizeof(unsigned long long), c->stream));
+    k_pack_bulk_moves<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<int2*>(c->moves_local.p), c->n_moves.p);
     ACVD_LAUNCH_CHECK();
-    ACVD_CUDA(cudaMemcpyAsync(c->n_moves.p, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
     RoundResult r;
     memset(&r, 0, sizeof r);
     const int64_t total = dist_gather_moves(c, sizeof(int2), r);

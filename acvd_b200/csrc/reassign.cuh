@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
     const unsigned* __restrict__ modbits = A.modbits;
     const int* __restrict__ ell = A.ell;
     const int64_t vpad = A.vpad;
-    unsigned n_bnd = 0, n_fused = 0, n_tests = 0;
+    unsigned n_bnd = 0, n_fused = 0, n_tests = 0, n_props = 0;
     // dense rounds: every block streams through one contiguous chunk of tiles, so the cluster ids of the mesh
     // rows above / below (needed again a row later) are still in this SM's L1; list rounds: grid-stride
     int ti_begin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, ti_end = n_active, ti_step = n_warps;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
                     double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
                     double best = dx * dx + dy * dy + dz * dz, w = 0.0;
                     if (A.bulk_stage == 1) {
-                        w = __ldg(A.items + (int64_t)v * A.item_stride + 3);
+                        w = __ldg(A.weight + v);
                         best = ca.w / (ca.w - w) * best;
                     }
 #pragma unroll
@@ -280,12 +280,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
                 if (best_b >= 0 && a < K && A.bulk_count_leave) atomicAdd(&A.bulk_leave[a], 1);
             }
             const unsigned mp = __ballot_sync(0xffffffffu, fused && best_b >= 0);
-            if (mp) {
-                int basep = 0;
-                if (lane == 0) basep = (int)atomicAdd(&A.ctr->proposals, (unsigned long long)__popc(mp));
-                basep = __shfl_sync(0xffffffffu, basep, 0);
-                if (fused && best_b >= 0) A.plist[basep + __popc(mp & lane_lt)] = v;
-            }
+            if (lane == 0) { A.prop_mask[tile] = mp; n_props += __popc(mp); }
             work = work && overflow_row;
         }
         const unsigned mw = __ballot_sync(0xffffffffu, work);
@@ -310,6 +305,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
     if (BULK) {
         warp_count_add(&A.ctr->pad[0], n_fused);   // vertices decided inside the scan
         warp_count_add(&A.ctr->tests, n_tests);
+        warp_count_add(&A.ctr->proposals, n_props);
     }
 }
 
@@ -511,7 +507,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_init(int K, int stride, const
 __global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, BulkArgs B, int count_leave, int stage, int stride) {
     const int K = A.K;
     const int n_work = (int)A.ctr->evaluated;
-    unsigned n_tests = 0;
+    unsigned n_tests = 0, n_props = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
         const int v = A.work[i];
         const int a = A.cid[v];
@@ -530,7 +526,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, Bulk
             const double da = dx * dx + dy * dy + dz * dz;
             double w = 0.0, best = da;
             if (stage == 1) {
-                w = __ldg(A.items + (int64_t)v * stride + 3);
+                w = __ldg(A.weight + v);
                 best = ca.w / (ca.w - w) * da;          // what leaving the own cluster gains (per unit weight)
             }
             for (int e = beg; e < end; e++) {
@@ -551,37 +547,48 @@ __global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, Bulk
         A.prop_dst[v] = best_b;
         if (best_b >= 0) {
             if (a < K && count_leave) atomicAdd(&B.leave_cnt[a], 1);
-            int slot = (int)atomicAdd(&A.ctr->proposals, 1ull);
-            A.plist[slot] = v;
+            atomicOr(&A.prop_mask[v >> 5], 1u << (v & 31));
+            n_props++;
         }
     }
     warp_count_add(&A.ctr->tests, n_tests);
+    warp_count_add(&A.ctr->proposals, n_props);
 }
 
 // Applies every proposal unless its source cluster would be emptied (then all of that cluster's leavers
-// wait: the decision depends only on totals, so it is deterministic).
+// wait: the decision depends only on totals, so it is deterministic).  One thread per vertex of the rank's
+// tile range; the proposers are the set bits of the tiles' proposal masks, which are cleared on the way.
 __global__ void __launch_bounds__(kThreads) k_bulk_commit(ReassignArgs A, BulkArgs B, int stride) {
     const int K = A.K;
-    const int n_props = (int)A.ctr->proposals;
+    const int64_t n = (int64_t)(A.tile_end - A.tile_begin) * 32;
+    const int lane = threadIdx.x & 31;
     unsigned n_mods = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
-        const int v = A.plist[i];
-        const int d = A.prop_dst[v];
-        const int a = A.cid[v];
-        if (a < K && B.leave_cnt[a] >= A.csize[a]) continue;
-        const double* it = A.items + (int64_t)v * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tile = A.tile_begin + (int)(i >> 5);
+        const unsigned m = A.prop_mask[tile];
+        if (m == 0) continue;                                  // warp-uniform
+        if ((m >> lane) & 1u) {
+            const int v = tile * 32 + lane;
+            const int d = A.prop_dst[v];
+            const int a = A.cid[v];
+            if (!(a < K && B.leave_cnt[a] >= A.csize[a])) {
+                const double* it = A.items + (int64_t)v * stride;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            long long f = __double2ll_rn(__ldg(it + k) * B.scale);
-            atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)d + k]), (unsigned long long)f);
-            if (a < K) atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)a + k]), (unsigned long long)(-f));
+                for (int k = 0; k < 4; k++) {
+                    long long f = __double2ll_rn(__ldg(it + k) * B.scale);
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)d + k]), (unsigned long long)f);
+                    if (a < K) atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)a + k]), (unsigned long long)(-f));
+                }
+                atomicAdd(&B.join_cnt[d], 1);
+                A.mod_round[d] = A.round;
+                if (a < K) A.mod_round[a] = A.round;
+                A.cid[v] = d;
+                mark_tiles_stale(A, v);
+                n_mods++;
+            }
         }
-        atomicAdd(&B.join_cnt[d], 1);
-        A.mod_round[d] = A.round;
-        if (a < K) A.mod_round[a] = A.round;
-        A.cid[v] = d;
-        mark_tiles_stale(A, v);
-        n_mods++;
+        __syncwarp();
+        if (lane == 0) A.prop_mask[tile] = 0;
     }
     warp_count_add(&A.ctr->mods, n_mods);
 }
@@ -675,11 +682,23 @@ __global__ void __launch_bounds__(kThreads) k_apply_moves(ReassignArgs A, const 
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_pack_bulk_moves(ReassignArgs A, int2* moves) {
-    const int n = (int)A.ctr->proposals;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int v = A.plist[i];
-        moves[i] = make_int2(v, A.prop_dst[v]);
+// multi-GPU bulk rounds: the rank's proposals (set bits of its tiles' masks) -> compact (vertex, destination) records
+__global__ void __launch_bounds__(kThreads) k_pack_bulk_moves(ReassignArgs A, int2* moves, unsigned long long* n_moves) {
+    const int64_t n = (int64_t)(A.tile_end - A.tile_begin) * 32;
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tile = A.tile_begin + (int)(i >> 5);
+        const unsigned m = A.prop_mask[tile];
+        if (m == 0) continue;                                  // warp-uniform
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(n_moves, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((m >> lane) & 1u) {
+            const int v = tile * 32 + lane;
+            moves[base + __popc(m & ((1u << lane) - 1u))] = make_int2(v, A.prop_dst[v]);
+        }
+        __syncwarp();
+        if (lane == 0) A.prop_mask[tile] = 0;
     }
 }
 

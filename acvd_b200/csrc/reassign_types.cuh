@@ -33,7 +33,9 @@ struct ReassignArgs {
     int* prop_dst;                      // V: proposed destination or -1
     unsigned long long* prop_key;       // V
     double2* prop_e;                    // V: (E(a - v), E(b + v)) of the proposal
-    int* plist;                         // compact list of proposing vertices this round
+    int* plist;                         // compact list of proposing vertices this round (exact rounds)
+    unsigned* prop_mask;                // n_tiles: proposing vertices of a bulk round, one bit per vertex of the tile
+    const double* __restrict__ weight;  // V: item weights (= items[v][3]), dense copy for the bulk rounds
     int* work;                          // compact list of boundary vertices to (re)evaluate this round
     const int* plist_prev;              // proposing vertices of the previous round
     const unsigned long long* n_prev_props;   // their count

@@ -308,3 +308,33 @@ def test_initial_sampling_matches_oracle(oracle_mod, gpu_ctx_factory, sphere):
     g.set_items("iso", o.items())
     g.initial_sampling()
     assert np.array_equal(g.clustering(), o.initial_sampling())
+
+
+@pytest.mark.parametrize("mesh", ["torus", "spindle"])
+def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle, mesh, monkeypatch):
+    """The TMA-staged dense bulk scan (k_scan_bulk_dense) and the list-based k_scan<W, true> take the same decisions:
+    identical clustering, tests, proposals and rounds on the same start."""
+    if mesh == "torus":
+        p, t, ind = torus
+        K, grad = 400, 1.5
+    else:
+        (p, t), ind, K, grad = spindle, None, 150, 0.0
+    res = []
+    for no_dense in ("", "1"):
+        if no_dense:
+            monkeypatch.setenv("ACVD_NO_DENSE_SCAN", "1")
+        else:
+            monkeypatch.delenv("ACVD_NO_DENSE_SCAN", raising=False)
+        g = gpu_ctx_factory()
+        g.set_mesh(p, t)
+        g.build_items("qem", grad, ind)
+        g.set_num_clusters(K)
+        g.initial_sampling()
+        rep = g.minimize(unconstrained_init=1)
+        res.append((g.clustering().copy(), rep))
+    (c0, r0), (c1, r1) = res
+    assert r0["bulk_rounds"] > 0
+    for k in ("rounds", "bulk_rounds", "tests", "proposals", "modifications", "evaluated"):
+        assert r0[k] == r1[k], k
+    assert np.array_equal(c0, c1)
+    assert r0["energy"] == r1["energy"]
