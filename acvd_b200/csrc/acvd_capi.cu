@@ -776,7 +776,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 1, stage, payload_npad(c->metric));
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    k_bulk_commit<<<grid_for((int64_t)c->V), kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric));
+    k_bulk_commit<<<grid_for((int64_t)n_tiles), kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric));
     ACVD_LAUNCH_CHECK();
     k_bulk_refresh<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->csize.p, B);
     ACVD_LAUNCH_CHECK();

@@ -556,39 +556,42 @@ __global__ void __launch_bounds__(kThreads) k_bulk_evaluate(ReassignArgs A, Bulk
 }
 
 // Applies every proposal unless its source cluster would be emptied (then all of that cluster's leavers
-// wait: the decision depends only on totals, so it is deterministic).  One thread per vertex of the rank's
-// tile range; the proposers are the set bits of the tiles' proposal masks, which are cleared on the way.
+// wait: the decision depends only on totals, so it is deterministic).  The proposers are the set bits of the
+// tiles' proposal masks: a warp reads 32 masks at a time (coalesced), clears them, and visits the non-empty tiles.
 __global__ void __launch_bounds__(kThreads) k_bulk_commit(ReassignArgs A, BulkArgs B, int stride) {
     const int K = A.K;
-    const int64_t n = (int64_t)(A.tile_end - A.tile_begin) * 32;
+    const int n_tiles = A.tile_end - A.tile_begin;
     const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned n_mods = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int tile = A.tile_begin + (int)(i >> 5);
-        const unsigned m = A.prop_mask[tile];
-        if (m == 0) continue;                                  // warp-uniform
-        if ((m >> lane) & 1u) {
-            const int v = tile * 32 + lane;
+    for (int base = warp * 32; base < n_tiles; base += n_warps * 32) {
+        const int t = A.tile_begin + base + lane;
+        const unsigned m = (base + lane < n_tiles) ? A.prop_mask[t] : 0u;
+        if (m) A.prop_mask[t] = 0;
+        unsigned nz = __ballot_sync(0xffffffffu, m != 0);
+        while (nz) {
+            const int src = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned mm = __shfl_sync(0xffffffffu, m, src);
+            if (!((mm >> lane) & 1u)) continue;
+            const int v = (A.tile_begin + base + src) * 32 + lane;
             const int d = A.prop_dst[v];
             const int a = A.cid[v];
-            if (!(a < K && B.leave_cnt[a] >= A.csize[a])) {
-                const double* it = A.items + (int64_t)v * stride;
+            if (a < K && B.leave_cnt[a] >= A.csize[a]) continue;
+            const double* it = A.items + (int64_t)v * stride;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    long long f = __double2ll_rn(__ldg(it + k) * B.scale);
-                    atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)d + k]), (unsigned long long)f);
-                    if (a < K) atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)a + k]), (unsigned long long)(-f));
-                }
-                atomicAdd(&B.join_cnt[d], 1);
-                A.mod_round[d] = A.round;
-                if (a < K) A.mod_round[a] = A.round;
-                A.cid[v] = d;
-                mark_tiles_stale(A, v);
-                n_mods++;
+            for (int k = 0; k < 4; k++) {
+                long long f = __double2ll_rn(__ldg(it + k) * B.scale);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)d + k]), (unsigned long long)f);
+                if (a < K) atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)a + k]), (unsigned long long)(-f));
             }
+            atomicAdd(&B.join_cnt[d], 1);
+            A.mod_round[d] = A.round;
+            if (a < K) A.mod_round[a] = A.round;
+            A.cid[v] = d;
+            mark_tiles_stale(A, v);
+            n_mods++;
         }
-        __syncwarp();
-        if (lane == 0) A.prop_mask[tile] = 0;
     }
     warp_count_add(&A.ctr->mods, n_mods);
 }
@@ -684,21 +687,35 @@ __global__ void __launch_bounds__(kThreads) k_apply_moves(ReassignArgs A, const 
 
 // multi-GPU bulk rounds: the rank's proposals (set bits of its tiles' masks) -> compact (vertex, destination) records
 __global__ void __launch_bounds__(kThreads) k_pack_bulk_moves(ReassignArgs A, int2* moves, unsigned long long* n_moves) {
-    const int64_t n = (int64_t)(A.tile_end - A.tile_begin) * 32;
+    const int n_tiles = A.tile_end - A.tile_begin;
     const int lane = threadIdx.x & 31;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int tile = A.tile_begin + (int)(i >> 5);
-        const unsigned m = A.prop_mask[tile];
-        if (m == 0) continue;                                  // warp-uniform
-        int base = 0;
-        if (lane == 0) base = (int)atomicAdd(n_moves, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if ((m >> lane) & 1u) {
-            const int v = tile * 32 + lane;
-            moves[base + __popc(m & ((1u << lane) - 1u))] = make_int2(v, A.prop_dst[v]);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 32; base < n_tiles; base += n_warps * 32) {
+        const int t = A.tile_begin + base + lane;
+        const unsigned m = (base + lane < n_tiles) ? A.prop_mask[t] : 0u;
+        if (m) A.prop_mask[t] = 0;
+        // exclusive prefix of the popcounts over the 32 tiles, one atomic per warp
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int slot0 = 0;
+        if (lane == 0) slot0 = (int)atomicAdd(n_moves, (unsigned long long)total);
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        const int my_off = slot0 + incl - cnt;
+        unsigned nz = __ballot_sync(0xffffffffu, m != 0);
+        while (nz) {
+            const int src = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned mm = __shfl_sync(0xffffffffu, m, src);
+            const int off = __shfl_sync(0xffffffffu, my_off, src);
+            if ((mm >> lane) & 1u) {
+                const int v = (A.tile_begin + base + src) * 32 + lane;
+                moves[off + __popc(mm & ((1u << lane) - 1u))] = make_int2(v, A.prop_dst[v]);
+            }
         }
-        __syncwarp();
-        if (lane == 0) A.prop_mask[tile] = 0;
     }
 }
 

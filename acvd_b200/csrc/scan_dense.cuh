@@ -32,15 +32,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// blocks until the phase with the given parity has completed; the suspend-time hint lets the hardware park the
+// warp instead of spinning through the issue slots the consumers need
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
     } while (!done);
 }
@@ -59,7 +61,7 @@ __device__ __forceinline__ int pick_slot(const int (&nb)[W], int k0) {
     return b;
 }
 
-// One block = 8 consumer warps + 1 producer warp; it owns a contiguous run of tiles, processed in groups of 8.
+// One block = 8 consumer warps + 1 producer warp; it owns a contiguous run of tiles, staged in groups of 8.
 // Requires: cid, xyz and weight allocated up to vpad vertices (whole tiles are copied).
 template <int W>
 __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignArgs A) {
@@ -76,7 +78,9 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignAr
     const int t1 = min(A.tile_end, t0 + chunk);
     const int n_groups = (t1 - t0 + kDenseConsumers - 1) / kDenseConsumers;
     const bool stage1 = A.bulk_stage == 1;
+    int* ticket = reinterpret_cast<int*>(smem_raw + 112);
     if (threadIdx.x == 0) {
+        *ticket = 0;
         for (int s = 0; s < kDenseStages; s++) {
             mbar_init(bar0 + 8 * s, 1);
             mbar_init(bar0 + 64 + 8 * s, kDenseConsumers);
@@ -110,38 +114,50 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignAr
         return;
     }
 
-    // ---- consumers: one tile per warp and group
+    // ---- consumers: every warp draws the next staged tile from a block-wide ticket counter, so a slow tile
+    // (many candidates, cache misses) never holds the other warps back; a stage is refilled once its 8 tiles are done
     const int K = A.K, V = A.V;
     const unsigned* __restrict__ modbits = A.modbits;
     const unsigned lane_lt = (1u << lane) - 1u;
     const bool all_dirty = A.force_all != 0;
     unsigned n_bnd = 0, n_fused = 0, n_tests = 0, n_props = 0;
-    for (int g = 0; g < n_groups; g++) {
+    const int n_tickets = n_groups * kDenseConsumers;
+    while (true) {
+        int n = 0;
+        if (lane == 0) n = atomicAdd(ticket, 1);
+        n = __shfl_sync(0xffffffffu, n, 0);
+        if (n >= n_tickets) break;
+        const int g = n / kDenseConsumers, slot = n % kDenseConsumers;
         const int s = g % kDenseStages, it = g / kDenseStages;
         mbar_wait(bar0 + 8 * s, it & 1);
-        const int tile = t0 + g * kDenseConsumers + warp;
+        const int tile = t0 + n;
         if (tile < t1) {
             const unsigned char* st = smem_raw + 128 + s * STAGE;
-            const int idx = warp * 32 + lane;
+            const int* s_cid = reinterpret_cast<const int*>(st);
+            const int idx = slot * 32 + lane;
             const int v = tile * 32 + lane;
             const bool valid = v < V;
-            const int a = valid ? reinterpret_cast<const int*>(st)[idx] : -1;
+            const int a = valid ? s_cid[idx] : -1;
             int nb[W];
 #pragma unroll
             for (int k = 0; k < W; k++) nb[k] = reinterpret_cast<const int*>(st + OFF_ELL)[k * GV + idx];
             const bool overflow_row = valid && nb[W - 1] == -2;
-            if (overflow_row) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
-            // neighbour cluster ids: from the staged group when the neighbour lies in it (v +- 1 mostly), else gathered
-            const int gv0 = (tile - warp) * 32;
-            const unsigned gvn = 32u * (unsigned)min(kDenseConsumers, t1 - (tile - warp));
+            if (__any_sync(0xffffffffu, overflow_row)) {
+                if (overflow_row) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
+            }
+            // neighbour cluster ids: from the staged group when the neighbour lies in it (v +- 1 mostly), else gathered;
+            // both loads are issued unconditionally on safe addresses (no branches around them)
+            const int gv0 = (tile - slot) * 32;
+            const unsigned gvn = 32u * (unsigned)min(kDenseConsumers, t1 - (tile - slot));
 #pragma unroll
             for (int k = 0; k < W; k++) {
                 const int j = nb[k];
                 const unsigned rel = (unsigned)(j - gv0);
-                int cj = a;                                                                 // a = no neighbour
-                if (rel < gvn) cj = reinterpret_cast<const int*>(st)[rel];
-                else if (j >= 0) cj = __ldg(A.cid + j);
-                nb[k] = cj;
+                const bool ing = rel < gvn;
+                const bool glob = !ing && j >= 0;
+                const int cs = s_cid[ing ? rel : 0u];
+                const int cg = __ldg(A.cid + (glob ? j : 0));
+                nb[k] = ing ? cs : (glob ? cg : a);                                         // a = no neighbour
             }
             // classification, branch-free: rem = slots holding a foreign assigned cluster
             unsigned rem = 0, dirty = all_dirty ? 1u : 0u;
