@@ -82,6 +82,7 @@ SYMBOLS = [
     ("acvd_boundary_flags", C.c_int, [_vp, _vp]),
     ("acvd_cluster_adjacency", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     ("acvd_dual_triangles", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    ("acvd_bench_kernel", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("acvd_dist_unique_id", C.c_int, [_vp]),
     ("acvd_dist_init", C.c_int, [_vp, C.c_int, C.c_int, _vp]),
 ]
@@ -285,6 +286,12 @@ class Context:
         return out
 
     # ---- multi-GPU
+    def bench_kernel(self, kernel=0, variant=0, stage=0, reps=20) -> float:
+        """ms per launch of one kernel on the current state (CUDA events on the library stream)."""
+        ms = C.c_float()
+        self._ck(self.L.acvd_bench_kernel(self.h, kernel, variant, stage, reps, C.byref(ms)))
+        return float(ms.value)
+
     @staticmethod
     def dist_unique_id() -> bytes:
         L = load_library()

@@ -489,7 +489,10 @@ static int clean_clustering(acvd_ctx* c) {
     TraceScope ts(c, "clean_clustering");
     const int V = c->V, K = c->K;
     c->label.alloc(V); c->comp_size.alloc(V); c->n_comp.alloc(K); c->winner.alloc(K);
-    k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->label.p);
+    if (c->ell_w == 6)
+        k_cc_init<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
+    else
+        k_cc_init<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
     ACVD_LAUNCH_CHECK();
     if (c->ell_w == 6)
         k_cc_hook<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
@@ -598,22 +601,36 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     return A;
 }
 
-// dense bulk rounds: the TMA-staged streaming scan (scan_dense.cuh), one wave of 4 blocks per SM
-template <int W>
+// dense bulk rounds: the TMA-staged streaming scan (scan_dense.cuh), one wave of MINB blocks per SM
+template <int W, int S, int MINB>
 static void launch_scan_bulk_dense(acvd_ctx* c, const ReassignArgs& A) {
     static bool configured = false;
     if (!configured) {
-        ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W)));
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense<W, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W, S)));
         configured = true;
     }
     const int n_tiles = A.tile_end - A.tile_begin;
-    const int grid = std::max(1, std::min(kNumSMs * 4, (n_tiles + kDenseConsumers - 1) / kDenseConsumers));
-    k_scan_bulk_dense<W><<<grid, kDenseThreads, dense_smem_bytes(W), c->stream>>>(A);
+    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
+    k_scan_bulk_dense<W, S, MINB><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
+}
+// (stages, blocks per SM) variants kept for the kernel micro-benchmark (acvd_bench_kernel); variant 0 is the product default
+static int g_dense_variant = getenv("ACVD_DENSE_VARIANT") ? atoi(getenv("ACVD_DENSE_VARIANT")) : 0;
+template <int W>
+static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, int variant) {
+    switch (variant) {
+        case 1: launch_scan_bulk_dense<W, 2, 4>(c, A); break;
+        case 2: launch_scan_bulk_dense<W, 4, 4>(c, A); break;
+        case 3: launch_scan_bulk_dense<W, 2, 5>(c, A); break;
+        case 4: launch_scan_bulk_dense<W, 3, 5>(c, A); break;
+        case 5: launch_scan_bulk_dense<W, 2, 6>(c, A); break;
+        case 6: launch_scan_bulk_dense<W, 3, 3>(c, A); break;
+        default: launch_scan_bulk_dense<W, 3, 4>(c, A); break;
+    }
 }
 
 static void launch_scan(acvd_ctx* c, const ReassignArgs& A, int grid) {
     if (A.bulk && A.all_tiles && A.sig_mode == 1 && !getenv("ACVD_NO_DENSE_SCAN")) {
-        if (c->ell_w == 6) launch_scan_bulk_dense<6>(c, A); else launch_scan_bulk_dense<8>(c, A);
+        if (c->ell_w == 6) launch_scan_bulk_dense_variant<6>(c, A, g_dense_variant); else launch_scan_bulk_dense_variant<8>(c, A, g_dense_variant);
         return;
     }
     if (A.bulk) {
@@ -1065,6 +1082,51 @@ extern "C" int acvd_representative_points(acvd_ctx* c, int32_t n, const double* 
     ACVD_CUDA(cudaMemcpyAsync(P3, p.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (rank_def) ACVD_CUDA(cudaMemcpyAsync(rank_def, rd.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel micro-benchmark: times `reps` back-to-back launches of one kernel on the current state (CUDA events on the
+// library stream).  kernel 0: dense bulk scan, `variant` = (stages, blocks/SM) variant, -1 = the list-based k_scan;
+// stage = bulk stage (0 Lloyd, 1 delta-E).  The state must come from a few bulk rounds (acvd_minimize with
+// max_loops set): proposals are overwritten, nothing is committed.
+extern "C" int acvd_bench_kernel(acvd_ctx* c, int kernel, int variant, int stage, int reps, float* ms_per_launch) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !c->have_items || kernel != 0 || reps <= 0 || !ms_per_launch) throw std::runtime_error("acvd_bench_kernel: bad arguments");
+    if (c->metric != M_ISO && c->metric != M_QEM) throw std::runtime_error("acvd_bench_kernel: bulk scan needs the isotropic or QEM metric");
+    ensure_fx_scale(c);
+    if (!c->stats_valid) recompute_statistics(c, 0, 0, 0);
+    bulk_init(c);
+    EvalCfg cfg = make_cfg(0, 0, 0);
+    ReassignArgs A = make_args(c, cfg, 0, 0);
+    A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 1;
+    A.all_tiles = 1; A.sig_mode = 1; A.tile_begin = 0; A.tile_end = (c->V + 31) / 32;
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, 0, c->modbits.p);
+    ACVD_LAUNCH_CHECK();
+    const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS);
+    cudaEvent_t e0, e1;
+    ACVD_CUDA(cudaEventCreate(&e0));
+    ACVD_CUDA(cudaEventCreate(&e1));
+    for (int r = -2; r < reps; r++) {          // two warm-up launches
+        if (r == 0) ACVD_CUDA(cudaEventRecord(e0, c->stream));
+        ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
+        if (variant < 0) {
+            if (c->ell_w == 6) k_scan<6, true><<<gs, kThreads, 0, c->stream>>>(A); else k_scan<8, true><<<gs, kThreads, 0, c->stream>>>(A);
+        } else if (c->ell_w == 6) launch_scan_bulk_dense_variant<6>(c, A, variant);
+        else launch_scan_bulk_dense_variant<8>(c, A, variant);
+        ACVD_LAUNCH_CHECK();
+    }
+    ACVD_CUDA(cudaEventRecord(e1, c->stream));
+    ACVD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    ACVD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ACVD_CUDA(cudaMemsetAsync(c->prop_mask.p, 0, (size_t)((c->V + 31) / 32) * sizeof(unsigned), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->leave_cnt.p, 0, (size_t)c->K * sizeof(int), c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats_valid = false;
     ACVD_API_END(c)
 }
 

@@ -99,6 +99,36 @@ __device__ __forceinline__ void cc_union(int* label, int u, int v) {
     }
 }
 
+// Initial forest without atomics (the first step of ECL-CC): every vertex points at its smallest same-cluster
+// neighbour with a smaller id, or at itself.  parent <= self everywhere and every link is a real same-cluster edge,
+// so the hooking pass that follows only has to join the few trees this leaves per cluster.
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_cc_init(int V, int K, int64_t vpad, const int* __restrict__ ell,
+                                                      const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                                      const int* __restrict__ cid, int* label) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const int c = cid[v];
+        int best = v;
+        if (c < K) {
+            int nb[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);
+            const bool overflow = nb[W - 1] == -2;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const int u = nb[k];
+                if (u >= 0 && u < best && cid[u] == c) best = u;
+            }
+            if (overflow)
+                for (int e = row_ptr[v] + W - 1; e < row_ptr[v + 1]; e++) {
+                    const int u = col[e];
+                    if (u < best && cid[u] == c) best = u;
+                }
+        }
+        label[v] = best;
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(kThreads) k_cc_hook(int V, int K, int64_t vpad, const int* __restrict__ ell,
                                                       const int* __restrict__ row_ptr, const int* __restrict__ col,

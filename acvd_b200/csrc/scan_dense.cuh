@@ -4,23 +4,26 @@
 // Same per-vertex work as k_scan<W, true> (reassign.cuh) -- the candidate set of the reference's ProcessOneLoop
 // (Common/vtkUniformClustering.h:833-995) over the boundary vertices, decided with the bulk criterion -- but the
 // four streams a tile needs (cluster ids, the W ELL columns, positions, and in stage 1 the item weights) are
-// contiguous over a run of tiles, so a producer warp moves them global -> shared with cp.async.bulk (the TMA
-// engine, completion on an mbarrier) several groups ahead of the eight consumer warps.  What is left on a
-// consumer's critical path are the gathers that hit L1/L2 (neighbour cluster ids, modified bits, centroids).
-// The scan writes one 32-bit proposal mask per tile instead of appending to a list: no atomics on the path,
-// and the order of the proposals is fixed.
+// contiguous over a run of tiles, so they are moved global -> shared by the TMA engine (cp.async.bulk, completion
+// on an mbarrier) in groups of 8 tiles, kept S groups ahead of the warps.  What is left on a warp's critical path
+// are the gathers that hit L1/L2 (neighbour cluster ids, modified bits, centroids).
+//   * every warp draws the next staged tile from a block-wide ticket counter, so a slow tile never holds the
+//     other warps back;
+//   * the warp that finishes the last tile of a group refills that stage itself (no producer warp, no "empty"
+//     barrier to poll);
+//   * the scan writes one 32-bit proposal mask per tile instead of appending to a list: no atomics on the path,
+//     and the order of the proposals is fixed.
 #pragma once
 #include "reassign_types.cuh"
 
 namespace acvd {
 
-constexpr int kDenseConsumers = 8;                        // consumer warps per block = tiles per group
-constexpr int kDenseThreads = 32 * (kDenseConsumers + 1); // + one producer warp
-constexpr int kDenseStages = 3;                           // groups in flight per block (3 x 12 KB: leaves ~100 KB of L1 per SM)
-constexpr int kDenseGroupV = 32 * kDenseConsumers;        // vertices per group
+constexpr int kDenseWarps = 8;                            // warps per block = tiles per staged group
+constexpr int kDenseThreads = 32 * kDenseWarps;
+constexpr int kDenseGroupV = 32 * kDenseWarps;            // vertices per group
 
 __host__ __device__ constexpr int dense_stage_bytes(int W) { return kDenseGroupV * (4 + 4 * W + 12 + 8); }
-__host__ __device__ constexpr int dense_smem_bytes(int W) { return 128 + kDenseStages * dense_stage_bytes(W); }
+__host__ __device__ constexpr int dense_smem_bytes(int W, int S) { return 128 + S * dense_stage_bytes(W); }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -61,74 +64,69 @@ __device__ __forceinline__ int pick_slot(const int (&nb)[W], int k0) {
     return b;
 }
 
-// One block = 8 consumer warps + 1 producer warp; it owns a contiguous run of tiles, staged in groups of 8.
+// One block owns a contiguous run of tiles, staged in groups of 8.  S = stages (groups in flight per block),
+// MINB = resident blocks per SM the register budget is sized for.
 // Requires: cid, xyz and weight allocated up to vpad vertices (whole tiles are copied).
-template <int W>
-__global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignArgs A) {
+template <int W, int S, int MINB>
+__global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(ReassignArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GV = kDenseGroupV;
     constexpr int STAGE = dense_stage_bytes(W);
     constexpr int OFF_ELL = 4 * GV, OFF_XYZ = OFF_ELL + 4 * W * GV, OFF_WGT = OFF_XYZ + 12 * GV;
-    const uint32_t bar0 = smem_addr(smem_raw);            // full[s] at +8 s, empty[s] at +64 + 8 s
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // control words: full[s] mbarriers at +8 s, per-stage done counters at +64 + 4 s, ticket at +112
+    const uint32_t bar0 = smem_addr(smem_raw);
+    int* done_cnt = reinterpret_cast<int*>(smem_raw + 64);
+    int* ticket = reinterpret_cast<int*>(smem_raw + 112);
+    const int lane = threadIdx.x & 31;
     const int n_tiles = A.tile_end - A.tile_begin;
     int chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
-    chunk = (chunk + kDenseConsumers - 1) / kDenseConsumers * kDenseConsumers;
+    chunk = (chunk + kDenseWarps - 1) / kDenseWarps * kDenseWarps;
     const int t0 = min(A.tile_end, A.tile_begin + (int)blockIdx.x * chunk);
     const int t1 = min(A.tile_end, t0 + chunk);
-    const int n_groups = (t1 - t0 + kDenseConsumers - 1) / kDenseConsumers;
+    const int n_groups = (t1 - t0 + kDenseWarps - 1) / kDenseWarps;
     const bool stage1 = A.bulk_stage == 1;
-    int* ticket = reinterpret_cast<int*>(smem_raw + 112);
+
+    // stage group g (tiles t0 + 8 g ...) into its slot: one elected thread arms the barrier and issues the copies
+    auto issue_group = [&](int g) {
+        uint64_t pol_stream, pol_keep;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+        const int s = g % S;
+        const int tile = t0 + g * kDenseWarps;
+        const uint32_t nv = 32u * (uint32_t)min(kDenseWarps, t1 - tile);
+        const int64_t v0 = (int64_t)tile * 32;
+        const uint32_t full = bar0 + 8 * s;
+        const uint32_t dst = bar0 + 128 + s * STAGE;
+        mbar_expect_tx(full, nv * (4u + 4u * W + 12u + (stage1 ? 8u : 0u)));
+        bulk_g2s(dst, A.cid + v0, 4 * nv, full, pol_keep);
+#pragma unroll
+        for (int k = 0; k < W; k++) bulk_g2s(dst + OFF_ELL + 4 * GV * k, A.ell + (int64_t)k * A.vpad + v0, 4 * nv, full, pol_stream);
+        bulk_g2s(dst + OFF_XYZ, A.xyz + 3 * v0, 12 * nv, full, pol_stream);
+        if (stage1) bulk_g2s(dst + OFF_WGT, A.weight + v0, 8 * nv, full, pol_stream);
+    };
+
     if (threadIdx.x == 0) {
         *ticket = 0;
-        for (int s = 0; s < kDenseStages; s++) {
-            mbar_init(bar0 + 8 * s, 1);
-            mbar_init(bar0 + 64 + 8 * s, kDenseConsumers);
-        }
+        for (int s = 0; s < S; s++) { mbar_init(bar0 + 8 * s, 1); done_cnt[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int g = 0; g < S && g < n_groups; g++) issue_group(g);
     }
     __syncthreads();
 
-    if (warp == kDenseConsumers) {
-        // ---- producer: keeps kDenseStages groups in flight
-        if (lane == 0) {
-            uint64_t pol_stream, pol_keep;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-            asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-            for (int g = 0; g < n_groups; g++) {
-                const int s = g % kDenseStages, it = g / kDenseStages;
-                if (it > 0) mbar_wait(bar0 + 64 + 8 * s, (it - 1) & 1);
-                const int tile = t0 + g * kDenseConsumers;
-                const uint32_t nv = 32u * (uint32_t)min(kDenseConsumers, t1 - tile);
-                const int64_t v0 = (int64_t)tile * 32;
-                const uint32_t full = bar0 + 8 * s;
-                const uint32_t dst = smem_addr(smem_raw + 128 + s * STAGE);
-                mbar_expect_tx(full, nv * (4u + 4u * W + 12u + (stage1 ? 8u : 0u)));
-                bulk_g2s(dst, A.cid + v0, 4 * nv, full, pol_keep);
-#pragma unroll
-                for (int k = 0; k < W; k++) bulk_g2s(dst + OFF_ELL + 4 * GV * k, A.ell + (int64_t)k * A.vpad + v0, 4 * nv, full, pol_stream);
-                bulk_g2s(dst + OFF_XYZ, A.xyz + 3 * v0, 12 * nv, full, pol_stream);
-                if (stage1) bulk_g2s(dst + OFF_WGT, A.weight + v0, 8 * nv, full, pol_stream);
-            }
-        }
-        return;
-    }
-
-    // ---- consumers: every warp draws the next staged tile from a block-wide ticket counter, so a slow tile
-    // (many candidates, cache misses) never holds the other warps back; a stage is refilled once its 8 tiles are done
     const int K = A.K, V = A.V;
     const unsigned* __restrict__ modbits = A.modbits;
     const unsigned lane_lt = (1u << lane) - 1u;
     const bool all_dirty = A.force_all != 0;
     unsigned n_bnd = 0, n_fused = 0, n_tests = 0, n_props = 0;
-    const int n_tickets = n_groups * kDenseConsumers;
+    const int n_tickets = n_groups * kDenseWarps;
     while (true) {
         int n = 0;
         if (lane == 0) n = atomicAdd(ticket, 1);
         n = __shfl_sync(0xffffffffu, n, 0);
         if (n >= n_tickets) break;
-        const int g = n / kDenseConsumers, slot = n % kDenseConsumers;
-        const int s = g % kDenseStages, it = g / kDenseStages;
+        const int g = n / kDenseWarps, slot = n % kDenseWarps;
+        const int s = g % S, it = g / S;
         mbar_wait(bar0 + 8 * s, it & 1);
         const int tile = t0 + n;
         if (tile < t1) {
@@ -142,13 +140,14 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignAr
 #pragma unroll
             for (int k = 0; k < W; k++) nb[k] = reinterpret_cast<const int*>(st + OFF_ELL)[k * GV + idx];
             const bool overflow_row = valid && nb[W - 1] == -2;
-            if (__any_sync(0xffffffffu, overflow_row)) {
+            const bool any_overflow = __any_sync(0xffffffffu, overflow_row);
+            if (any_overflow) {
                 if (overflow_row) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
             }
             // neighbour cluster ids: from the staged group when the neighbour lies in it (v +- 1 mostly), else gathered;
             // both loads are issued unconditionally on safe addresses (no branches around them)
             const int gv0 = (tile - slot) * 32;
-            const unsigned gvn = 32u * (unsigned)min(kDenseConsumers, t1 - (tile - slot));
+            const unsigned gvn = 32u * (unsigned)min(kDenseWarps, t1 - (tile - slot));
 #pragma unroll
             for (int k = 0; k < W; k++) {
                 const int j = nb[k];
@@ -159,22 +158,18 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignAr
                 const int cg = __ldg(A.cid + (glob ? j : 0));
                 nb[k] = ing ? cs : (glob ? cg : a);                                         // a = no neighbour
             }
-            // classification, branch-free: rem = slots holding a foreign assigned cluster
-            unsigned rem = 0, dirty = all_dirty ? 1u : 0u;
+            // rem = slots holding a foreign assigned cluster (the candidates); boundary = any foreign neighbour
+            unsigned rem = 0;
             bool bnd = false;
 #pragma unroll
             for (int k = 0; k < W; k++) {
-                const int bb = nb[k];
-                const bool isb = bb != a;
-                const bool asg = isb && (unsigned)bb < (unsigned)K;
+                const bool isb = nb[k] != a;
                 bnd |= isb;
-                rem |= (asg ? 1u : 0u) << k;
-                if (!all_dirty) {
-                    const int c = asg ? bb : 0;
-                    dirty |= (modbits[c >> 5] >> (c & 31)) & (asg ? 1u : 0u);
-                }
+                rem |= ((isb && (unsigned)nb[k] < (unsigned)K) ? 1u : 0u) << k;
             }
-            if (__any_sync(0xffffffffu, overflow_row)) {        // finish long rows from the CSR, warp-uniformly
+            // "recently modified" rule (:909-920): own cluster now, candidate clusters inside the candidate loop
+            unsigned dirty = all_dirty ? 1u : 0u;
+            if (any_overflow) {        // finish long rows from the CSR, warp-uniformly (their decision is k_bulk_evaluate's)
                 const int e0 = overflow_row ? A.row_ptr[v] + W : 0, e1 = overflow_row ? A.row_ptr[v + 1] : 0;
                 const int steps = __reduce_max_sync(0xffffffffu, e1 - e0);
                 for (int q = 0; q < steps; q++) {
@@ -186,42 +181,56 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignAr
             }
             bnd = bnd && valid;
             n_bnd += bnd ? 1u : 0u;
-            if (!all_dirty) {
-                const int c = (bnd && a < K) ? a : 0;
-                dirty |= (modbits[c >> 5] >> (c & 31)) & ((bnd && a < K) ? 1u : 0u);
-            }
-            const bool work = bnd && dirty != 0;
-            const bool fused = work && !overflow_row;
-            // ---- bulk decision for the fused lanes, candidates in slot order (first occurrence of every cluster)
+            const bool cand = bnd && !overflow_row;      // decided here if dirty
             int best_b = -1;
-            if (__any_sync(0xffffffffu, fused)) {
+            if (__any_sync(0xffffffffu, bnd)) {
                 double px = 0, py = 0, pz = 0, best = 0, w = 0;
                 bool blocked = true;
-                if (!fused) rem = 0;
-                else {
-                    n_fused++;
-                    if (a >= K) {   // NULL cluster: adopt the first assigned neighbour cluster
-                        if (rem) best_b = pick_slot<W>(nb, __ffs(rem) - 1);
-                        rem = 0;
-                    } else {
-                        const float* xs = reinterpret_cast<const float*>(st + OFF_XYZ) + 3 * idx;
-                        px = xs[0]; py = xs[1]; pz = xs[2];
-                        blocked = A.csize[a] == 1;
-                        const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)a);
-                        const double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
-                        best = dx * dx + dy * dy + dz * dz;
-                        if (stage1) {
-                            w = reinterpret_cast<const double*>(st + OFF_WGT)[idx];
-                            best = ca.w / (ca.w - w) * best;
+                unsigned ntest = 0;
+                const bool own = bnd && a < K;
+                {
+                    const int c = own ? a : 0;
+                    dirty |= (modbits[c >> 5] >> (c & 31)) & (own ? 1u : 0u);
+                }
+                if (!cand) {
+                    if (overflow_row && !all_dirty) {    // long row: only the dirty flag of the first W slots is still missing
+                        while (rem) {
+                            const int b = pick_slot<W>(nb, __ffs(rem) - 1);
+                            rem &= rem - 1;
+                            dirty |= (modbits[b >> 5] >> (b & 31)) & 1u;
                         }
                     }
+                    rem = 0;
+                } else if (a >= K) {   // NULL cluster: adopt the first assigned neighbour cluster; dirty if any neighbour cluster is
+                    if (rem) best_b = pick_slot<W>(nb, __ffs(rem) - 1);
+                    if (!all_dirty) {
+                        while (rem) {
+                            const int b = pick_slot<W>(nb, __ffs(rem) - 1);
+                            rem &= rem - 1;
+                            dirty |= (modbits[b >> 5] >> (b & 31)) & 1u;
+                        }
+                    }
+                    rem = 0;
+                } else {
+                    const float* xs = reinterpret_cast<const float*>(st + OFF_XYZ) + 3 * idx;
+                    px = xs[0]; py = xs[1]; pz = xs[2];
+                    blocked = A.csize[a] == 1;
+                    const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)a);
+                    const double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
+                    best = dx * dx + dy * dy + dz * dz;
+                    if (stage1) {
+                        w = reinterpret_cast<const double*>(st + OFF_WGT)[idx];
+                        best = ca.w / (ca.w - w) * best;
+                    }
                 }
+                // candidates in slot order (first occurrence of every distinct cluster)
                 while (__any_sync(0xffffffffu, rem != 0)) {
                     if (rem) {
                         const int b = pick_slot<W>(nb, __ffs(rem) - 1);
 #pragma unroll
                         for (int k = 0; k < W; k++) rem &= ~((nb[k] == b ? 1u : 0u) << k);
-                        n_tests++;
+                        ntest++;
+                        dirty |= (modbits[b >> 5] >> (b & 31)) & 1u;
                         if (!blocked) {
                             const double4 cb = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)b);
                             const double dx = px - cb.x, dy = py - cb.y, dz = pz - cb.z;
@@ -231,6 +240,9 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignAr
                         }
                     }
                 }
+                // a vertex none of whose clusters changed keeps its earlier outcome: it is neither counted nor proposed
+                if (!(cand && dirty)) best_b = -1;
+                else { n_fused++; n_tests += ntest; }
                 if (best_b >= 0) {
                     A.prop_dst[v] = best_b;
                     if (a < K && A.bulk_count_leave) atomicAdd(&A.bulk_leave[a], 1);
@@ -239,16 +251,29 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_scan_bulk_dense(ReassignAr
             const unsigned mp = __ballot_sync(0xffffffffu, best_b >= 0);
             if (lane == 0) { A.prop_mask[tile] = mp; n_props += __popc(mp); }
             // rows longer than W (rare) are decided by k_bulk_evaluate from the work list
-            const unsigned mw = __ballot_sync(0xffffffffu, work && overflow_row);
-            if (mw) {
-                int basew = 0;
-                if (lane == 0) basew = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)__popc(mw));
-                basew = __shfl_sync(0xffffffffu, basew, 0);
-                if (work && overflow_row) A.work[basew + __popc(mw & lane_lt)] = v;
+            if (any_overflow) {
+                const bool ow = bnd && overflow_row && dirty != 0;
+                const unsigned mw = __ballot_sync(0xffffffffu, ow);
+                if (mw) {
+                    int basew = 0;
+                    if (lane == 0) basew = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)__popc(mw));
+                    basew = __shfl_sync(0xffffffffu, basew, 0);
+                    if (ow) A.work[basew + __popc(mw & lane_lt)] = v;
+                }
             }
         }
+        // the warp that finishes the last tile of the group refills the stage with the group S ahead
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 64 + 8 * s);
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&done_cnt[s], 1) == kDenseWarps - 1) {
+                done_cnt[s] = 0;
+                if (g + S < n_groups) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue_group(g + S);
+                }
+            }
+        }
     }
     warp_count_add(&A.ctr->boundary, n_bnd);
     warp_count_add(&A.ctr->pad[0], n_fused);

@@ -160,6 +160,12 @@ int acvd_cluster_adjacency(acvd_ctx* ctx, int64_t* out, int64_t cap, int64_t* n)
 /* dual-mesh triangles in first-occurrence order over input faces; out=NULL queries the count */
 int acvd_dual_triangles(acvd_ctx* ctx, int32_t* out /*3*cap*/, int64_t cap, int64_t* n);
 
+/* ---- measurement hook ---------------------------------------------------------------------- */
+/* Times `reps` back-to-back launches of one kernel on the current state with CUDA events on the library's
+ * stream (scripts/bench_kernels.py).  kernel 0 = dense bulk scan of the reassignment loop; variant >= 0 selects a
+ * (stages, blocks/SM) instantiation of the TMA-staged kernel, -1 the list-based scan; stage = bulk stage. */
+int acvd_bench_kernel(acvd_ctx* ctx, int kernel, int variant, int stage, int reps, float* ms_per_launch);
+
 /* ---- multi-GPU (one process per GPU; vertex-range partition) ------------------ */
 #define ACVD_NCCL_ID_BYTES 128
 int acvd_dist_unique_id(void* id_out /*ACVD_NCCL_ID_BYTES*/);
