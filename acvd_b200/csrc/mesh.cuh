@@ -170,14 +170,14 @@ __global__ void k_pack_rows(int64_t n, int np, int npad, const double* __restric
     }
 }
 
-// ELL copy of the adjacency for the frontier scan: column-major, ell[k * vpad + v] = k-th neighbour of v, -1 when
+// ELL copy of the adjacency for the frontier scan: column-major, ell[k * vpad + v] = k-th neighbour of v, v itself when
 // the row is shorter, and -2 in the last column when the row is longer than W (the scan then finishes the row
 // from the CSR).  Thread v reads ell[k * vpad + v]: every load of a warp is one coalesced 128-byte line.
 __global__ void k_build_ell(int V, int64_t vpad, int W, const int* __restrict__ row_ptr, const int* __restrict__ col, int* ell) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vpad; v += gridDim.x * blockDim.x) {
         const int beg = v < V ? row_ptr[v] : 0, deg = v < V ? row_ptr[v + 1] - beg : 0;
         for (int k = 0; k < W; k++) {
-            int val = k < deg ? col[beg + k] : -1;
+            int val = k < deg ? col[beg + k] : (v < V ? v : 0);   // short rows are padded with the vertex itself
             if (k == W - 1 && deg > W) val = -2;
             ell[(int64_t)k * vpad + v] = val;
         }

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(ReassignArgs A) {
         const bool overflow_row = nb[W - 1] == -2;
         if (overflow_row) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
 #pragma unroll
-        for (int k = 0; k < W; k++) nb[k] = nb[k] >= 0 ? A.cid[nb[k]] : a;            // neighbour cluster ids (a = no neighbour)
+        for (int k = 0; k < W; k++) nb[k] = valid ? A.cid[nb[k]] : a;               // neighbour cluster ids (short rows are padded with v itself)
         // the signature is rebuilt only when a vertex in / next to the tile moved since it was recorded
         const bool rebuild = A.sig_mode == 2 || (A.sig_mode == 0 && (A.force_all || A.tile_stale[tile]));
         bool sig_overflow = false;

@@ -136,28 +136,24 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
             const int v = tile * 32 + lane;
             const bool valid = v < V;
             const int a = valid ? s_cid[idx] : -1;
+            // own cluster's size, centroid and modified bit are needed by every boundary vertex: issued now, they
+            // travel together with the neighbour gathers instead of after them
+            const int ac = (unsigned)a < (unsigned)K ? a : 0;
+            const int a_size = __ldg(A.csize + ac);
+            const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)ac);
+            const unsigned a_mod = all_dirty ? 1u : (modbits[ac >> 5] >> (ac & 31)) & 1u;
             int nb[W];
 #pragma unroll
             for (int k = 0; k < W; k++) nb[k] = reinterpret_cast<const int*>(st + OFF_ELL)[k * GV + idx];
             const bool overflow_row = valid && nb[W - 1] == -2;
-            const bool any_overflow = __any_sync(0xffffffffu, overflow_row);
+            const bool any_overflow = __any_sync(0xffffffffu, nb[W - 1] == -2);
             if (any_overflow) {
                 if (overflow_row) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
+                else if (nb[W - 1] == -2) nb[W - 1] = 0;
             }
-            // neighbour cluster ids: from the staged group when the neighbour lies in it (v +- 1 mostly), else gathered;
-            // both loads are issued unconditionally on safe addresses (no branches around them)
-            const int gv0 = (tile - slot) * 32;
-            const unsigned gvn = 32u * (unsigned)min(kDenseWarps, t1 - (tile - slot));
+            // neighbour cluster ids: the ELL pads short rows with the vertex itself, so every slot is a valid index
 #pragma unroll
-            for (int k = 0; k < W; k++) {
-                const int j = nb[k];
-                const unsigned rel = (unsigned)(j - gv0);
-                const bool ing = rel < gvn;
-                const bool glob = !ing && j >= 0;
-                const int cs = s_cid[ing ? rel : 0u];
-                const int cg = __ldg(A.cid + (glob ? j : 0));
-                nb[k] = ing ? cs : (glob ? cg : a);                                         // a = no neighbour
-            }
+            for (int k = 0; k < W; k++) nb[k] = __ldg(A.cid + nb[k]);
             // rem = slots holding a foreign assigned cluster (the candidates); boundary = any foreign neighbour
             unsigned rem = 0;
             bool bnd = false;
@@ -167,6 +163,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
                 bnd |= isb;
                 rem |= ((isb && (unsigned)nb[k] < (unsigned)K) ? 1u : 0u) << k;
             }
+            if (!valid) { rem = 0; bnd = false; }
             // "recently modified" rule (:909-920): own cluster now, candidate clusters inside the candidate loop
             unsigned dirty = all_dirty ? 1u : 0u;
             if (any_overflow) {        // finish long rows from the CSR, warp-uniformly (their decision is k_bulk_evaluate's)
@@ -187,11 +184,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
                 double px = 0, py = 0, pz = 0, best = 0, w = 0;
                 bool blocked = true;
                 unsigned ntest = 0;
-                const bool own = bnd && a < K;
-                {
-                    const int c = own ? a : 0;
-                    dirty |= (modbits[c >> 5] >> (c & 31)) & (own ? 1u : 0u);
-                }
+                if (bnd && a < K) dirty |= a_mod;
                 if (!cand) {
                     if (overflow_row && !all_dirty) {    // long row: only the dirty flag of the first W slots is still missing
                         while (rem) {
@@ -214,8 +207,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
                 } else {
                     const float* xs = reinterpret_cast<const float*>(st + OFF_XYZ) + 3 * idx;
                     px = xs[0]; py = xs[1]; pz = xs[2];
-                    blocked = A.csize[a] == 1;
-                    const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)a);
+                    blocked = a_size == 1;
                     const double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
                     best = dx * dx + dy * dy + dz * dz;
                     if (stage1) {
@@ -245,7 +237,8 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
                 else { n_fused++; n_tests += ntest; }
                 if (best_b >= 0) {
                     A.prop_dst[v] = best_b;
-                    if (a < K && A.bulk_count_leave) atomicAdd(&A.bulk_leave[a], 1);
+                    // plain RED: the compiler's warp-aggregation loop around atomicAdd costs more than the atomics it saves
+                    if (a < K && A.bulk_count_leave) asm volatile("red.global.add.s32 [%0], 1;" ::"l"(A.bulk_leave + a) : "memory");
                 }
             }
             const unsigned mp = __ballot_sync(0xffffffffu, best_b >= 0);
