@@ -175,10 +175,15 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
         ACVD_CUDA(cudaMemcpyAsync(&max_deg, d_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
         c->ell_w = max_deg <= 6 ? 6 : 8;
+        c->max_deg = max_deg;
         c->ell.alloc((size_t)c->ell_w * c->vpad);
         k_build_ell<<<grid_for(c->vpad), kThreads, 0, c->stream>>>(V, c->vpad, c->ell_w, c->row_ptr.p, c->col.p, c->ell.p);
         ACVD_LAUNCH_CHECK();
     }
+    // --- ring adjacency matrices for the connexity predicate of k_evaluate
+    c->ringadj.alloc((size_t)V);
+    k_build_ringadj<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->row_ptr.p, c->col.p, c->ringadj.p);
+    ACVD_LAUNCH_CHECK();
     // --- vertex -> face incidence (ascending face id per vertex)
     {
         int64_t n = 3 * (int64_t)F;
@@ -579,7 +584,7 @@ struct RoundResult { unsigned long long proposals, mods, tests, evaluated, bound
 static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all) {
     ReassignArgs A;
     A.V = c->V; A.K = c->K;
-    A.row_ptr = c->row_ptr.p; A.col = c->col.p; A.ell = c->ell.p; A.vpad = c->vpad; A.cid = c->cid.p;
+    A.row_ptr = c->row_ptr.p; A.col = c->col.p; A.ell = c->ell.p; A.ringadj = c->ringadj.p; A.vpad = c->vpad; A.cid = c->cid.p;
     A.items = c->items.p; A.csum = c->csum.p; A.cenergy = c->cenergy.p; A.csize = c->csize.p;
     A.mod_round = c->mod_round.p;
     A.modbits = c->modbits.p;
@@ -661,6 +666,28 @@ static void update_density(acvd_ctx* c, RoundResult& r) {
     } else c->dense_next = (double)r.active_tiles > 0.6 * (double)(((int64_t)c->V + 31) / 32);
 }
 
+// candidate evaluation of the work list: ring-in-registers kernel, plus the per-slot kernel when the mesh has rows
+// longer than kRingW
+static void launch_evaluate(acvd_ctx* c, const ReassignArgs& A, bool as_iso, int ge) {
+#define ACVD_EVAL(KERNEL)                                                                          \
+    switch (c->metric) {                                                                           \
+        case M_ISO: KERNEL<M_ISO, 4><<<ge, kThreads, 0, c->stream>>>(A); break;                    \
+        case M_QEM:                                                                                \
+            if (as_iso) KERNEL<M_ISO, 14><<<ge, kThreads, 0, c->stream>>>(A);                      \
+            else KERNEL<M_QEM, 14><<<ge, kThreads, 0, c->stream>>>(A);                             \
+            break;                                                                                 \
+        case M_ANISO: KERNEL<M_ANISO, 14><<<ge, kThreads, 0, c->stream>>>(A); break;               \
+        default: KERNEL<M_ANISOQ, 22><<<ge, kThreads, 0, c->stream>>>(A); break;                   \
+    }
+    ACVD_EVAL(k_evaluate)
+    ACVD_LAUNCH_CHECK();
+    if (c->max_deg > kRingW) {
+        ACVD_EVAL(k_evaluate_long)
+        ACVD_LAUNCH_CHECK();
+    }
+#undef ACVD_EVAL
+}
+
 static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso) {
     // proposals of the previous round become the carry list (none survive a phase start: everything is dirty)
     if (force_all) ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p + 1, 0, sizeof(unsigned long long), c->stream));
@@ -688,16 +715,7 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
         ACVD_LAUNCH_CHECK();
     }
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    switch (c->metric) {
-        case M_ISO: k_evaluate<M_ISO, 4><<<ge, kThreads, 0, c->stream>>>(A); break;
-        case M_QEM:
-            if (as_iso) k_evaluate<M_ISO, 14><<<ge, kThreads, 0, c->stream>>>(A);
-            else k_evaluate<M_QEM, 14><<<ge, kThreads, 0, c->stream>>>(A);
-            break;
-        case M_ANISO: k_evaluate<M_ANISO, 14><<<ge, kThreads, 0, c->stream>>>(A); break;
-        default: k_evaluate<M_ANISOQ, 22><<<ge, kThreads, 0, c->stream>>>(A); break;
-    }
-    ACVD_LAUNCH_CHECK();
+    launch_evaluate(c, A, as_iso, ge);
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     for (int pass = 0; pass < c->commit_passes; pass++) {
         if (pass > 0) {

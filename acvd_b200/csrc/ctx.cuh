@@ -30,8 +30,9 @@ struct acvd_ctx {
     DevBuf<float> xyz;
     DevBuf<int> tri, row_ptr, col, vf_ptr, ell;
     int ell_w = 0;                    // ELL width (6 or 8)
+    int max_deg = 0;                  // longest adjacency row
     int64_t vpad = 0;
-    DevBuf<unsigned long long> vf_keys;
+    DevBuf<unsigned long long> vf_keys, ringadj;
     // items
     int metric = -1;
     DevBuf<double> area, weight, items;

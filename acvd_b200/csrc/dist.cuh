@@ -106,16 +106,7 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
         ACVD_LAUNCH_CHECK();
     }
     ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    switch (c->metric) {
-        case M_ISO: k_evaluate<M_ISO, 4><<<ge, kThreads, 0, c->stream>>>(A); break;
-        case M_QEM:
-            if (as_iso) k_evaluate<M_ISO, 14><<<ge, kThreads, 0, c->stream>>>(A);
-            else k_evaluate<M_QEM, 14><<<ge, kThreads, 0, c->stream>>>(A);
-            break;
-        case M_ANISO: k_evaluate<M_ANISO, 14><<<ge, kThreads, 0, c->stream>>>(A); break;
-        default: k_evaluate<M_ANISOQ, 22><<<ge, kThreads, 0, c->stream>>>(A); break;
-    }
-    ACVD_LAUNCH_CHECK();
+    launch_evaluate(c, A, as_iso, ge);
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->moves_local.alloc(((size_t)c->K / 2 + 64) * sizeof(MoveRec));
     RoundResult r;

@@ -347,19 +347,75 @@ __global__ void __launch_bounds__(kThreads) k_resubmit(ReassignArgs A) {
     }
 }
 
-// k_evaluate: one thread per work-list vertex (dense: every lane evaluates a dirty boundary vertex).
+// ---------------------------------------------------------------------------------------------------
+// k_evaluate: every work-list vertex evaluates its candidate moves.
 // EM: metric whose energy is evaluated; STRIDE: doubles per payload row in memory.
 // (QEM's unconstrained phase evaluates the isotropic energy on the first 4 doubles of its rows.)
+//
+// The heavy part of a test is the energy of the grown destination cluster (for the quadric metrics a 3x3
+// eigen-solve).  A warp therefore walks the candidates by *rank*: all lanes evaluate their first distinct adjacent
+// cluster together, then their second, ... -- two or three executions of the heavy body per warp instead of one
+// per ring slot.  The ring (<= kRingW neighbours) lives in registers; the connexity predicate
+// (vtkVerticesProcessing::ConnexityConstraintProblemLocal, DiscreteRemeshing/vtkVerticesProcessing.h:168-237)
+// is evaluated with bit operations on the precomputed ring adjacency matrix (k_build_ringadj).  Rows longer than
+// kRingW are left to k_evaluate_long.
+constexpr int kRingW = 8;
+
+// ringadj[v]: bit 8 i + j is set iff the i-th and the j-th neighbour of v (CSR order) are joined by a mesh edge;
+// 0 for rows longer than kRingW (those use connexity_problem).  Static topology, built once per mesh.
+__global__ void __launch_bounds__(kThreads) k_build_ringadj(int V, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                                            unsigned long long* ringadj) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const int beg = row_ptr[v], deg = row_ptr[v + 1] - beg;
+        unsigned long long m = 0;
+        if (deg <= kRingW) {
+            int ring[kRingW];
+#pragma unroll
+            for (int k = 0; k < kRingW; k++) ring[k] = k < deg ? col[beg + k] : -1;
+            for (int i = 0; i < deg; i++) {
+                const int u = ring[i];
+                for (int e = row_ptr[u]; e < row_ptr[u + 1]; e++) {
+                    const int w = col[e];
+#pragma unroll
+                    for (int j = 0; j < kRingW; j++)
+                        if (ring[j] == w) m |= 1ull << (8 * i + j);
+                }
+            }
+        }
+        ringadj[v] = m;
+    }
+}
+
+// "the ring members of cluster a (bit mask L over the ring slots) are connected in the sub-graph they induce"
+__device__ __forceinline__ bool connexity_problem_ring(unsigned L, unsigned long long adj) {
+    if ((L & (L - 1)) == 0) return false;           // zero or one member
+    unsigned reach = L & (0u - L);
+#pragma unroll 1
+    for (int iter = 0; iter < kRingW; iter++) {
+        unsigned nxt = reach;
+#pragma unroll
+        for (int i = 0; i < kRingW; i++)
+            if ((reach >> i) & 1u) nxt |= (unsigned)(adj >> (8 * i)) & 0xffu;
+        nxt &= L;
+        if (nxt == reach) break;
+        reach = nxt;
+    }
+    return reach != L;
+}
+
+// k_evaluate_long: the work-list vertices whose rows are longer than kRingW, one thread per vertex, per-slot walk.
+// Launched only for meshes that have such vertices.
 template <int EM, int STRIDE>
-__global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) {
-    constexpr int NL = MetricTraits<EM>::NPAD;   // doubles loaded per row
+__global__ void __launch_bounds__(kThreads) k_evaluate_long(ReassignArgs A) {
+    constexpr int NL = MetricTraits<EM>::NPAD;
     const int K = A.K;
-    const int n_work = (int)A.ctr->evaluated;    // written by k_scan of this round
+    const int n_work = (int)A.ctr->evaluated;
     unsigned n_tests = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
         const int v = A.work[i];
-        const int a = A.cid[v];
         const int beg = A.row_ptr[v], end = A.row_ptr[v + 1];
+        if (end - beg <= kRingW) continue;               // k_evaluate's
+        const int a = A.cid[v];
         int best_b = -1;
         double best_delta = 0.0, best_ea = 0.0, best_eb = 0.0;
         unsigned long long key = 0;
@@ -415,6 +471,103 @@ __global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) {
             atomicMin(&A.best[best_b], key);
             int slot = (int)atomicAdd(&A.ctr->proposals, 1ull);
             A.plist[slot] = v;
+        }
+    }
+    warp_count_add(&A.ctr->tests, n_tests);
+}
+
+template <int EM, int STRIDE>
+__global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) {
+    constexpr int NL = MetricTraits<EM>::NPAD;   // doubles loaded per row
+    const int K = A.K;
+    const int n_work = (int)A.ctr->evaluated;    // written by k_scan of this round
+    const int lane = threadIdx.x & 31;
+    unsigned n_tests = 0;
+    // warp-uniform trip count: the candidate loop below votes across the warp
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < n_work; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        const int v = i < n_work ? A.work[i] : 0;
+        const int beg = A.row_ptr[v], deg = A.row_ptr[v + 1] - beg;
+        const bool active = i < n_work && deg <= kRingW;      // longer rows: k_evaluate_long
+        const int a = active ? A.cid[v] : K;
+        int best_b = -1;
+        double best_delta = 0.0, best_ea = 0.0, best_eb = 0.0;
+        unsigned long long key = 0;
+        unsigned nt = 0;
+        // ---- fast path: ring in registers
+        int nbc[kRingW];
+#pragma unroll
+        for (int k = 0; k < kRingW; k++) nbc[k] = (active && k < deg) ? A.cid[A.col[beg + k]] : a;
+        unsigned rem = 0;
+        bool blocked = true;
+        double it[NL], s[NL];
+        double ea_new = 0.0, cur_a = 0.0;
+        double anchor_pt[3];
+        if (active) {
+            if (a >= K) {
+                // NULL cluster: adopt the first assigned, non-frozen neighbour cluster; top priority
+#pragma unroll
+                for (int k = kRingW - 1; k >= 0; k--)
+                    if (nbc[k] < K && !(A.frozen && A.frozen[nbc[k]])) best_b = nbc[k];
+                key = (unsigned long long)(unsigned)v;
+            } else if (!(A.frozen && A.frozen[a])) {
+                unsigned L = 0;
+#pragma unroll
+                for (int k = 0; k < kRingW; k++) {
+                    const int b = nbc[k];
+                    const bool asg = b != a && b < K && !(A.frozen && A.frozen[b]);
+                    rem |= (asg ? 1u : 0u) << k;
+                    L |= ((k < deg && b == a) ? 1u : 0u) << k;
+                }
+                blocked = (A.csize[a] == 1) || (A.anchor && A.anchor[a] == v);
+                if (!blocked && A.connexity) blocked = connexity_problem_ring(L, A.ringadj[v]);
+                cur_a = A.cenergy[a];
+                if (!blocked) {
+                    load_row_ro<NL>(A.items + (int64_t)v * STRIDE, it);
+                    load_row<NL>(A.csum + (int64_t)a * STRIDE, s);
+#pragma unroll
+                    for (int k = 0; k < NL; k++) s[k] -= it[k];
+                    ea_new = cluster_energy<EM>(s, A.cfg, nullptr, anchor_point<EM>(A, a, anchor_pt));
+                }
+            }
+        }
+        // candidates by rank (first occurrence of every distinct adjacent cluster, in ring order)
+        while (__any_sync(0xffffffffu, rem != 0)) {
+            if (rem) {
+                const int k0 = __ffs(rem) - 1;
+                int b = nbc[0];
+#pragma unroll
+                for (int k = 1; k < kRingW; k++) b = (k0 == k) ? nbc[k] : b;
+#pragma unroll
+                for (int k = 0; k < kRingW; k++) rem &= ~((nbc[k] == b ? 1u : 0u) << k);
+                nt++;
+                if (!blocked) {
+                    const double2* ps = reinterpret_cast<const double2*>(A.csum + (int64_t)b * STRIDE);
+#pragma unroll
+                    for (int k = 0; k < NL / 2; k++) { double2 u = ps[k]; s[2 * k] = u.x + it[2 * k]; s[2 * k + 1] = u.y + it[2 * k + 1]; }
+                    const double eb_new = cluster_energy<EM>(s, A.cfg, nullptr, anchor_point<EM>(A, b, anchor_pt));
+                    const double tr = ea_new + eb_new;
+                    const double cur = cur_a + A.cenergy[b];
+                    if (tr < cur) {
+                        const double delta = tr - cur;
+                        if (best_b < 0 || delta < best_delta) { best_b = b; best_delta = delta; best_ea = ea_new; best_eb = eb_new; }
+                    }
+                }
+            }
+        }
+        if (active) {
+            if (a < K && best_b >= 0)
+                key = ((unsigned long long)ordered_float_bits(__double2float_rn(best_delta)) << 32) | (unsigned)v;
+            n_tests += nt;
+            A.prop_dst[v] = best_b;
+            if (best_b >= 0) {
+                A.prop_key[v] = key;
+                A.prop_e[v] = make_double2(best_ea, best_eb);
+                if (a < K) atomicMin(&A.best[a], key);
+                atomicMin(&A.best[best_b], key);
+                int slot = (int)atomicAdd(&A.ctr->proposals, 1ull);
+                A.plist[slot] = v;
+            }
         }
     }
     warp_count_add(&A.ctr->tests, n_tests);

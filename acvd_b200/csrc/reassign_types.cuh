@@ -17,6 +17,7 @@ struct ReassignArgs {
     int V, K;
     const int* __restrict__ row_ptr;
     const int* __restrict__ col;
+    const unsigned long long* __restrict__ ringadj;   // V: 8x8 adjacency matrix of every vertex ring (rows <= 8)
     const int* __restrict__ ell;        // column-major padded adjacency (W columns of vpad entries)
     long long vpad;
     int* cid;
