@@ -35,6 +35,8 @@ static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("AC
 // ACVD_TRACE=1: wall-clock trace of the host driver's stages on stderr (the reference's ConsoleOutput>1
 // per-loop lines are the analogue, Common/vtkUniformClustering.h:752-760)
 constexpr int64_t kReplicatedTailProposals = 4096;
+constexpr int kRoundSlots = 8;            // exact rounds that may be in flight between two host synchronisations
+constexpr int kTailBatch = 4;             // rounds launched back to back in the long tail of the last phases
 
 static bool trace_on() {
     static int on = -1;
@@ -93,8 +95,8 @@ extern "C" int acvd_create(acvd_ctx** out, int device) {
         ACVD_CUDA(cudaSetDevice(device));
         ACVD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) ACVD_CUDA(cudaEventCreate(&ev));
-        ACVD_CUDA(cudaMallocHost(&c->h_ctr, sizeof(RoundCounters)));
-        ACVD_CUDA(cudaMallocHost(&c->h_scalars, 8 * sizeof(unsigned long long)));
+        ACVD_CUDA(cudaMallocHost(&c->h_ctr, kRoundSlots * sizeof(RoundCounters)));
+        ACVD_CUDA(cudaMallocHost(&c->h_scalars, (8 + kRoundSlots) * sizeof(unsigned long long)));
         c->ctr.alloc(1);
         c->scalars.alloc(8);
     } catch (const CudaError& err) {
@@ -652,6 +654,7 @@ static bool plan_scan(acvd_ctx* c, ReassignArgs& A, int force_all, int t0, int t
     A.tile_begin = t0; A.tile_end = t1;
     const bool dense = force_all || c->dense_next;
     c->last_tile_count = t1 - t0;
+    c->last_bulk = A.bulk;
     if (dense) { A.all_tiles = 1; A.sig_mode = 1; c->sig_valid = false; c->last_all_tiles = 1; return false; }
     if (!c->sig_valid) { A.all_tiles = 1; A.sig_mode = 2; c->sig_valid = true; c->last_all_tiles = 1; return false; }
     A.all_tiles = 0; A.sig_mode = 0; c->last_all_tiles = 0;
@@ -660,10 +663,13 @@ static bool plan_scan(acvd_ctx* c, ReassignArgs& A, int force_all, int t0, int t
 // after the round: decide the next round's mode from how much of the mesh was active (counters summed over ranks,
 // so every rank takes the same decision)
 static void update_density(acvd_ctx* c, RoundResult& r) {
+    // break-even points measured on C4: the TMA-staged dense bulk scan costs what the list-based scan costs on about
+    // half of the tiles; the exact rounds use the list-based kernel in both modes, where only the tile filter is saved
+    const double to_sparse = c->last_bulk ? 0.27 : 0.5, to_dense = c->last_bulk ? 0.55 : 0.6;
     if (c->last_all_tiles) {
         r.active_tiles = (unsigned long long)(((int64_t)c->V + 31) / 32);
-        c->dense_next = r.boundary > 0 && (double)r.evaluated > 0.5 * (double)r.boundary;
-    } else c->dense_next = (double)r.active_tiles > 0.6 * (double)(((int64_t)c->V + 31) / 32);
+        c->dense_next = r.boundary > 0 && (double)r.evaluated > to_sparse * (double)r.boundary;
+    } else c->dense_next = (double)r.active_tiles > to_dense * (double)(((int64_t)c->V + 31) / 32);
 }
 
 // candidate evaluation of the work list: ring-in-registers kernel, plus the per-slot kernel when the mesh has rows
@@ -688,7 +694,8 @@ static void launch_evaluate(acvd_ctx* c, const ReassignArgs& A, bool as_iso, int
 #undef ACVD_EVAL
 }
 
-static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso) {
+static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso, int slot = 0) {
+    cudaEvent_t* ev = c->ev + 4 * slot;
     // proposals of the previous round become the carry list (none survive a phase start: everything is dirty)
     if (force_all) ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p + 1, 0, sizeof(unsigned long long), c->stream));
     else ACVD_CUDA(cudaMemcpyAsync(c->round_scalars.p + 1, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
@@ -702,7 +709,7 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
     ACVD_LAUNCH_CHECK();
     const int n_tiles = (c->V + 31) / 32;
     const bool filtered = plan_scan(c, A, force_all, 0, n_tiles);
-    ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    ACVD_CUDA(cudaEventRecord(ev[0], c->stream));
     if (filtered) {
         k_tile_filter<<<grid_for(n_tiles), kThreads, 0, c->stream>>>(0, n_tiles, c->K, 0, reinterpret_cast<const int4*>(c->tile_sig.p),
                                                                     c->modbits.p, c->tile_active.p, c->active_tiles.p, c->round_scalars.p);
@@ -714,9 +721,9 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
         k_carry<<<gc, kThreads, 0, c->stream>>>(A);
         ACVD_LAUNCH_CHECK();
     }
-    ACVD_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    ACVD_CUDA(cudaEventRecord(ev[3], c->stream));
     launch_evaluate(c, A, as_iso, ge);
-    ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    ACVD_CUDA(cudaEventRecord(ev[1], c->stream));
     for (int pass = 0; pass < c->commit_passes; pass++) {
         if (pass > 0) {
             ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
@@ -734,9 +741,9 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
         }
         ACVD_LAUNCH_CHECK();
     }
-    ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
-    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 7, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaEventRecord(ev[2], c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_ctr + slot, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 8 + slot, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     c->round++;
 }
 
@@ -817,20 +824,22 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
     ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
-    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 7, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 8, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     c->round++;
     c->stats_valid = false;
 }
 
-static RoundResult finish_round(acvd_ctx* c) {
+static RoundResult finish_round(acvd_ctx* c, int slot = 0, bool last_of_batch = true) {
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    const RoundCounters* h = c->h_ctr + slot;
+    cudaEvent_t* ev = c->ev + 4 * slot;
     RoundResult r;
-    r.proposals = c->h_ctr->proposals; r.mods = c->h_ctr->mods; r.tests = c->h_ctr->tests;
-    r.evaluated = c->h_ctr->evaluated + c->h_ctr->pad[0]; r.boundary = c->h_ctr->boundary; r.active_tiles = c->h_scalars[7];
-    ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, c->ev[0], c->ev[3]));
-    ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
-    ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
-    update_density(c, r);
+    r.proposals = h->proposals; r.mods = h->mods; r.tests = h->tests;
+    r.evaluated = h->evaluated + h->pad[0]; r.boundary = h->boundary; r.active_tiles = c->h_scalars[8 + slot];
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, ev[0], ev[3]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, ev[3], ev[1]));
+    ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, ev[1], ev[2]));
+    if (last_of_batch) update_density(c, r);
     return r;
 }
 
@@ -930,6 +939,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     // prime: FillHoles, ReComputeStatistics, SetAllClustersToModified (:727-730)
     timed_clean([&] { fill_holes(c); recompute_statistics(c, constrained, qlevel, thr); });
     int force_all = 1;
+    int64_t last_proposals = -1;
     bool reeval_all = false;   // first replicated round of a multi-GPU tail
     int nconv = 0;
     // earlyStopItems = items of non-frozen clusters (:733-736)
@@ -997,14 +1007,32 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         // re-evaluates every boundary vertex, because stored proposals are only known to the rank that owns them.
         RoundResult r;
         if (force_all) c->replicated_tail = false;
+        // In the long tail of the last phases (connexity on: the phase can only end with a round without moves) a few
+        // rounds are launched back to back and their counters read together: a round after the one that made no move
+        // finds no modified cluster and changes nothing, so the result is the one of round-by-round polling, with a
+        // quarter of the host synchronisations.
+        int batch = 1;
+        if ((c->world == 1 || c->replicated_tail) && nconv >= 2 && !force_all && !reeval_all && !p.log_energy && !trace_on() &&
+            last_proposals >= 0 && last_proposals <= kReplicatedTailProposals)
+            batch = (int)std::min<int64_t>(kTailBatch, std::max<int64_t>(1, p.max_loops - loops));
         if (c->world > 1 && !c->replicated_tail) {
             r = run_round_dist(c, cfg, connexity, force_all, as_iso);
             if ((int64_t)r.proposals <= kReplicatedTailProposals && r.mods > 0) { c->replicated_tail = true; reeval_all = true; }
         } else {
-            launch_round(c, cfg, connexity, (force_all || reeval_all) ? 1 : 0, as_iso);
-            r = finish_round(c);
+            for (int j = 0; j < batch; j++) launch_round(c, cfg, connexity, (j == 0 && (force_all || reeval_all)) ? 1 : 0, as_iso, j);
+            for (int j = 0; j < batch; j++) {
+                r = finish_round(c, j, j == batch - 1);
+                if (j == batch - 1 || r.mods == 0) break;
+                // an intermediate round of the batch: account for it like any other round
+                loops++;
+                R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;
+                R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;
+                R.round_launches++; R.scan_bytes += scan_bytes(c, r); R.evaluate_bytes += eval_bytes(c, r, as_iso);
+                R.evaluated += (int64_t)r.evaluated;
+            }
             reeval_all = false;
         }
+        last_proposals = (int64_t)r.proposals;
         force_all = 0;
         loops++;
         R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;

@@ -55,7 +55,7 @@ struct acvd_ctx {
     int plist_cur = 0;
     bool sig_valid = false;           // tile signatures describe the current clustering
     bool dense_next = true;           // next round scans all tiles (activity was high)
-    int last_all_tiles = 0, last_tile_count = 0;
+    int last_all_tiles = 0, last_tile_count = 0, last_bulk = 0;
     // bulk (Lloyd-criterion) rounds
     DevBuf<long long> isum;
     DevBuf<double> bulk_cen, bulk_energy, bulk_energy_sum;
@@ -65,14 +65,14 @@ struct acvd_ctx {
     DevBuf<unsigned> modbits;
     DevBuf<RoundCounters> ctr;
     int commit_passes = 4;            // select+commit passes per round (ACVD_COMMIT_PASSES)
-    RoundCounters* h_ctr = nullptr;   // pinned
+    RoundCounters* h_ctr = nullptr;   // pinned, kRoundSlots entries (rounds launched back to back report into separate slots)
     int round = 1;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4 * 8] = {};       // 4 events per round slot
     // generic scratch
     DevBuf<char> cub_temp;
     DevBuf<int> sort_k0, sort_k1, sort_v0, sort_v1, seg, label, comp_size, n_comp, null_list, pick;
     DevBuf<unsigned long long> winner, scalars;   // scalars: small device counters
-    unsigned long long* h_scalars = nullptr;      // pinned, 8 entries
+    unsigned long long* h_scalars = nullptr;      // pinned, 8 entries + one active-tile count per round slot
     std::vector<double> energy_log;
     int stats_constrained = 1, stats_qlevel = 3;
     // multi-GPU (acvd_dist.cu)
