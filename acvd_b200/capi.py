@@ -41,6 +41,8 @@ class Report(C.Structure):
         ("round_launches", C.c_int64), ("scan_bytes", C.c_int64), ("evaluate_bytes", C.c_int64),
         ("evaluated", C.c_int64), ("ms_device", C.c_double),
         ("kernel_launches", C.c_int64), ("bulk_rounds", C.c_int64),
+        ("dense_scan_launches", C.c_int64), ("ms_dense_scan", C.c_double), ("dense_scan_bytes", C.c_int64),
+        ("dense_scan_vertices", C.c_int64),
     ]
 
     def asdict(self):

@@ -636,7 +636,9 @@ static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, i
 }
 
 static void launch_scan(acvd_ctx* c, const ReassignArgs& A, int grid) {
+    c->last_dense_kernel = false;
     if (A.bulk && A.all_tiles && A.sig_mode == 1 && !getenv("ACVD_NO_DENSE_SCAN")) {
+        c->last_dense_kernel = true;
         if (c->ell_w == 6) launch_scan_bulk_dense_variant<6>(c, A, g_dense_variant); else launch_scan_bulk_dense_variant<8>(c, A, g_dense_variant);
         return;
     }
@@ -980,6 +982,12 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                     R.proposals += (int64_t)r.proposals; R.evaluated += (int64_t)r.evaluated;
                     R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;
                     R.round_launches++; R.scan_bytes += scan_bytes(c, r) + bulk_eval_bytes(c, r);
+                    if (c->last_dense_kernel) {   // this round's scan was the TMA-staged dense kernel: the dominant kernel, reported on its own
+                        // counters are summed over the ranks, so are the vertices (every rank scans its share of the tiles)
+                        const int64_t nt = ((int64_t)c->V + 31) / 32, nv = nt * 32;
+                        R.dense_scan_launches++; R.ms_dense_scan += r.ms_scan; R.dense_scan_vertices += nv;
+                        R.dense_scan_bytes += (int64_t)((double)nv * (8.0 + 8.0 * (double)c->nnz / c->V)) + 4 * nt + bulk_eval_bytes(c, r);
+                    }
                     if (p.log_energy) {   // exact energy of the current clustering (test/trace path only)
                         recompute_statistics(c, constrained, qlevel, thr);
                         c->energy_log.push_back(global_energy(c));

@@ -87,16 +87,21 @@ __device__ __forceinline__ int cc_find_compress(int* label, int x) {
     }
 }
 
-__device__ __forceinline__ void cc_union(int* label, int u, int v) {
-    int ru = cc_find_compress(label, u), rv = cc_find_compress(label, v);
+// joins the trees rooted at (or above) ru and rv; returns the smaller representative reached.  A failed CAS hands
+// back the parent somebody else installed, which is closer to the root: the walk continues from there (ECL-CC).
+__device__ __forceinline__ int cc_hook_roots(int* label, int ru, int rv) {
     while (ru != rv) {
-        const int hi = max(ru, rv), lo = min(ru, rv);
-        const int old = atomicMin(label + hi, lo);
-        if (old == hi) return;          // hi was still a root: hooked
-        // somebody re-parented hi meanwhile: continue from the trees as they are now
-        ru = cc_find_compress(label, old);
-        rv = cc_find_compress(label, lo);
+        if (rv < ru) {
+            const int ret = atomicCAS(label + ru, ru, rv);
+            if (ret == ru) return rv;
+            ru = ret;
+        } else {
+            const int ret = atomicCAS(label + rv, rv, ru);
+            if (ret == rv) return ru;
+            rv = ret;
+        }
     }
+    return rv;
 }
 
 // Initial forest without atomics (the first step of ECL-CC): every vertex points at its smallest same-cluster
@@ -140,15 +145,16 @@ __global__ void __launch_bounds__(kThreads) k_cc_hook(int V, int K, int64_t vpad
 #pragma unroll
         for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);
         const bool overflow = nb[W - 1] == -2;
+        int rv = cc_find_compress(label, v);          // own representative: found once, updated by every hook
 #pragma unroll
         for (int k = 0; k < W; k++) {
             const int u = nb[k];
-            if (u >= 0 && u < v && cid[u] == c) cc_union(label, u, v);
+            if (u >= 0 && u < v && cid[u] == c) rv = cc_hook_roots(label, cc_find_compress(label, u), rv);
         }
         if (overflow)
             for (int e = row_ptr[v] + W - 1; e < row_ptr[v + 1]; e++) {
                 const int u = col[e];
-                if (u < v && cid[u] == c) cc_union(label, u, v);
+                if (u < v && cid[u] == c) rv = cc_hook_roots(label, cc_find_compress(label, u), rv);
             }
     }
 }

@@ -56,6 +56,7 @@ struct acvd_ctx {
     bool sig_valid = false;           // tile signatures describe the current clustering
     bool dense_next = true;           // next round scans all tiles (activity was high)
     int last_all_tiles = 0, last_tile_count = 0, last_bulk = 0;
+    bool last_dense_kernel = false;   // the last scan launch was k_scan_bulk_dense
     // bulk (Lloyd-criterion) rounds
     DevBuf<long long> isum;
     DevBuf<double> bulk_cen, bulk_energy, bulk_energy_sum;

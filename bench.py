@@ -290,24 +290,32 @@ def main():
     e2e = {"value": e2e_tests / t_e2e if args.e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "s_per_step": t_e2e / max(1, args.e2e_steps), "steps": args.e2e_steps}
 
-    # ---- roofline of the dominant kernel of the reassignment loop, timed with CUDA events inside the library
-    # (k_scan = frontier scan, k_evaluate = candidate evaluation; the one with the larger share is reported,
-    # the other is given beside it)
+    # ---- roofline of the dominant kernel of the reassignment loop, timed with CUDA events inside the library on the
+    # stream the kernels are launched on.  The dominant kernel is the TMA-staged dense bulk scan (k_scan_bulk_dense);
+    # the other frontier-scan launches (list-based k_scan) and the candidate evaluation (k_evaluate) are given beside it.
+    # Counters are summed over the ranks while every rank times its own share, hence the division by `world`.
     peak, peak_src = measured_peak()
     n_l = sum(r["round_launches"] for r in reps)
 
-    def kernel_roof(name, label, bytes_key, ms_key):
-        by = sum(r[bytes_key] for r in reps)
-        ms = sum(r[ms_key] for r in reps)
+    def kernel_roof(name, label, by, ms, launches):
+        by = by / world
         ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         return {"bound": "hbm", "kernel": label, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": profiled_traffic(args.workload, name), "peak_source": peak_src,
-                "bytes_per_launch": by / max(1, n_l), "us_per_launch": 1e3 * ms / max(1, n_l),
-                "share_of_step": ms / ms_dev}
-    roof_scan = kernel_roof("k_scan", "k_scan (frontier scan of the boundary-item reassignment loop)", "scan_bytes", "ms_scan")
-    roof_eval = kernel_roof("k_evaluate", "k_evaluate (candidate energy evaluation of the reassignment loop)", "evaluate_bytes", "ms_evaluate")
-    roofline, other = (roof_scan, roof_eval) if roof_scan["share_of_step"] >= roof_eval["share_of_step"] else (roof_eval, roof_scan)
-    roofline["second_kernel"] = {k: other[k] for k in ("kernel", "achieved", "frac", "bytes_per_launch", "us_per_launch", "share_of_step", "traffic")}
+                "traffic": profiled_traffic(args.workload, name) if world == 1 else None, "peak_source": peak_src,
+                "bytes_per_launch": by / max(1, launches), "us_per_launch": 1e3 * ms / max(1, launches),
+                "launches_per_step": launches / args.steps, "share_of_step": ms / ms_dev}
+    S = lambda k: sum(r[k] for r in reps)
+    roof_dense = kernel_roof("k_scan_bulk_dense", "k_scan_bulk_dense (TMA-staged frontier scan + bulk decision of the reassignment loop, all tiles)",
+                             S("dense_scan_bytes"), S("ms_dense_scan"), S("dense_scan_launches"))
+    if S("dense_scan_launches"):
+        roof_dense["scan_only_GBps"] = S("dense_scan_vertices") / world * 56.0 / (S("ms_dense_scan") * 1e-3) / 1e9
+        roof_dense["scan_only_note"] = "frontier-scan bytes alone (8 + 8 deg = 56 B per vertex, SURVEY 8d), without the tests' operands"
+    roof_scan = kernel_roof("k_scan", "k_scan (all frontier-scan launches of the loop, dense + list-based)", S("scan_bytes"), S("ms_scan"), n_l)
+    roof_eval = kernel_roof("k_evaluate", "k_evaluate (candidate energy evaluation of the exact rounds)", S("evaluate_bytes"), S("ms_evaluate"),
+                            n_l - S("bulk_rounds"))
+    roofline = roof_dense if S("dense_scan_launches") else roof_scan
+    roofline["other_kernels"] = [{k: o[k] for k in ("kernel", "achieved", "frac", "bytes_per_launch", "us_per_launch", "launches_per_step", "share_of_step", "traffic")}
+                                 for o in (roof_scan, roof_eval)]
 
     # ---- CPU baseline beside it (rank 0, N=1 only): sequential restated reference, bounded sample
     cpu = None

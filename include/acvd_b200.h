@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ACVD_B200_ABI_VERSION 1
+#define ACVD_B200_ABI_VERSION 2
 
 typedef struct acvd_ctx acvd_ctx;
 
@@ -126,6 +126,10 @@ typedef struct acvd_report {
     double ms_device;        /* CUDA-event time of the whole call on the context's stream */
     int64_t kernel_launches; /* kernels this call launched */
     int64_t bulk_rounds;     /* rounds run with the bulk (Lloyd-criterion) commit */
+    int64_t dense_scan_launches; /* launches of the TMA-staged dense bulk scan (k_scan_bulk_dense), the dominant kernel */
+    double ms_dense_scan;        /* device time in those launches */
+    int64_t dense_scan_bytes;    /* algorithmic bytes they moved (SURVEY 8d model: 8 + 8 deg per vertex + the tests' operands) */
+    int64_t dense_scan_vertices; /* vertices they scanned */
 } acvd_report;
 
 /* MinimizeEnergy (Common/vtkUniformClustering.h:725-830) with ProcessOneLoop (:833-995) replaced by
