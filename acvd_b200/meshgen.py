@@ -184,6 +184,31 @@ def ridged_ellipsoid(n: int = 316, axes=(1.0, 0.6, 0.4), ridge: float = 0.03, fr
     return pts.astype(dtype), tris
 
 
+def ellipsoid_principal_directions(points, axes=(1.0, 0.6, 0.4)):
+    """Analytic curvature of the ellipsoid x^2/a^2 + y^2/b^2 + z^2/c^2 = 1 at the radial projections of ``points``
+    (the C3 inputs the reference takes from vtkCurvatureMeasure: "analytic-curvature" runs).
+
+    Returns ``(pd, indicator)``: ``pd[v] = (sqrt|k1| d1, sqrt|k2| d2)`` as float32 with the larger |k| first
+    (the PrincipalDirections layout of Common/vtkCurvatureMeasure.cxx:445-484) and ``indicator = sqrt(k1^2 + k2^2)``.
+    The shape operator of the level set F = 1 is P H P / |grad F| with P = I - n n^T and H = diag(2/a^2, 2/b^2, 2/c^2)."""
+    ax = np.asarray(axes, dtype=np.float64)
+    q = np.asarray(points, dtype=np.float64)
+    q = q / np.sqrt(((q / ax) ** 2).sum(axis=1))[:, None]          # onto the ellipsoid
+    grad = 2.0 * q / ax ** 2
+    gn = np.linalg.norm(grad, axis=1)
+    n = grad / gn[:, None]
+    P = np.eye(3)[None, :, :] - n[:, :, None] * n[:, None, :]
+    H = np.diag(2.0 / ax ** 2)
+    S = P @ H[None, :, :] @ P / gn[:, None, None]
+    w, vec = np.linalg.eigh(S)                                      # ascending; one eigenvalue ~0 along n
+    order = np.argsort(-np.abs(w), axis=1)                          # |k| descending: k1, k2, ~0
+    idx = np.arange(q.shape[0])
+    k1, k2 = w[idx, order[:, 0]], w[idx, order[:, 1]]
+    d1, d2 = vec[idx, :, order[:, 0]], vec[idx, :, order[:, 1]]
+    pd = np.concatenate([np.sqrt(np.abs(k1))[:, None] * d1, np.sqrt(np.abs(k2))[:, None] * d2], axis=1)
+    return pd.astype(np.float32), np.sqrt(k1 * k1 + k2 * k2)
+
+
 def subdivide(points, triangles):
     """One 1->4 midpoint subdivision (old points first, then one midpoint per edge)."""
     p = np.asarray(points, dtype=np.float64)
@@ -232,6 +257,11 @@ def workload(name: str):
         p, t = torus_grid(500, 325, noise=0.002, seed=1)
         return dict(points=p, triangles=t, K=6250, metric="qem", gradation=1.5,
                     indicator=torus_curvature_indicator(500, 325))
+    if name in ("C3", "C3s"):  # AnisotropicRemeshingQ 1.5 on the ridged ellipsoid (C3s: 1/16 size)
+        p, t = ridged_ellipsoid(316 if name == "C3" else 79)
+        pd, ind = ellipsoid_principal_directions(p)
+        return dict(points=p, triangles=t, K=10000 if name == "C3" else 625, metric="anisoq", gradation=1.5,
+                    indicator=ind, pd=pd)
     if name == "C4":
         p, t = displaced_sphere(2000)
         return dict(points=p, triangles=t, K=400000, metric="qem", gradation=0.0, indicator=None)

@@ -34,6 +34,8 @@ WORKLOADS = {
     "C2": "ACVDQ gradation 1.5 (analytic curvature) on a 2.6M-vertex noisy torus -> 100k clusters (configs[1])",
     "C2s": "1/16-scale C2",
     "C1": "ACVD isotropic on a 163,842-vertex icosphere -> 3000 clusters (configs[0])",
+    "C3": "AnisotropicRemeshingQ gradation 1.5 (analytic curvature) on a 998,562-vertex ridged ellipsoid -> 10k clusters (configs[2])",
+    "C3s": "1/16-scale C3",
 }
 
 
@@ -125,7 +127,7 @@ def cpu_sample(w, threads, loops, steps=1, warmup=0):
     from oracle import oracle
     t0 = time.time()
     o = oracle.Oracle(w["points"], w["triangles"])
-    o.build_metric(w["metric"], w["gradation"], w["indicator"])
+    o.build_metric(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
     o.set_num_clusters(w["K"])
     cl0 = o.initial_sampling().copy()
     setup_s = time.time() - t0
@@ -226,9 +228,11 @@ def main():
         return t, t.numpy()
     _k1, h_xyz = pinned(w["points"])
     _k2, h_tri = pinned(w["triangles"])
-    h_ind = None
+    h_ind = h_pd = None
     if w["indicator"] is not None:
         _k3, h_ind = pinned(w["indicator"])
+    if w.get("pd") is not None:
+        _k6, h_pd = pinned(w["pd"])
 
     ctx = capi.Context(local_rank)
     if world > 1:
@@ -237,7 +241,7 @@ def main():
         ctx.dist_init(rank, world, uid[0])
     t0 = time.time()
     ctx.set_mesh(h_xyz, h_tri)
-    ctx.build_items(w["metric"], w["gradation"], h_ind)
+    ctx.build_items(w["metric"], w["gradation"], h_ind, h_pd)
     ctx.set_num_clusters(K)
     ctx.initial_sampling()          # host, sequential; outside the timed region as in the reference (:690)
     ctx.save_clustering()
@@ -275,7 +279,7 @@ def main():
     t_e2e0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         ctx.set_mesh(h_xyz, h_tri)
-        ctx.build_items(w["metric"], w["gradation"], h_ind)
+        ctx.build_items(w["metric"], w["gradation"], h_ind, h_pd)
         ctx.set_num_clusters(K)
         ctx.set_clustering(h_cl0)
         r = ctx.minimize(**mparams)
@@ -284,7 +288,7 @@ def main():
         e2e_tests += r["tests"]
     barrier()
     t_e2e = time.perf_counter() - t_e2e0
-    h2d = h_xyz.nbytes + h_tri.nbytes + h_cl0.nbytes + (h_ind.nbytes if h_ind is not None else 0)
+    h2d = h_xyz.nbytes + h_tri.nbytes + h_cl0.nbytes + (h_ind.nbytes if h_ind is not None else 0) + (h_pd.nbytes if h_pd is not None else 0)
     np_pay = {"iso": 4, "qem": 13, "aniso": 13, "anisoq": 22}[w["metric"]]
     d2h = h_out.nbytes + K * (np_pay * 8 + 24 + 8 + 4)
     e2e = {"value": e2e_tests / t_e2e if args.e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -17,7 +17,7 @@ if __name__ == "__main__":
     w = meshgen.workload(wl)
     g = capi.Context(0)
     g.set_mesh(w["points"], w["triangles"])
-    g.build_items(w["metric"], w["gradation"], w["indicator"])
+    g.build_items(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
     g.set_num_clusters(int(w["K"]))
     g.initial_sampling()
     rep = g.minimize(unconstrained_init=1, max_loops=n)

@@ -30,7 +30,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         g.dist_init(rank, world, uid[0])
         g.set_mesh(w["points"], w["triangles"])
-        g.build_items(w["metric"], w["gradation"], w["indicator"])
+        g.build_items(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
         g.set_num_clusters(w["K"])
         g.initial_sampling()
         g.save_clustering()
@@ -51,7 +51,7 @@ def main():
         if rank == 0:
             s = capi.Context(local)              # single-GPU run of the same problem
             s.set_mesh(w["points"], w["triangles"])
-            s.build_items(w["metric"], w["gradation"], w["indicator"])
+            s.build_items(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
             s.set_num_clusters(w["K"])
             s.initial_sampling()
             s.save_clustering()

@@ -11,7 +11,7 @@ if __name__ == "__main__":
     w = meshgen.workload(wl)
     g = capi.Context(0)
     g.set_mesh(w["points"], w["triangles"])
-    g.build_items(w["metric"], w["gradation"], w["indicator"])
+    g.build_items(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
     g.set_num_clusters(int(w["K"]))
     g.initial_sampling()
     kw.setdefault("unconstrained_init", 1 if w["metric"] == "qem" else 0)

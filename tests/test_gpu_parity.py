@@ -338,3 +338,85 @@ def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle,
         assert r0[k] == r1[k], k
     assert np.array_equal(c0, c1)
     assert r0["energy"] == r1["energy"]
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_full_size_properties(gpu_ctx_factory, name):
+    """BASELINE-size configurations (C2: ACVDQ gradation 1.5, 2.6 M vertices -> 100 k clusters; C3: AnisotropicRemeshingQ
+    1.5, 1 M vertices -> 10 k) through size-independent properties: every cluster non-empty and connected, sizes sum to
+    V, energy below the initial one, a further round finds no improving move (idempotence), two runs identical."""
+    w = meshgen.workload(name)
+    p, t, K = w["points"], w["triangles"], int(w["K"])
+    uncon = 1 if w["metric"] == "qem" else 0
+    runs = []
+    for _ in range(2):
+        g = gpu_ctx_factory()
+        g.set_mesh(p, t)
+        g.build_items(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
+        g.set_num_clusters(K)
+        g.initial_sampling()
+        g.fill_holes()
+        g.recompute_statistics(0 if uncon else 1, 3)
+        e0 = g.global_energy()
+        rep = g.minimize(unconstrained_init=uncon)
+        cl = g.clustering()
+        runs.append((cl.copy(), rep))
+        assert cl.min() >= 0 and cl.max() < K
+        sz = np.bincount(cl, minlength=K)
+        assert sz.min() >= 1 and sz.sum() == p.shape[0]
+        _, _, _, zg = g.cluster_stats()
+        assert np.array_equal(zg, sz)
+        assert rep["disconnected"] == 0 and g.clean_clustering() == 0
+        if not uncon:
+            assert rep["energy"] < e0            # same energy functional before and after
+        again = g.reassign_round(1, 3, 1)
+        assert again["proposals"] == 0 and again["modifications"] == 0
+        g.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1]["energy"] == runs[1][1]["energy"]
+
+
+def test_bench_kernel_hook(gpu_ctx_factory, torus):
+    """acvd_bench_kernel times the dense bulk scan variants on the current state and leaves the context usable."""
+    p, t, ind = torus
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    g.build_items("qem", 1.5, ind)
+    g.set_num_clusters(400)
+    g.initial_sampling()
+    g.save_clustering()
+    g.minimize(unconstrained_init=1, max_loops=4)
+    for variant in (-1, 0, 1):
+        assert g.bench_kernel(0, variant, 0, 3) > 0.0
+    g.restore_clustering()
+    rep = g.minimize(unconstrained_init=1)
+    cl = g.clustering()
+    assert rep["disconnected"] == 0 and np.bincount(cl, minlength=400).min() >= 1
+
+
+@pytest.mark.parametrize("metric", ["aniso", "anisoq"])
+def test_minimize_anisotropic_within_one_percent(oracle_mod, gpu_ctx_factory, metric):
+    """The anisotropic metrics (vtkAnisotropicMetricForClustering / vtkQuadricAnisotropicMetricForClustering) through the
+    whole minimisation against the sequential oracle, on a small ridged ellipsoid with analytic principal directions."""
+    p, t = meshgen.ridged_ellipsoid(32)
+    pd, ind = meshgen.ellipsoid_principal_directions(p)
+    K = 150
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K, 1.5, ind, pd)
+    g.set_items(metric, o.items())
+    cl0 = o.initial_sampling()
+    g.set_clustering(cl0)
+    o.minimize()
+    o.recompute_statistics()
+    rep = g.minimize()
+    cg = g.clustering()
+    sizes = np.bincount(cg, minlength=K)
+    assert cg.min() >= 0 and cg.max() < K and sizes.min() >= 1 and sizes.sum() == p.shape[0]
+    assert g.clean_clustering() == 0
+    e_o, e_g = o.global_energy(), rep["energy"]
+    assert abs(e_g - e_o) <= 0.01 * abs(e_o)
+    o2 = oracle_mod.Oracle(p, t)
+    o2.build_metric(metric, 1.5, ind, pd)
+    o2.set_num_clusters(K)
+    o2.set_clustering(cg)
+    o2.set_connexity(1)
+    o2.prime()
+    assert o2.process_one_loop() == 0

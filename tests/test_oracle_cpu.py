@@ -286,3 +286,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp", ".cxx")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.lower().replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_ellipsoid_principal_directions_generator():
+    """Analytic C3 curvature inputs: tangent, mutually orthogonal directions scaled by sqrt|k|, larger |k| first; on a
+    sphere both curvatures are 1/R."""
+    from acvd_b200 import meshgen
+    p, _ = meshgen.ridged_ellipsoid(8)
+    pd, ind = meshgen.ellipsoid_principal_directions(p)
+    assert pd.dtype == np.float32 and pd.shape == (p.shape[0], 6) and ind.shape == (p.shape[0],)
+    ax = np.array([1.0, 0.6, 0.4])
+    q = p.astype(np.float64)
+    q = q / np.sqrt(((q / ax) ** 2).sum(axis=1))[:, None]
+    n = q / ax ** 2
+    n /= np.linalg.norm(n, axis=1)[:, None]
+    d1, d2 = pd[:, :3].astype(np.float64), pd[:, 3:].astype(np.float64)
+    assert np.abs((d1 * n).sum(axis=1)).max() < 1e-5 and np.abs((d2 * n).sum(axis=1)).max() < 1e-5
+    assert np.abs((d1 * d2).sum(axis=1)).max() < 1e-5
+    k1, k2 = (d1 ** 2).sum(axis=1), (d2 ** 2).sum(axis=1)          # |k| = |sqrt|k| d|^2
+    assert (k1 >= k2 - 1e-6).all()
+    assert np.allclose(np.sqrt(k1 ** 2 + k2 ** 2), ind, rtol=1e-4)
+    s, _ = meshgen.geodesic_icosphere(4)
+    pds, inds = meshgen.ellipsoid_principal_directions(2.0 * s, axes=(2.0, 2.0, 2.0))
+    assert np.allclose(inds, np.sqrt(2.0) / 2.0, rtol=1e-6)
