@@ -345,8 +345,8 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
     ACVD_CUDA(cudaMemsetAsync(c->anchor.p, 0xff, (size_t)K * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->frozen.p, 0, (size_t)K, c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->csize.p, 0, (size_t)K * sizeof(int), c->stream));
-    std::vector<int> all_null(V, K);
-    ACVD_CUDA(cudaMemcpyAsync(c->cid.p, all_null.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_fill<<<grid_for(c->vpad), kThreads, 0, c->stream>>>((int)c->vpad, K, c->cid.p);     // every vertex in the NULL cluster
+    ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     c->has_frozen = c->has_anchor = false;
     c->fixed.clear();

@@ -10,6 +10,9 @@
 
 namespace acvd {
 
+__global__ void k_fill(int n, int value, int* out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = value;
+}
 __global__ void k_iota(int n, int* out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
 }

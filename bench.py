@@ -264,6 +264,11 @@ def main():
         barrier()
         t_wall = time.perf_counter() - t_wall0
     ms_dev = sum(r["ms_device"] for r in reps)
+    lr = reps[-1]
+    log(f"[rank {rank}] last step: device {lr['ms_device']:.1f} ms = scan {lr['ms_scan']:.1f} (dense bulk {lr['ms_dense_scan']:.1f} in "
+        f"{lr['dense_scan_launches']} launches) + evaluate {lr['ms_evaluate']:.1f} + commit {lr['ms_commit']:.1f} + stats/clean/fill {lr['ms_clean']:.1f} "
+        f"+ other {lr['ms_device'] - lr['ms_scan'] - lr['ms_evaluate'] - lr['ms_commit'] - lr['ms_clean']:.1f}; rounds {lr['rounds']} "
+        f"({lr['bulk_rounds']} bulk), launches {lr['kernel_launches']}")
     if dist is not None:
         tt = torch.tensor([ms_dev], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -278,14 +283,17 @@ def main():
     barrier()
     t_e2e0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        ctx.set_mesh(h_xyz, h_tri)
-        ctx.build_items(w["metric"], w["gradation"], h_ind, h_pd)
-        ctx.set_num_clusters(K)
-        ctx.set_clustering(h_cl0)
-        r = ctx.minimize(**mparams)
-        ctx.clustering(h_out)
-        sums, cen, en, sz = ctx.cluster_stats()
+        tt = [time.perf_counter()]
+        ctx.set_mesh(h_xyz, h_tri); tt.append(time.perf_counter())
+        ctx.build_items(w["metric"], w["gradation"], h_ind, h_pd); tt.append(time.perf_counter())
+        ctx.set_num_clusters(K); tt.append(time.perf_counter())
+        ctx.set_clustering(h_cl0); tt.append(time.perf_counter())
+        r = ctx.minimize(**mparams); tt.append(time.perf_counter())
+        ctx.clustering(h_out); tt.append(time.perf_counter())
+        sums, cen, en, sz = ctx.cluster_stats(); tt.append(time.perf_counter())
         e2e_tests += r["tests"]
+        log(f"[rank {rank}] e2e step: " + ", ".join(f"{n} {1e3 * (b - a):.1f} ms" for n, a, b in zip(
+            ("set_mesh", "build_items", "set_num_clusters", "set_clustering", "minimize", "get_clustering", "get_cluster_stats"), tt, tt[1:])))
     barrier()
     t_e2e = time.perf_counter() - t_e2e0
     h2d = h_xyz.nbytes + h_tri.nbytes + h_cl0.nbytes + (h_ind.nbytes if h_ind is not None else 0) + (h_pd.nbytes if h_pd is not None else 0)
