@@ -94,6 +94,13 @@ extern "C" int acvd_create(acvd_ctx** out, int device) {
         c->device = device;
         ACVD_CUDA(cudaSetDevice(device));
         ACVD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        {   // keep freed blocks in the pool (the default threshold 0 returns them to the driver at every synchronisation)
+            cudaMemPool_t pool;
+            ACVD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t keep = ~0ull;
+            ACVD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        AllocScope alloc_scope(c->stream);
         for (auto& ev : c->ev) ACVD_CUDA(cudaEventCreate(&ev));
         ACVD_CUDA(cudaMallocHost(&c->h_ctr, kRoundSlots * sizeof(RoundCounters)));
         ACVD_CUDA(cudaMallocHost(&c->h_scalars, (8 + kRoundSlots) * sizeof(unsigned long long)));

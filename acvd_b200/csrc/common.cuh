@@ -34,6 +34,13 @@ inline int grid_for(int64_t n, int threads = kThreads, int blocks_per_sm = 8) {
     return (int)(need < cap ? need : cap);
 }
 
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync) on the stream of the context
+// whose API call is running: temporaries of one call are recycled by the next instead of going back to the driver
+// (cudaMalloc / cudaFree of multi-GB scratch cost more than the kernels that use it).  Outside an API call
+// (context teardown) the plain synchronous calls are used.
+inline thread_local cudaStream_t g_alloc_stream = nullptr;
+inline thread_local bool g_alloc_async = false;
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -42,11 +49,15 @@ struct DevBuf {
         if (count <= n && p) return;
         release();
         if (count == 0) return;
-        ACVD_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (g_alloc_async) ACVD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), g_alloc_stream));
+        else ACVD_CUDA(cudaMalloc(&p, count * sizeof(T)));
         n = count;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (g_alloc_async) cudaFreeAsync(p, g_alloc_stream);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }

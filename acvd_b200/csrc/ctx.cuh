@@ -92,10 +92,16 @@ inline int fail(acvd_ctx* c, int code, const std::string& msg) {
     return code;
 }
 
+struct AllocScope {   // routes DevBuf allocations of this API call to the context's stream-ordered pool
+    AllocScope(cudaStream_t s) { g_alloc_stream = s; g_alloc_async = true; }
+    ~AllocScope() { g_alloc_stream = nullptr; g_alloc_async = false; }
+};
+
 #define ACVD_API_BEGIN(ctx)                                                          \
     if (!(ctx)) return fail(nullptr, ACVD_EINVAL, "null context");                   \
     try {                                                                            \
-        ACVD_CUDA(cudaSetDevice((ctx)->device));
+        ACVD_CUDA(cudaSetDevice((ctx)->device));                                     \
+        AllocScope _alloc_scope((ctx)->stream);
 #define ACVD_API_END(ctx)                                                            \
     }                                                                                \
     catch (const CudaError& e) {                                                     \
