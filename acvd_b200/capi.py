@@ -60,6 +60,7 @@ SYMBOLS = [
     ("acvd_set_mesh", C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     ("acvd_get_num_edges", C.c_int, [_vp, C.POINTER(_i64)]),
     ("acvd_get_csr", C.c_int, [_vp, _vp, _vp]),
+    ("acvd_curvature", C.c_int, [_vp, _i32, _vp, _vp]),
     ("acvd_build_items", C.c_int, [_vp, C.c_int, _d, _vp, _vp]),
     ("acvd_set_items", C.c_int, [_vp, C.c_int, _vp]),
     ("acvd_get_items", C.c_int, [_vp, _vp]),
@@ -154,6 +155,13 @@ class Context:
         col = np.zeros(2 * E, dtype=np.int32)
         self._ck(self.L.acvd_get_csr(self.h, _p(rp), _p(col)))
         return rp, col
+
+    def curvature(self, ring_size=3, principal_directions=True):
+        """vtkCurvatureMeasure (polynomial fitting, vertices, n-ring): (indicator[V] float64, info[V, 6] float32 or None)."""
+        ind = np.zeros(self.V)
+        info = np.zeros((self.V, 6), dtype=np.float32) if principal_directions else None
+        self._ck(self.L.acvd_curvature(self.h, int(ring_size), _p(ind), _p(info)))
+        return ind, info
 
     def build_items(self, metric="iso", gradation=0.0, custom_weights=None, principal_dirs=None):
         m = METRICS[metric] if isinstance(metric, str) else int(metric)

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "cleanup.cuh"
+#include "curvature.cuh"
 #include "common.cuh"
 #include "ctx.cuh"
 #include "host_sampling.hpp"
@@ -219,6 +220,41 @@ extern "C" int acvd_get_csr(acvd_ctx* c, int32_t* row_ptr, int32_t* col) {
     if (!c->V) throw std::runtime_error("acvd_get_csr: no mesh");
     if (row_ptr) ACVD_CUDA(cudaMemcpy(row_ptr, c->row_ptr.p, ((size_t)c->V + 1) * sizeof(int), cudaMemcpyDeviceToHost));
     if (col) ACVD_CUDA(cudaMemcpy(col, c->col.p, (size_t)c->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// curvature (the inputs of the gradation > 0 runs)
+extern "C" int acvd_curvature(acvd_ctx* c, int32_t ring_size, double* indicator, float* info6) {
+    ACVD_API_BEGIN(c)
+    if (!c->V || !indicator) throw std::runtime_error("acvd_curvature: set the mesh first");
+    if (ring_size < 1) throw std::runtime_error("acvd_curvature: ring_size must be >= 1");
+    const int V = c->V;
+    DevBuf<double> d_ind;
+    DevBuf<float> d_info;
+    DevBuf<int> d_big, d_scratch;
+    d_ind.alloc(V); d_big.alloc(V);
+    if (info6) d_info.alloc(6 * (size_t)V);
+    ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    CurvMesh M{V, c->row_ptr.p, c->col.p, c->vf_ptr.p, c->vf_keys.p, c->xyz.p, c->tri.p};
+    k_curvature<<<grid_for(V, 128, 16), 128, 0, c->stream>>>(M, ring_size, d_ind.p, info6 ? d_info.p : nullptr, d_big.p, c->scalars.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t n_big = (int64_t)c->h_scalars[0];
+    if (n_big > 0) {   // neighbourhoods that did not fit the local list
+        d_scratch.alloc((size_t)n_big * kCurvGlobalCap);
+        int* d_failed = reinterpret_cast<int*>(c->scalars.p + 1);
+        k_curvature_big<<<grid_for(n_big, 128, 16), 128, 0, c->stream>>>(M, ring_size, d_ind.p, info6 ? d_info.p : nullptr, d_big.p, (int)n_big,
+                                                                         d_scratch.p, d_failed);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 1, c->scalars.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->h_scalars[1] != 0) throw std::runtime_error("acvd_curvature: a vertex neighbourhood exceeds 8192 vertices");
+    }
+    ACVD_CUDA(cudaMemcpyAsync(indicator, d_ind.p, (size_t)V * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (info6) ACVD_CUDA(cudaMemcpyAsync(info6, d_info.p, 6 * (size_t)V * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
     ACVD_API_END(c)
 }
 

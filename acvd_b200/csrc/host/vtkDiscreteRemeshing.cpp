@@ -62,95 +62,41 @@ void vtkDiscreteRemeshingB200::CheckSubsamplingRatio() {
             for (size_t i = n_old; i < n_new; i++) ind[i] = 0.5 * (CustomIndicator[(size_t)Parent1[i]] + CustomIndicator[(size_t)Parent2[i]]);
             CustomIndicator.swap(ind);
         }
+        if (!PrincipalDirections.empty()) {   // same linear interpolation for the (sqrt|k| d) pairs
+            const size_t n_old = (size_t)Input->GetNumberOfPoints(), n_new = (size_t)next->GetNumberOfPoints();
+            std::vector<float> pd(6 * n_new);
+            for (size_t i = 0; i < 6 * n_old; i++) pd[i] = PrincipalDirections[i];
+            for (size_t i = n_old; i < n_new; i++)
+                for (int d = 0; d < 6; d++)
+                    pd[6 * i + d] = 0.5f * (PrincipalDirections[6 * (size_t)Parent1[i] + d] + PrincipalDirections[6 * (size_t)Parent2[i] + d]);
+            PrincipalDirections.swap(pd);
+        }
         if (!OriginalInput) OriginalInput = Input; else Input->Delete();
         Input = next;
         NumberOfSubdivisionsBeforeClustering++;
     }
 }
 
-// Curvature indicator sqrt(k1^2 + k2^2) and principal directions when the metric needs them and the caller
-// supplied none.  The reference fits a polynomial patch over the 3-ring (vtkCurvatureMeasure, SURVEY §8f-2, not
-// rebuilt yet); this build fits the second fundamental form to the normal curvatures of the 1-ring edges.
-// Runs that rely on it say so on the console.
+// Curvature indicator sqrt(k1^2 + k2^2) and principal directions when the metric needs them and the caller supplied
+// none: vtkCurvatureMeasure with polynomial fitting over the 3-ring (DiscreteRemeshing/vtkDiscreteRemeshing.h:640-653),
+// computed on the device (acvd_curvature) on the mesh as given, i.e. before any subdivision; CheckSubsamplingRatio then
+// interpolates it to the midpoints (:733-745).
 void vtkDiscreteRemeshingB200::SamplingPreProcessing() {
     const bool need_ind = Metric.IsCurvatureIndicatorNeeded() && CustomIndicator.empty();
     const bool need_pd = Metric.IsPrincipalDirectionsNeeded() && PrincipalDirections.empty();
     if (!need_ind && !need_pd) return;
     const vtkIdType nv = Input->GetNumberOfPoints(), nf = Input->GetNumberOfCells();
-    cout << "Curvature: discrete per-vertex estimate (normal-curvature tensor over the 1-ring); vtkCurvatureMeasure's "
-            "polynomial fitting over the 3-ring is not part of this build" << endl;
-    const float* X = Input->Points();
-    const int* T = Input->Triangles();
-    // area-weighted vertex normals
-    std::vector<double> nrm((size_t)nv * 3, 0.0);
-    for (vtkIdType f = 0; f < nf; f++) {
-        const int v[3] = {T[3 * f], T[3 * f + 1], T[3 * f + 2]};
-        double p[3][3];
-        for (int k = 0; k < 3; k++) for (int d = 0; d < 3; d++) p[k][d] = X[3 * (size_t)v[k] + d];
-        const double e1[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
-        const double e2[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
-        const double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-        for (int k = 0; k < 3; k++) for (int d = 0; d < 3; d++) nrm[3 * (size_t)v[k] + d] += cr[d];
+    if (!Ctx && !Check(acvd_create(&Ctx, Device), "acvd_create")) {
+        cout << "ERROR : " << acvd_last_error(nullptr) << endl;
+        return;
     }
-    if (need_ind) CustomIndicator.assign((size_t)nv, 0.0);
-    if (need_pd) PrincipalDirections.assign((size_t)nv * 6, 0.0f);
-    vtkIdList* nb = vtkIdList::New();
-    for (vtkIdType v = 0; v < nv; v++) {
-        double* n = &nrm[3 * (size_t)v];
-        const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-        if (nl <= 0) continue;
-        for (int d = 0; d < 3; d++) n[d] /= nl;
-        // tangent frame
-        double a[3] = {std::fabs(n[0]) < 0.9 ? 1.0 : 0.0, std::fabs(n[0]) < 0.9 ? 0.0 : 1.0, 0.0};
-        double t1[3] = {a[1] * n[2] - a[2] * n[1], a[2] * n[0] - a[0] * n[2], a[0] * n[1] - a[1] * n[0]};
-        const double t1l = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
-        for (int d = 0; d < 3; d++) t1[d] /= t1l;
-        const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
-        // least squares for the second fundamental form: kn(theta) = A c^2 + 2 B c s + C s^2
-        double M[3][3] = {{0}}, rhs[3] = {0, 0, 0};
-        Input->GetVertexNeighbours(v, nb);
-        for (vtkIdType j = 0; j < nb->GetNumberOfIds(); j++) {
-            const vtkIdType u = nb->GetId(j);
-            double e[3];
-            for (int d = 0; d < 3; d++) e[d] = (double)X[3 * (size_t)u + d] - (double)X[3 * (size_t)v + d];
-            const double l2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-            if (l2 <= 0) continue;
-            const double kn = -2.0 * (n[0] * e[0] + n[1] * e[1] + n[2] * e[2]) / l2;   // outward normal: convex -> positive
-            double c = e[0] * t1[0] + e[1] * t1[1] + e[2] * t1[2], sn = e[0] * t2[0] + e[1] * t2[1] + e[2] * t2[2];
-            const double cl = std::sqrt(c * c + sn * sn);
-            if (cl <= 0) continue;
-            c /= cl; sn /= cl;
-            const double row[3] = {c * c, 2 * c * sn, sn * sn};
-            for (int r = 0; r < 3; r++) { rhs[r] += row[r] * kn; for (int q = 0; q < 3; q++) M[r][q] += row[r] * row[q]; }
-        }
-        // solve the 3x3 normal equations (Cramer)
-        auto det3 = [](double m[3][3]) {
-            return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
-                   m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
-        };
-        const double D = det3(M);
-        if (std::fabs(D) < 1e-300) continue;
-        double sol[3];
-        for (int k = 0; k < 3; k++) {
-            double Mk[3][3];
-            for (int r = 0; r < 3; r++) for (int q = 0; q < 3; q++) Mk[r][q] = (q == k) ? rhs[r] : M[r][q];
-            sol[k] = det3(Mk) / D;
-        }
-        const double A = sol[0], B = sol[1], C = sol[2];
-        const double tr = A + C, df = std::sqrt((A - C) * (A - C) * 0.25 + B * B);
-        double k1 = 0.5 * tr + df, k2 = 0.5 * tr - df;
-        double ang = 0.5 * std::atan2(2 * B, A - C);
-        double d1[3], d2[3];
-        for (int d = 0; d < 3; d++) { d1[d] = std::cos(ang) * t1[d] + std::sin(ang) * t2[d]; d2[d] = -std::sin(ang) * t1[d] + std::cos(ang) * t2[d]; }
-        if (std::fabs(k2) > std::fabs(k1)) { std::swap(k1, k2); for (int d = 0; d < 3; d++) std::swap(d1[d], d2[d]); }
-        if (need_ind) CustomIndicator[(size_t)v] = std::sqrt(k1 * k1 + k2 * k2);
-        if (need_pd) {
-            // (sqrt|ka| da, sqrt|kb| db), larger |k| first, float32 (vtkCurvatureMeasure.cxx:445-484, :742)
-            const double s1 = std::sqrt(std::fabs(k1)), s2 = std::sqrt(std::fabs(k2));
-            for (int d = 0; d < 3; d++) { PrincipalDirections[6 * (size_t)v + d] = (float)(s1 * d1[d]); PrincipalDirections[6 * (size_t)v + 3 + d] = (float)(s2 * d2[d]); }
-        }
-    }
-    nb->Delete();
+    cout << "Computing Curvature ........" << endl;
+    if (!Check(acvd_set_mesh(Ctx, (int32_t)nv, (int32_t)nf, Input->Points(), Input->Triangles()), "acvd_set_mesh")) return;
+    std::vector<double> ind((size_t)nv);
+    std::vector<float> pd(need_pd ? 6 * (size_t)nv : 0);
+    if (!Check(acvd_curvature(Ctx, 3, ind.data(), need_pd ? pd.data() : nullptr), "acvd_curvature")) return;
+    if (need_ind) CustomIndicator.swap(ind);
+    if (need_pd) PrincipalDirections.swap(pd);
 }
 
 void vtkDiscreteRemeshingB200::FetchClusters() {
@@ -331,8 +277,8 @@ int vtkDiscreteRemeshingB200::DetectNonManifoldOutputVertices() {
 
 void vtkDiscreteRemeshingB200::Remesh() {
     if (!Input) { cout << "ERROR : no input mesh" << endl; return; }
+    SamplingPreProcessing();      // on the mesh as given (the reference measures curvature before subdividing, :641-644)
     CheckSubsamplingRatio();
-    SamplingPreProcessing();
     if (ConsoleOutput)
         cout << "Input mesh: " << Input->GetNumberOfPoints() << " vertices	and	" << Input->GetNumberOfCells() << " faces" << endl;
     bool compute = true;

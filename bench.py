@@ -280,9 +280,16 @@ def main():
     # ---- end to end through the C ABI from pinned host buffers (fresh context state every step)
     e2e_tests = 0
     _k5, h_out = pinned(np.zeros(V, dtype=np.int32))
+    # one untimed pass first (when e2e is measured at all): the first pass after the device-resident steps re-grows
+    # the memory pool for the mesh-build scratch, a one-off of the process, not of the path
+    e2e_passes = args.e2e_steps + (1 if args.e2e_steps else 0)
     barrier()
     t_e2e0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    for e2e_it in range(e2e_passes):
+        if e2e_it == 1:
+            barrier()
+            t_e2e0 = time.perf_counter()
+            e2e_tests = 0
         tt = [time.perf_counter()]
         ctx.set_mesh(h_xyz, h_tri); tt.append(time.perf_counter())
         ctx.build_items(w["metric"], w["gradation"], h_ind, h_pd); tt.append(time.perf_counter())

@@ -59,6 +59,13 @@ int acvd_set_mesh(acvd_ctx* ctx, int32_t V, int32_t F, const float* xyz, const i
 int acvd_get_num_edges(acvd_ctx* ctx, int64_t* E);
 int acvd_get_csr(acvd_ctx* ctx, int32_t* row_ptr /*V+1*/, int32_t* col /*2E*/);
 
+/* vtkCurvatureMeasure with ComputationMethod 1 (polynomial fitting), ElementsType 1 (vertices) and the n-ring
+ * neighbourhood (Common/vtkCurvatureMeasure.cxx:188-508, 625-718; defaults :1175-1196: ring_size 3), as called by
+ * vtkDiscreteRemeshing::SamplingPreProcessing (DiscreteRemeshing/vtkDiscreteRemeshing.h:640-653).
+ * indicator[V] = sqrt(k1^2 + k2^2) (the CustomWeights of acvd_build_items); info6[6 V] = (sqrt|k_a| d_a, sqrt|k_b| d_b),
+ * larger |k| first, float32 (the PrincipalDirections of the anisotropic metrics), may be NULL. */
+int acvd_curvature(acvd_ctx* ctx, int32_t ring_size, double* indicator /*V*/, float* info6 /*6V or NULL*/);
+
 /* ---- items: replaces Metric::BuildMetric (vtkIsotropicMetricForClustering.h:214-271,
  * vtkQEMetricForClustering.h:297-345, vtk(Quadric)AnisotropicMetricForClustering.h BuildMetric):
  * vertex areas, weights = area * indicator^gradation clamped to [mean/R, mean*R], Value = w*p,

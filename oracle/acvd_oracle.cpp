@@ -138,6 +138,117 @@ double triangle_area(const double* p1, const double* p2, const double* p3) {
     return 0.5 * std::sqrt(nx * nx + ny * ny + nz * nz);
 }
 
+// ---- [VTK, from memory] helpers of vtkCurvatureMeasure's polynomial fitting ------------------------------------
+// vtkMath::InvertMatrix = LUFactorLinearSystem (Crout, implicit scaling, |pivot| <= 1e-12 -> singular) + one
+// LUSolveLinearSystem per column of the identity.  A is n x n row-major and is destroyed.
+int vtk_invert_matrix(double* A, double* AI, int n) {
+    std::vector<int> index(n);
+    std::vector<double> scale(n), col(n);
+    for (int i = 0; i < n; i++) {
+        double largest = 0;
+        for (int j = 0; j < n; j++) largest = std::max(largest, std::fabs(A[i * n + j]));
+        if (largest == 0.0) return 0;
+        scale[i] = 1.0 / largest;
+    }
+    for (int j = 0; j < n; j++) {
+        for (int i = 0; i < j; i++) {
+            double sum = A[i * n + j];
+            for (int k = 0; k < i; k++) sum -= A[i * n + k] * A[k * n + j];
+            A[i * n + j] = sum;
+        }
+        double largest = 0;
+        int maxI = j;
+        for (int i = j; i < n; i++) {
+            double sum = A[i * n + j];
+            for (int k = 0; k < j; k++) sum -= A[i * n + k] * A[k * n + j];
+            A[i * n + j] = sum;
+            double t = scale[i] * std::fabs(sum);
+            if (t >= largest) { largest = t; maxI = i; }
+        }
+        if (j != maxI) {
+            for (int k = 0; k < n; k++) std::swap(A[maxI * n + k], A[j * n + k]);
+            scale[maxI] = scale[j];
+        }
+        index[j] = maxI;
+        if (std::fabs(A[j * n + j]) <= 1.0e-12) return 0;
+        if (j != n - 1) {
+            double t = 1.0 / A[j * n + j];
+            for (int i = j + 1; i < n; i++) A[i * n + j] *= t;
+        }
+    }
+    for (int c = 0; c < n; c++) {
+        for (int i = 0; i < n; i++) col[i] = (i == c) ? 1.0 : 0.0;
+        int ii = -1;
+        for (int i = 0; i < n; i++) {            // forward substitution with the row permutation
+            int idx = index[i];
+            double sum = col[idx];
+            col[idx] = col[i];
+            if (ii >= 0) for (int j = ii; j <= i - 1; j++) sum -= A[i * n + j] * col[j];
+            else if (sum != 0.0) ii = i;
+            col[i] = sum;
+        }
+        for (int i = n - 1; i >= 0; i--) {       // back substitution
+            double sum = col[i];
+            for (int j = i + 1; j < n; j++) sum -= A[i * n + j] * col[j];
+            col[i] = sum / A[i * n + i];
+        }
+        for (int i = 0; i < n; i++) AI[i * n + c] = col[i];
+    }
+    return 1;
+}
+
+// vtkMath::JacobiN for n = 2 (Numerical Recipes "jacobi" on the UPPER triangle, at most 20 sweeps), eigenvalues
+// sorted in decreasing order (">=" comparison), each eigenvector (a column of v) negated when it has fewer than
+// ceil(n/2) non-negative components.
+int vtk_jacobi2(double a[2][2], double w[2], double v[2][2]) {
+    const int n = 2;
+    double b[2], z[2];
+    for (int ip = 0; ip < n; ip++) {
+        for (int iq = 0; iq < n; iq++) v[ip][iq] = 0.0;
+        v[ip][ip] = 1.0;
+        b[ip] = w[ip] = a[ip][ip];
+        z[ip] = 0.0;
+    }
+    int i;
+    for (i = 0; i < 20; i++) {
+        double sm = std::fabs(a[0][1]);
+        if (sm == 0.0) break;
+        double tresh = (i < 3) ? 0.2 * sm / (n * n) : 0.0;
+        {
+            const int ip = 0, iq = 1;
+            double g = 100.0 * std::fabs(a[ip][iq]);
+            if (i > 3 && (std::fabs(w[ip]) + g) == std::fabs(w[ip]) && (std::fabs(w[iq]) + g) == std::fabs(w[iq])) a[ip][iq] = 0.0;
+            else if (std::fabs(a[ip][iq]) > tresh) {
+                double h = w[iq] - w[ip], t;
+                if ((std::fabs(h) + g) == std::fabs(h)) t = a[ip][iq] / h;
+                else {
+                    double theta = 0.5 * h / a[ip][iq];
+                    t = 1.0 / (std::fabs(theta) + std::sqrt(1.0 + theta * theta));
+                    if (theta < 0.0) t = -t;
+                }
+                double c = 1.0 / std::sqrt(1 + t * t), sn = t * c, tau = sn / (1.0 + c);
+                h = t * a[ip][iq];
+                z[ip] -= h; z[iq] += h; w[ip] -= h; w[iq] += h;
+                a[ip][iq] = 0.0;
+                for (int j = 0; j < n; j++) {       // rotate the eigenvector columns ip, iq
+                    double gg = v[j][ip], hh = v[j][iq];
+                    v[j][ip] = gg - sn * (hh + gg * tau);
+                    v[j][iq] = hh + sn * (gg - hh * tau);
+                }
+            }
+        }
+        for (int ip = 0; ip < n; ip++) { b[ip] += z[ip]; w[ip] = b[ip]; z[ip] = 0.0; }
+    }
+    if (i >= 20) return 0;
+    if (w[1] >= w[0]) { std::swap(w[0], w[1]); std::swap(v[0][0], v[0][1]); std::swap(v[1][0], v[1][1]); }
+    for (int j = 0; j < n; j++) {
+        int num_pos = 0;
+        for (int k = 0; k < n; k++) if (v[k][j] >= 0.0) num_pos++;
+        if (num_pos < 1) for (int k = 0; k < n; k++) v[k][j] *= -1.0;
+    }
+    return 1;
+}
+
 struct Ctx {
     // ---- mesh in the reference's edge order (Common/vtkSurfaceBase.cxx:1166-1221, 1407-1468) ----
     int V = 0, F = 0, E = 0;
@@ -230,6 +341,134 @@ struct Ctx {
         point(tri[3 * f], a); point(tri[3 * f + 1], b); point(tri[3 * f + 2], c);
         return triangle_area(a, b, c);
     }
+    // ---------------- vtkCurvatureMeasure, polynomial fitting on vertices ----------------
+    // vtkNeighbourhoodComputation::ComputeNRingCells, CellType 1 (Common/vtkNeighbourhoodComputation.cxx:38-110):
+    // faces around the vertex, then ring_size expansions; every expansion visits the edge ring of each not yet
+    // visited vertex of the current front, appends the far end to the next front and the edge's faces to the list.
+    void nring_faces(int v0, int ring_size, std::vector<int>& flist, std::vector<unsigned char>& face_tag,
+                     std::vector<unsigned char>& vert_tag, std::vector<int>& touched_v) const {
+        flist.clear();
+        touched_v.clear();
+        int fl[256];
+        int n = vertex_faces(v0, fl);
+        for (int i = 0; i < n; i++) { flist.push_back(fl[i]); face_tag[fl[i]] = 1; }
+        std::vector<int> vlist{v0}, vlist2;
+        for (int j = 0; j < ring_size; j++) {
+            vlist2.clear();
+            for (int v1 : vlist) {
+                if (vert_tag[v1]) continue;
+                vert_tag[v1] = 1;
+                touched_v.push_back(v1);
+                for (int l = 0; l < ring_len[v1]; l++) {
+                    int e = ring[ring_ptr[v1] + l];
+                    vlist2.push_back(other(e, v1));
+                    int f1 = ep1[e], f2 = ep2[e];
+                    if (f1 >= 0) {
+                        if (!face_tag[f1]) { flist.push_back(f1); face_tag[f1] = 1; }
+                        if (f2 >= 0 && !face_tag[f2]) { flist.push_back(f2); face_tag[f2] = 1; }
+                    }
+                }
+            }
+            vlist.swap(vlist2);
+        }
+        for (int f : flist) face_tag[f] = 0;
+        for (int u : touched_v) vert_tag[u] = 0;
+    }
+
+    // vtkSinglePolynomialMeasure::ComputeFitting (Common/vtkCurvatureMeasure.cxx:188-508): z = q0 + q1 x + q2 y +
+    // q3 x^2 + q4 xy + q5 y^2 over the face barycentres in the frame of the area-weighted mean normal; returns
+    // sqrt(k1^2 + k2^2), info6 = (sqrt|k_a| d_a, sqrt|k_b| d_b) with the larger |k| first.
+    double curvature_fit(const std::vector<int>& flist, double* info) const {
+        for (int i = 0; i < 6; i++) info[i] = 0;
+        const int n = (int)flist.size();
+        double SArea = 0, Origin[3] = {0, 0, 0}, Frame[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        std::vector<double> bary(3 * (size_t)n);
+        for (int j = 0; j < n; j++) {
+            int f = flist[j];
+            double p1[3], p2[3], p3[3];
+            point(tri[3 * f], p1); point(tri[3 * f + 1], p2); point(tri[3 * f + 2], p3);
+            // [VTK, from memory] vtkTriangle::ComputeNormal: (p3 - p2) x (p1 - p2), normalised when non-zero
+            double ax = p3[0] - p2[0], ay = p3[1] - p2[1], az = p3[2] - p2[2];
+            double bx = p1[0] - p2[0], by = p1[1] - p2[1], bz = p1[2] - p2[2];
+            double N[3] = {ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx};
+            double len = std::sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+            if (len != 0.0) { N[0] /= len; N[1] /= len; N[2] /= len; }
+            // vtkSurface::GetCellMassProperties (Common/vtkSurface.cxx:1380-1420)
+            double Area = triangle_area(p1, p2, p3), B[3];
+            for (int k = 0; k < 3; k++) {
+                B[k] = Area * (p1[k] + p2[k] + p3[k]) / 3.0;
+                if (Area > 0) B[k] /= Area;
+                bary[3 * j + k] = B[k];
+                Origin[k] += Area * B[k];
+                Frame[0][k] += Area * N[k];
+            }
+            SArea += Area;
+        }
+        for (int k = 0; k < 3; k++) Origin[k] /= SArea;
+        auto normalize = [](double* x) { double l = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]); if (l != 0.0) { x[0] /= l; x[1] /= l; x[2] /= l; } };
+        auto cross = [](const double* a, const double* b, double* c) {
+            double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+            c[0] = x; c[1] = y; c[2] = z;
+        };
+        normalize(Frame[0]);
+        for (int k = 0; k < 3; k++) Frame[2][k] = Frame[0][k];
+        Frame[1][1] = Frame[2][0]; Frame[1][2] = Frame[2][1]; Frame[1][0] = Frame[2][2];
+        cross(Frame[1], Frame[2], Frame[0]);
+        normalize(Frame[0]);
+        cross(Frame[2], Frame[0], Frame[1]);
+        if (n <= 6) return 0.0;                              // NumberOfCellsWithSmallNeighbourhood
+        std::vector<double> X(6 * (size_t)n), Z(n);
+        double h = 0;
+        for (int j = 0; j < n; j++) {
+            double d[3] = {bary[3 * j] - Origin[0], bary[3 * j + 1] - Origin[1], bary[3 * j + 2] - Origin[2]};
+            double x = d[0] * Frame[0][0] + d[1] * Frame[0][1] + d[2] * Frame[0][2];
+            double y = d[0] * Frame[1][0] + d[1] * Frame[1][1] + d[2] * Frame[1][2];
+            double z = d[0] * Frame[2][0] + d[1] * Frame[2][1] + d[2] * Frame[2][2];
+            double* r = &X[6 * (size_t)j];
+            r[0] = 1.0; r[1] = x; r[2] = y; r[3] = x * x; r[4] = x * y; r[5] = y * y;
+            Z[j] = z;
+            h += std::sqrt(x * x + y * y);
+        }
+        h /= (double)n;
+        for (int j = 0; j < n; j++) {
+            double* r = &X[6 * (size_t)j];
+            r[1] /= h; r[2] /= h; r[3] /= h * h; r[4] /= h * h; r[5] /= h * h;
+        }
+        // SolveLeastSquares (:510-621): normal equations, upper half accumulated then mirrored, vtkMath::InvertMatrix
+        double XXt[36], XXtI[36], XYt[6], Q[6];
+        for (int i = 0; i < 36; i++) XXt[i] = 0;
+        for (int i = 0; i < 6; i++) XYt[i] = 0;
+        for (int k = 0; k < n; k++) {
+            const double* r = &X[6 * (size_t)k];
+            for (int i = 0; i < 6; i++) {
+                for (int j = i; j < 6; j++) XXt[i * 6 + j] += r[i] * r[j];
+                XYt[i] += r[i] * Z[k];
+            }
+        }
+        for (int i = 0; i < 6; i++) for (int j = 0; j < i; j++) XXt[i * 6 + j] = XXt[j * 6 + i];
+        if (!vtk_invert_matrix(XXt, XXtI, 6)) return 0.0;   // NumberOfBadMatrices
+        for (int i = 0; i < 6; i++) { Q[i] = 0; for (int k = 0; k < 6; k++) Q[i] += XXtI[i * 6 + k] * XYt[k]; }
+        Q[1] /= h; Q[2] /= h; Q[3] /= h * h; Q[4] /= h * h; Q[5] /= h * h;
+        double E = 1.0 + Q[1] * Q[1], Fm = Q[1] * Q[2], G = 1.0 + Q[2] * Q[2];
+        double den = std::sqrt(Q[1] * Q[1] + 1.0 + Q[2] * Q[2]);
+        double e = 2.0 * Q[3] / den, f = 2.0 * Q[4] / den, g = 2.0 * Q[5] / den;
+        double A[4] = {E, Fm, Fm, G}, B[4];
+        if (!vtk_invert_matrix(A, B, 2)) return 0.0;
+        double S[2][2];
+        S[0][0] = -(e * B[0] + f * B[2]);
+        S[1][0] = -(e * B[1] + f * B[3]);
+        S[0][1] = -(f * B[0] + g * B[2]);
+        S[1][1] = -(f * B[1] + g * B[3]);
+        double w[2], ev[2][2];
+        if (!vtk_jacobi2(S, w, ev)) return 0.0;
+        for (int i = 0; i < 2; i++)
+            for (int j = 0; j < 2; j++)
+                for (int k = 0; k < 3; k++) info[k + 3 * j] += std::sqrt(std::fabs(w[j])) * ev[i][j] * Frame[i][k];
+        if (std::fabs(w[0]) < std::fabs(w[1]))
+            for (int i = 0; i < 3; i++) std::swap(info[i], info[i + 3]);
+        return std::sqrt(w[0] * w[0] + w[1] * w[1]);
+    }
+
     // Common/vtkSurface.cxx:1342-1359
     double vertex_area(int v) const {
         int fl[256]; int n = vertex_faces(v, fl);
@@ -924,6 +1163,21 @@ void orc_boundary_flags(void* h, unsigned char* out) {
     }
 }
 // cluster adjacency: sorted unique (lo,hi) pairs of clusters joined by a mesh edge. Returns count.
+// vtkCurvatureMeasure (ComputationMethod 1 = polynomial fitting, ElementsType 1 = vertices, n-ring neighbourhood;
+// Common/vtkCurvatureMeasure.cxx:625-718, defaults :1175-1196): indicator[V] (double), info[6 V] (float, as the
+// reference stores CellsCurvatureInfo in a vtkFloatArray, :742)
+void orc_curvature(void* h, int ring_size, double* indicator, float* info6) {
+    Ctx* c = (Ctx*)h;
+    std::vector<int> flist, touched;
+    std::vector<unsigned char> face_tag(c->F, 0), vert_tag(c->V, 0);
+    for (int v = 0; v < c->V; v++) {
+        c->nring_faces(v, ring_size, flist, face_tag, vert_tag, touched);
+        double info[6];
+        indicator[v] = c->curvature_fit(flist, info);
+        if (info6) for (int i = 0; i < 6; i++) info6[6 * (size_t)v + i] = (float)info[i];
+    }
+}
+
 int64_t orc_cluster_adjacency(void* h, int64_t* out, int64_t cap) {
     Ctx* c = (Ctx*)h; std::vector<int64_t> p;
     for (int e = 0; e < c->E; e++) {

@@ -53,6 +53,7 @@ def lib():
             ("orc_triangle_area", [vp, vp, vp], d), ("orc_mt19937_first", [vp, i], None),
             ("orc_dual_triangles", [vp, vp, i], i), ("orc_boundary_flags", [vp, vp], None),
             ("orc_cluster_adjacency", [vp, vp, C.c_int64], C.c_int64),
+            ("orc_curvature", [vp, i, vp, vp], None),
         ]:
             f = getattr(L, name)
             f.argtypes = args
@@ -119,6 +120,13 @@ class Oracle:
         out = np.zeros(self.V)
         lib().orc_vertex_areas(self.h, _p(out))
         return out
+
+    def curvature(self, ring_size=3):
+        """vtkCurvatureMeasure (polynomial fitting, vertices, n-ring): (indicator[V] float64, info[V, 6] float32)."""
+        ind = np.zeros(self.V)
+        info = np.zeros((self.V, 6), dtype=np.float32)
+        lib().orc_curvature(self.h, int(ring_size), _p(ind), _p(info))
+        return ind, info
 
     # metric
     def build_metric(self, metric="iso", gradation=0.0, custom_weights=None, principal_dirs=None):

@@ -309,3 +309,52 @@ def test_ellipsoid_principal_directions_generator():
     s, _ = meshgen.geodesic_icosphere(4)
     pds, inds = meshgen.ellipsoid_principal_directions(2.0 * s, axes=(2.0, 2.0, 2.0))
     assert np.allclose(inds, np.sqrt(2.0) / 2.0, rtol=1e-6)
+
+
+def _grid_height_field(n, fn, span=1.0):
+    """(n+1)^2 grid over [-span, span]^2 lifted by z = fn(x, y), two triangles per cell (CCW seen from +z)."""
+    xs = np.linspace(-span, span, n + 1)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    P = np.stack([X.ravel(), Y.ravel(), fn(X, Y).ravel()], axis=1).astype(np.float32)
+    idx = lambda i, j: i * (n + 1) + j
+    T = []
+    for i in range(n):
+        for j in range(n):
+            T.append([idx(i, j), idx(i + 1, j), idx(i + 1, j + 1)])
+            T.append([idx(i, j), idx(i + 1, j + 1), idx(i, j + 1)])
+    return P, np.asarray(T, dtype=np.int32)
+
+
+def test_curvature_oracle_known_answers(oracle_mod):
+    """vtkCurvatureMeasure restatement (polynomial fitting, vertices, 3-ring): sphere of radius R -> sqrt(2)/R and tangent
+    directions; plane -> 0; quadratic height field z = a x^2 + b y^2 -> principal curvatures 2a, 2b at the apex with
+    the larger one first; fewer than 7 faces in the neighbourhood -> 0."""
+    from acvd_b200 import meshgen
+    p, t = meshgen.geodesic_icosphere(16)
+    R = 2.0
+    o = oracle_mod.Oracle((R * p).astype(np.float32), t)
+    ind, info = o.curvature(3)
+    good = ind > 0                                   # the reference's frame construction degenerates where n ~ (1,1,1)/sqrt(3)
+    assert good.mean() > 0.99
+    assert np.allclose(np.median(ind[good]), np.sqrt(2.0) / R, rtol=0.02)
+    n = p / np.linalg.norm(p, axis=1)[:, None]
+    assert np.abs((info[:, :3] * n).sum(axis=1)).max() < 0.02 and np.abs((info[:, 3:] * n).sum(axis=1)).max() < 0.02
+    # plane
+    P, T = _grid_height_field(12, lambda x, y: 0.25 + 0 * x)
+    ind, info = oracle_mod.Oracle(P, T).curvature(3)
+    assert np.abs(ind).max() < 1e-6
+    # paraboloid: k = (2a, 2b) at the origin, larger |k| first along its axis
+    a, b = 0.8, 0.3
+    P, T = _grid_height_field(40, lambda x, y: a * x * x + b * y * y, span=0.2)
+    ind, info = oracle_mod.Oracle(P, T).curvature(3)
+    c = (40 + 1) * 20 + 20                           # centre vertex (0, 0)
+    assert np.allclose(P[c], 0, atol=1e-7)
+    assert np.allclose(ind[c], 2.0 * np.hypot(a, b), rtol=0.02)
+    d1, d2 = info[c, :3].astype(np.float64), info[c, 3:].astype(np.float64)
+    assert np.allclose(d1 @ d1, 2 * a, rtol=0.03) and np.allclose(d2 @ d2, 2 * b, rtol=0.05)
+    assert abs(d1[0]) > 0.99 * np.linalg.norm(d1) and abs(d2[1]) > 0.99 * np.linalg.norm(d2)
+    # tetrahedron: 4 faces <= 6 -> 0
+    P = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float32)
+    T = np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]], dtype=np.int32)
+    ind, info = oracle_mod.Oracle(P, T).curvature(3)
+    assert np.all(ind == 0) and np.all(info == 0)
