@@ -708,9 +708,10 @@ static bool plan_scan(acvd_ctx* c, ReassignArgs& A, int force_all, int t0, int t
 // after the round: decide the next round's mode from how much of the mesh was active (counters summed over ranks,
 // so every rank takes the same decision)
 static void update_density(acvd_ctx* c, RoundResult& r) {
-    // break-even points measured on C4: the TMA-staged dense bulk scan costs what the list-based scan costs on about
-    // half of the tiles; the exact rounds use the list-based kernel in both modes, where only the tile filter is saved
-    const double to_sparse = c->last_bulk ? 0.27 : 0.5, to_dense = c->last_bulk ? 0.55 : 0.6;
+    // break-even points measured on C4: a TMA-staged dense bulk scan (0.71 ms) costs what the list-based scan costs on
+    // 45 % of the tiles, and leaving dense mode costs one signature-rebuilding pass (1.6 ms), so bulk rounds stay dense
+    // until little is left; the exact rounds use the list-based kernel in both modes, where only the tile filter is saved
+    const double to_sparse = c->last_bulk ? 0.12 : 0.5, to_dense = c->last_bulk ? 0.45 : 0.6;
     if (c->last_all_tiles) {
         r.active_tiles = (unsigned long long)(((int64_t)c->V + 31) / 32);
         c->dense_next = r.boundary > 0 && (double)r.evaluated > to_sparse * (double)r.boundary;
