@@ -647,7 +647,7 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.round = c->round; A.force_all = force_all; A.bulk = 0; A.connexity = connexity; A.cfg = cfg;
     A.bulk_stage = 0; A.bulk_count_leave = 0; A.bulk_cen = c->bulk_cen.p; A.bulk_leave = c->leave_cnt.p;
     A.item_stride = payload_npad(c->metric);
-    A.all_tiles = 0; A.tile_begin = 0; A.tile_end = (c->V + 31) / 32; A.sig_mode = 0;
+    A.all_tiles = 0; A.tile_begin = 0; A.tile_end = (c->V + 31) / 32; A.sig_mode = 0; A.track_stale = 1;
     return A;
 }
 
@@ -700,9 +700,9 @@ static bool plan_scan(acvd_ctx* c, ReassignArgs& A, int force_all, int t0, int t
     const bool dense = force_all || c->dense_next;
     c->last_tile_count = t1 - t0;
     c->last_bulk = A.bulk;
-    if (dense) { A.all_tiles = 1; A.sig_mode = 1; c->sig_valid = false; c->last_all_tiles = 1; return false; }
-    if (!c->sig_valid) { A.all_tiles = 1; A.sig_mode = 2; c->sig_valid = true; c->last_all_tiles = 1; return false; }
-    A.all_tiles = 0; A.sig_mode = 0; c->last_all_tiles = 0;
+    if (dense) { A.all_tiles = 1; A.sig_mode = 1; A.track_stale = 0; c->sig_valid = false; c->last_all_tiles = 1; return false; }
+    if (!c->sig_valid) { A.all_tiles = 1; A.sig_mode = 2; A.track_stale = 1; c->sig_valid = true; c->last_all_tiles = 1; return false; }
+    A.all_tiles = 0; A.sig_mode = 0; A.track_stale = 1; c->last_all_tiles = 0;
     return true;
 }
 // after the round: decide the next round's mode from how much of the mesh was active (counters summed over ranks,

@@ -27,6 +27,7 @@ namespace acvd {
 
 // A vertex that changes cluster changes the signature of its own tile and of its neighbours' tiles.
 __device__ __forceinline__ void mark_tiles_stale(const ReassignArgs& A, int v) {
+    if (!A.track_stale) return;          // dense mode: the signatures are invalid as a whole and will be rebuilt for every tile
     A.tile_stale[v >> 5] = 1;
     for (int e = A.row_ptr[v]; e < A.row_ptr[v + 1]; e++) A.tile_stale[A.col[e] >> 5] = 1;
 }

@@ -57,6 +57,7 @@ struct ReassignArgs {
     int all_tiles;                      // dense round: scan tiles [tile_begin, tile_end) directly, no filter / list
     int tile_begin, tile_end;
     int sig_mode;                       // 0: rebuild stale signatures, 1: leave signatures alone, 2: rebuild all
+    int track_stale;                    // moves mark the tiles around them stale (only while the signatures are valid)
     int connexity;
     EvalCfg cfg;
 };

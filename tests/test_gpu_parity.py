@@ -340,16 +340,17 @@ def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle,
     assert r0["energy"] == r1["energy"]
 
 
-@pytest.mark.parametrize("name", ["C2", "C3"])
+@pytest.mark.parametrize("name", ["C2", "C3", "C4"])
 def test_full_size_properties(gpu_ctx_factory, name):
     """BASELINE-size configurations (C2: ACVDQ gradation 1.5, 2.6 M vertices -> 100 k clusters; C3: AnisotropicRemeshingQ
-    1.5, 1 M vertices -> 10 k) through size-independent properties: every cluster non-empty and connected, sizes sum to
-    V, energy below the initial one, a further round finds no improving move (idempotence), two runs identical."""
+    1.5, 1 M vertices -> 10 k; C4: ACVDQ, 40 M vertices -> 400 k, the bench workload) through size-independent
+    properties: every cluster non-empty and connected, sizes sum to V, energy below the initial one, a further round
+    finds no improving move (idempotence), two runs identical (C4: one run; scripts/c5_check.py does the same at 160 M)."""
     w = meshgen.workload(name)
     p, t, K = w["points"], w["triangles"], int(w["K"])
     uncon = 1 if w["metric"] == "qem" else 0
     runs = []
-    for _ in range(2):
+    for _ in range(1 if name == "C4" else 2):
         g = gpu_ctx_factory()
         g.set_mesh(p, t)
         g.build_items(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
@@ -372,7 +373,8 @@ def test_full_size_properties(gpu_ctx_factory, name):
         again = g.reassign_round(1, 3, 1)
         assert again["proposals"] == 0 and again["modifications"] == 0
         g.close()
-    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1]["energy"] == runs[1][1]["energy"]
+    if len(runs) == 2:
+        assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1]["energy"] == runs[1][1]["energy"]
 
 
 def test_bench_kernel_hook(gpu_ctx_factory, torus):
