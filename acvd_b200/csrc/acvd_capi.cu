@@ -538,26 +538,27 @@ extern "C" int acvd_recompute_statistics(acvd_ctx* c, int constrained, int qleve
 static int clean_clustering(acvd_ctx* c) {
     TraceScope ts(c, "clean_clustering");
     const int V = c->V, K = c->K;
-    c->label.alloc(V); c->comp_size.alloc(V); c->n_comp.alloc(K); c->winner.alloc(K);
+    c->label.alloc(V); c->comp_size.alloc(V); c->n_comp.alloc(K); c->winner.alloc(K); c->n_roots.alloc(K);
+    ACVD_CUDA(cudaMemsetAsync(c->n_roots.p, 0, (size_t)K * sizeof(int), c->stream));
     if (c->ell_w == 6)
-        k_cc_init<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
+        k_cc_init<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
     else
-        k_cc_init<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
+        k_cc_init<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
     ACVD_LAUNCH_CHECK();
     if (c->ell_w == 6)
-        k_cc_hook<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
+        k_cc_hook<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
     else
-        k_cc_hook<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p);
+        k_cc_hook<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
     ACVD_LAUNCH_CHECK();
-    k_cc_flatten<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->label.p);
+    k_cc_flatten<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->n_roots.p, c->label.p);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaMemsetAsync(c->comp_size.p, 0, (size_t)V * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->n_comp.p, 0, (size_t)K * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->winner.p, 0, (size_t)K * sizeof(unsigned long long), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
     const int* anchor = c->has_anchor ? c->anchor.p : nullptr;
-    k_cc_sizes<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, anchor);
-    k_cc_winner<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, c->n_comp.p, c->winner.p);
+    k_cc_sizes<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, anchor, c->n_roots.p);
+    k_cc_winner<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, c->n_comp.p, c->winner.p, c->n_roots.p);
     k_count_ge2<<<grid_for(K), kThreads, 0, c->stream>>>(K, c->n_comp.p, c->scalars.p + 1);
     k_cc_apply<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->n_comp.p, c->winner.p, c->scalars.p + 2);
     c->launches += 3;

@@ -109,11 +109,11 @@ __device__ __forceinline__ int cc_hook_roots(int* label, int ru, int rv) {
 
 // Initial forest without atomics (the first step of ECL-CC): every vertex points at its smallest same-cluster
 // neighbour with a smaller id, or at itself.  parent <= self everywhere and every link is a real same-cluster edge,
-// so the hooking pass that follows only has to join the few trees this leaves per cluster.
+// so the hooking pass that follows only has to join the few trees this leaves per cluster; n_roots[c] counts them.
 template <int W>
 __global__ void __launch_bounds__(kThreads) k_cc_init(int V, int K, int64_t vpad, const int* __restrict__ ell,
                                                       const int* __restrict__ row_ptr, const int* __restrict__ col,
-                                                      const int* __restrict__ cid, int* label) {
+                                                      const int* __restrict__ cid, int* label, int* n_roots) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         const int c = cid[v];
         int best = v;
@@ -134,16 +134,19 @@ __global__ void __launch_bounds__(kThreads) k_cc_init(int V, int K, int64_t vpad
                 }
         }
         label[v] = best;
+        // a cluster whose initial forest has a single root is connected (one tree spans it): only the clusters with
+        // several roots go through the hooking and the component bookkeeping
+        if (c < K && best == v) atomicAdd(n_roots + c, 1);
     }
 }
 
 template <int W>
 __global__ void __launch_bounds__(kThreads) k_cc_hook(int V, int K, int64_t vpad, const int* __restrict__ ell,
                                                       const int* __restrict__ row_ptr, const int* __restrict__ col,
-                                                      const int* __restrict__ cid, int* label) {
+                                                      const int* __restrict__ cid, int* label, const int* __restrict__ n_roots) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         const int c = cid[v];
-        if (c >= K) continue;
+        if (c >= K || n_roots[c] <= 1) continue;
         int nb[W];
 #pragma unroll
         for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);
@@ -162,15 +165,19 @@ __global__ void __launch_bounds__(kThreads) k_cc_hook(int V, int K, int64_t vpad
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_cc_flatten(int V, int* label) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) label[v] = cc_find(label, v);
+__global__ void __launch_bounds__(kThreads) k_cc_flatten(int V, int K, const int* __restrict__ cid, const int* __restrict__ n_roots, int* label) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const int c = cid[v];
+        if (c >= K || n_roots[c] <= 1) continue;
+        label[v] = cc_find(label, v);
+    }
 }
 
 __global__ void k_cc_sizes(int V, int K, const int* __restrict__ cid, const int* __restrict__ label, int* comp_size,
-                           const int* __restrict__ anchor) {
+                           const int* __restrict__ anchor, const int* __restrict__ n_roots) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         int c = cid[v];
-        if (c >= K) continue;
+        if (c >= K || n_roots[c] <= 1) continue;
         // an anchored item weighs 1e9 so that its component always wins (:440-447)
         int w = (anchor && anchor[c] == v) ? 1000000000 : 1;
         atomicAdd(&comp_size[label[v]], w);
@@ -181,10 +188,10 @@ __global__ void k_cc_sizes(int V, int K, const int* __restrict__ cid, const int*
 // Reference quirk kept: the component discovered at item 0 is never recorded because 0 doubles as the
 // "unvisited" sentinel of VisitedCluster (:463-467), so it is neither counted nor ever reset.
 __global__ void k_cc_winner(int V, int K, const int* __restrict__ cid, const int* __restrict__ label,
-                            const int* __restrict__ comp_size, int* n_comp, unsigned long long* winner) {
+                            const int* __restrict__ comp_size, int* n_comp, unsigned long long* winner, const int* __restrict__ n_roots) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         int c = cid[v];
-        if (c >= K || label[v] != v || v == 0) continue;
+        if (c >= K || n_roots[c] <= 1 || label[v] != v || v == 0) continue;
         atomicAdd(&n_comp[c], 1);
         unsigned long long key = ((unsigned long long)(unsigned)comp_size[v] << 32) | (unsigned)(0xffffffffu - (unsigned)v);
         atomicMax(&winner[c], key);

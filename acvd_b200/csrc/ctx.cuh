@@ -71,7 +71,7 @@ struct acvd_ctx {
     cudaEvent_t ev[4 * 8] = {};       // 4 events per round slot
     // generic scratch
     DevBuf<char> cub_temp;
-    DevBuf<int> sort_k0, sort_k1, sort_v0, sort_v1, seg, label, comp_size, n_comp, null_list, pick;
+    DevBuf<int> sort_k0, sort_k1, sort_v0, sort_v1, seg, label, comp_size, n_comp, n_roots, null_list, pick;
     DevBuf<unsigned long long> winner, scalars;   // scalars: small device counters
     unsigned long long* h_scalars = nullptr;      // pinned, 8 entries + one active-tile count per round slot
     std::vector<double> energy_log;
