@@ -545,6 +545,9 @@ static int clean_clustering(acvd_ctx* c) {
     else
         k_cc_init<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
     ACVD_LAUNCH_CHECK();
+    // flatten the initial chains first: the hooking pass then finds every representative in one or two hops
+    k_cc_flatten<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->n_roots.p, c->label.p);
+    ACVD_LAUNCH_CHECK();
     if (c->ell_w == 6)
         k_cc_hook<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
     else
@@ -1067,7 +1070,8 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         int batch = 1;
         if ((c->world == 1 || c->replicated_tail) && nconv >= 2 && !force_all && !reeval_all && !p.log_energy && !trace_on() &&
             last_proposals >= 0 && last_proposals <= kReplicatedTailProposals)
-            batch = (int)std::min<int64_t>(kTailBatch, std::max<int64_t>(1, p.max_loops - loops));
+            batch = (int)std::min<int64_t>(p.rounds_per_sync > 0 ? std::min(p.rounds_per_sync, kRoundSlots) : kTailBatch,
+                                           std::max<int64_t>(1, p.max_loops - loops));
         if (c->world > 1 && !c->replicated_tail) {
             r = run_round_dist(c, cfg, connexity, force_all, as_iso);
             if ((int64_t)r.proposals <= kReplicatedTailProposals && r.mods > 0) { c->replicated_tail = true; reeval_all = true; }

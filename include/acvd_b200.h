@@ -107,7 +107,7 @@ typedef struct acvd_params {
     int32_t max_convergences;     /* MaxNumberOfConvergences, <=0 -> 1000000000 */
     int32_t early_stop_div;       /* <=0 -> 1000 (vtkUniformClustering.h:775) */
     int32_t log_energy;           /* keep a per-round global-energy trace (energy.txt analogue) */
-    int32_t rounds_per_sync;      /* rounds between host polls of the counters, <=0 -> 1 */
+    int32_t rounds_per_sync;      /* rounds launched back to back between host polls in the tail of the last phases, <=0 -> 4, max 8 */
     double sv_threshold;          /* <=0 -> 1e-3 (Common/vtkQuadricTools.h:36) */
     int32_t bulk_rounds;          /* early phases: 0 -> bulk Lloyd-criterion rounds on (cap 1000), <0 -> off, >0 -> cap */
     int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 2 on one GPU, 1 across GPUs */
