@@ -329,8 +329,10 @@ def main():
     if S("dense_scan_launches"):
         roof_dense["scan_only_GBps"] = S("dense_scan_vertices") / world * 56.0 / (S("ms_dense_scan") * 1e-3) / 1e9
         roof_dense["scan_only_note"] = "frontier-scan bytes alone (8 + 8 deg = 56 B per vertex, SURVEY 8d), without the tests' operands"
-    roof_scan = kernel_roof("k_scan", "k_scan (all frontier-scan launches of the loop, dense + list-based)", S("scan_bytes"), S("ms_scan"), n_l)
-    roof_eval = kernel_roof("k_evaluate", "k_evaluate (candidate energy evaluation of the exact rounds)", S("evaluate_bytes"), S("ms_evaluate"),
+    roof_scan = kernel_roof("k_scan_avg", "k_scan (all frontier-scan launches of the loop, dense + list-based)", S("scan_bytes"), S("ms_scan"), n_l)
+    # (the ncu DRAM figures of these two are per full-activity launch and do not pair with per-launch averages over a
+    # whole run, so no `traffic` is attached to them; profiles/README.md has the full-launch captures)
+    roof_eval = kernel_roof("k_evaluate_avg", "k_evaluate (candidate energy evaluation of the exact rounds)", S("evaluate_bytes"), S("ms_evaluate"),
                             n_l - S("bulk_rounds"))
     roofline = roof_dense if S("dense_scan_launches") else roof_scan
     roofline["other_kernels"] = [{k: o[k] for k in ("kernel", "achieved", "frac", "bytes_per_launch", "us_per_launch", "launches_per_step", "share_of_step", "traffic")}
