@@ -60,6 +60,8 @@ SYMBOLS = [
     ("acvd_set_mesh", C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     ("acvd_get_num_edges", C.c_int, [_vp, C.POINTER(_i64)]),
     ("acvd_get_csr", C.c_int, [_vp, _vp, _vp]),
+    ("acvd_subdivide", C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    ("acvd_get_subdivision", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ("acvd_curvature", C.c_int, [_vp, _i32, _vp, _vp]),
     ("acvd_build_items", C.c_int, [_vp, C.c_int, _d, _vp, _vp]),
     ("acvd_set_items", C.c_int, [_vp, C.c_int, _vp]),
@@ -155,6 +157,17 @@ class Context:
         col = np.zeros(2 * E, dtype=np.int32)
         self._ck(self.L.acvd_get_csr(self.h, _p(rp), _p(col)))
         return rp, col
+
+    def subdivide(self):
+        """vtkSurface::Subdivide of the context's mesh: (points float32 [nv,3], triangles int32 [nf,3], parent1, parent2)."""
+        nv, nf = _i32(), _i32()
+        self._ck(self.L.acvd_subdivide(self.h, C.byref(nv), C.byref(nf)))
+        p = np.zeros((nv.value, 3), dtype=np.float32)
+        t = np.zeros((nf.value, 3), dtype=np.int32)
+        p1 = np.zeros(nv.value, dtype=np.int32)
+        p2 = np.zeros(nv.value, dtype=np.int32)
+        self._ck(self.L.acvd_get_subdivision(self.h, _p(p), _p(t), _p(p1), _p(p2)))
+        return p, t, p1, p2
 
     def curvature(self, ring_size=3, principal_directions=True):
         """vtkCurvatureMeasure (polynomial fitting, vertices, n-ring): (indicator[V] float64, info[V, 6] float32 or None)."""

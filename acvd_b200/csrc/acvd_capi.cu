@@ -141,7 +141,7 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     ACVD_API_BEGIN(c)
     if (V <= 0 || F <= 0 || !xyz || !tri) throw std::runtime_error("acvd_set_mesh: bad arguments");
     c->V = V; c->F = F;
-    c->have_items = false; c->stats_valid = false;
+    c->have_items = false; c->stats_valid = false; c->sub_V = c->sub_F = 0;
     c->vpad = (((int64_t)V + 31) / 32) * 32;      // per-vertex streams are padded to whole 32-vertex tiles (TMA copies whole tiles)
     c->xyz.alloc(3 * (size_t)c->vpad);
     c->tri.alloc(3 * (size_t)F);
@@ -220,6 +220,92 @@ extern "C" int acvd_get_csr(acvd_ctx* c, int32_t* row_ptr, int32_t* col) {
     if (!c->V) throw std::runtime_error("acvd_get_csr: no mesh");
     if (row_ptr) ACVD_CUDA(cudaMemcpy(row_ptr, c->row_ptr.p, ((size_t)c->V + 1) * sizeof(int), cudaMemcpyDeviceToHost));
     if (col) ACVD_CUDA(cudaMemcpy(col, c->col.p, (size_t)c->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1 -> 4 subdivision of the context's mesh (kept on the device until fetched)
+static void inclusive_sum(acvd_ctx* c, const int* in, int* out, int64_t n) {
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, in, out, n, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceScan::InclusiveSum(t, tb, in, out, n, c->stream));
+}
+
+extern "C" int acvd_subdivide(acvd_ctx* c, int32_t* n_vertices, int32_t* n_faces) {
+    ACVD_API_BEGIN(c)
+    if (!c->V || !n_vertices || !n_faces) throw std::runtime_error("acvd_subdivide: set the mesh first");
+    const int V = c->V, F = c->F;
+    const int64_t n = 3 * (int64_t)F;
+    if (n >= ((int64_t)1 << 31)) throw std::runtime_error("acvd_subdivide: mesh too large");
+    DevBuf<unsigned long long> keys, keys_alt;
+    DevBuf<int> slots, slots_alt, head, run_incl, first_slot, run_id, first_sorted, run_sorted, edge_of_run, edge_of_slot, flag, rank_incl;
+    keys.alloc(n); keys_alt.alloc(n); slots.alloc(n); slots_alt.alloc(n); head.alloc(n); run_incl.alloc(n);
+    k_sub_edge_keys<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, keys.p, slots.p);
+    ACVD_LAUNCH_CHECK();
+    {   // stable: equal keys keep ascending slot order, so a run starts with the first occurrence of its edge
+        cub::DoubleBuffer<unsigned long long> dk(keys.p, keys_alt.p);
+        cub::DoubleBuffer<int> dv(slots.p, slots_alt.p);
+        size_t tb = 0;
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, n, 0, 64, c->stream));
+        void* t = cub_temp(c, tb);
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, dk, dv, n, 0, 64, c->stream));
+        if (dk.Current() != keys.p) ACVD_CUDA(cudaMemcpyAsync(keys.p, dk.Current(), n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+        if (dv.Current() != slots.p) ACVD_CUDA(cudaMemcpyAsync(slots.p, dv.Current(), n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    k_sub_heads<<<grid_for(n), kThreads, 0, c->stream>>>(n, keys.p, head.p);
+    ACVD_LAUNCH_CHECK();
+    inclusive_sum(c, head.p, run_incl.p, n);
+    int E = 0;
+    ACVD_CUDA(cudaMemcpyAsync(&E, run_incl.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    if ((int64_t)V + E >= ((int64_t)1 << 31)) throw std::runtime_error("acvd_subdivide: too many vertices");
+    first_slot.alloc(std::max(E, 1)); run_id.alloc(std::max(E, 1)); first_sorted.alloc(std::max(E, 1)); run_sorted.alloc(std::max(E, 1));
+    edge_of_run.alloc(std::max(E, 1)); edge_of_slot.alloc(n);
+    k_sub_first_slots<<<grid_for(n), kThreads, 0, c->stream>>>(n, head.p, run_incl.p, slots.p, first_slot.p, run_id.p);
+    ACVD_LAUNCH_CHECK();
+    if (E > 0) {
+        size_t tb = 0;
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, first_slot.p, first_sorted.p, run_id.p, run_sorted.p, E, 0, 32, c->stream));
+        void* t = cub_temp(c, tb);
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, first_slot.p, first_sorted.p, run_id.p, run_sorted.p, E, 0, 32, c->stream));
+    }
+    const int Vn = V + E;
+    c->sub_xyz.alloc(3 * (size_t)Vn); c->sub_parent1.alloc(Vn); c->sub_parent2.alloc(Vn);
+    k_sub_old_points<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->xyz.p, c->sub_xyz.p, c->sub_parent1.p, c->sub_parent2.p);
+    ACVD_LAUNCH_CHECK();
+    if (E > 0) {
+        k_sub_edges<<<grid_for(E), kThreads, 0, c->stream>>>(E, V, first_sorted.p, run_sorted.p, c->tri.p, c->xyz.p, edge_of_run.p, c->sub_xyz.p,
+                                                              c->sub_parent1.p, c->sub_parent2.p);
+        ACVD_LAUNCH_CHECK();
+        k_sub_slot_edges<<<grid_for(n), kThreads, 0, c->stream>>>(n, keys.p, run_incl.p, slots.p, edge_of_run.p, edge_of_slot.p);
+        ACVD_LAUNCH_CHECK();
+    }
+    flag.alloc(F); rank_incl.alloc(F);
+    k_sub_face_flags<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, flag.p);
+    ACVD_LAUNCH_CHECK();
+    inclusive_sum(c, flag.p, rank_incl.p, F);
+    int n_kept = 0;
+    ACVD_CUDA(cudaMemcpyAsync(&n_kept, rank_incl.p + (F - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    if (4 * (int64_t)n_kept >= ((int64_t)1 << 31) / 3) throw std::runtime_error("acvd_subdivide: too many faces");
+    c->sub_tri.alloc(12 * (size_t)std::max(n_kept, 1));
+    k_sub_faces<<<grid_for(F), kThreads, 0, c->stream>>>(F, V, c->tri.p, flag.p, rank_incl.p, edge_of_slot.p, c->sub_tri.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->sub_V = Vn; c->sub_F = 4 * n_kept;
+    *n_vertices = Vn; *n_faces = 4 * n_kept;
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_subdivision(acvd_ctx* c, float* xyz, int32_t* tri, int32_t* parent1, int32_t* parent2) {
+    ACVD_API_BEGIN(c)
+    if (!c->sub_V) throw std::runtime_error("acvd_get_subdivision: call acvd_subdivide first");
+    if (xyz) ACVD_CUDA(cudaMemcpyAsync(xyz, c->sub_xyz.p, 3 * (size_t)c->sub_V * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (tri) ACVD_CUDA(cudaMemcpyAsync(tri, c->sub_tri.p, 3 * (size_t)c->sub_F * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (parent1) ACVD_CUDA(cudaMemcpyAsync(parent1, c->sub_parent1.p, (size_t)c->sub_V * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (parent2) ACVD_CUDA(cudaMemcpyAsync(parent2, c->sub_parent2.p, (size_t)c->sub_V * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
     ACVD_API_END(c)
 }
 

@@ -33,6 +33,10 @@ struct acvd_ctx {
     int max_deg = 0;                  // longest adjacency row
     int64_t vpad = 0;
     DevBuf<unsigned long long> vf_keys, ringadj;
+    // last subdivision of this mesh (acvd_subdivide), kept until the next acvd_set_mesh
+    int sub_V = 0, sub_F = 0;
+    DevBuf<float> sub_xyz;
+    DevBuf<int> sub_tri, sub_parent1, sub_parent2;
     // items
     int metric = -1;
     DevBuf<double> area, weight, items;

@@ -49,11 +49,18 @@ void vtkDiscreteRemeshingB200::SetNumberOfClusters(int n) {
 void vtkDiscreteRemeshingB200::CheckSubsamplingRatio() {
     while (Input->GetNumberOfPoints() < (vtkIdType)SubsamplingThreshold * NumberOfClusters) {
         if (ConsoleOutput) cout << "Subdividing mesh" << endl;
-        vtkIntArray *p1 = vtkIntArray::New(), *p2 = vtkIntArray::New();
-        vtkSurface* next = Input->Subdivide(p1, p2);
+        // vtkSurface::Subdivide on the device (acvd_subdivide: same vertex / face numbering as the host method)
+        if (!Ctx && !Check(acvd_create(&Ctx, Device), "acvd_create")) return;
+        if (!Check(acvd_set_mesh(Ctx, (int32_t)Input->GetNumberOfPoints(), (int32_t)Input->GetNumberOfCells(), Input->Points(), Input->Triangles()), "acvd_set_mesh")) return;
+        int32_t nv2 = 0, nf2 = 0;
+        if (!Check(acvd_subdivide(Ctx, &nv2, &nf2), "acvd_subdivide")) return;
+        std::vector<float> xyz2(3 * (size_t)nv2);
+        std::vector<int> tri2(3 * (size_t)nf2);
         // parents of the new level expressed in vertices of the level below; old vertices are their own parents
-        Parent1 = p1->v; Parent2 = p2->v;
-        p1->Delete(); p2->Delete();
+        Parent1.assign((size_t)nv2, 0); Parent2.assign((size_t)nv2, 0);
+        if (!Check(acvd_get_subdivision(Ctx, xyz2.data(), tri2.data(), Parent1.data(), Parent2.data()), "acvd_get_subdivision")) return;
+        vtkSurface* next = vtkSurface::New();
+        next->CreateFromArrays(nv2, xyz2.data(), nf2, tri2.data());
         if (!CustomIndicator.empty()) {
             // the curvature indicator is interpolated linearly to the midpoints (:733-745)
             const size_t n_old = (size_t)Input->GetNumberOfPoints(), n_new = (size_t)next->GetNumberOfPoints();

@@ -184,6 +184,84 @@ __global__ void k_build_ell(int V, int64_t vpad, int W, const int* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 1 -> 4 subdivision (vtkSurface::Subdivide, reference Common/vtkSurface.cxx:605-677): old points first, then one
+// midpoint per edge in EDGE-ID order -- the reference numbers edges in the order AddEdge first sees them over the
+// faces (Common/vtkSurfaceBase.cxx:1166-1221) --, then per face (V1,V4,V6) (V4,V2,V5) (V5,V3,V6) (V4,V5,V6).
+// Edge ids on the device: sort the 3F undirected half-edges by (min,max) with their slot 3f+k as payload (stable, so
+// the first entry of a run is the first occurrence), rank the runs by that first slot.
+
+// undirected edge key of slot 3f+k, ~0 for inactive faces (first two vertices equal, vtkSurfaceBase.cxx:1443) / self loops
+__global__ void k_sub_edge_keys(int F, const int* __restrict__ tri, unsigned long long* keys, int* slots) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        const int v[3] = {tri[3 * f], tri[3 * f + 1], tri[3 * f + 2]};
+        const bool active = v[0] != v[1];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const unsigned a = (unsigned)v[k], b = (unsigned)v[(k + 1) % 3];
+            const bool ok = active && a != b;
+            keys[3 * (int64_t)f + k] = ok ? (((unsigned long long)min(a, b) << 32) | max(a, b)) : ~0ull;
+            slots[3 * (int64_t)f + k] = 3 * f + k;
+        }
+    }
+}
+// head[i] = 1 where a run of equal valid keys starts
+__global__ void k_sub_heads(int64_t n, const unsigned long long* __restrict__ keys, int* head) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        head[i] = (keys[i] != ~0ull && (i == 0 || keys[i - 1] != keys[i])) ? 1 : 0;
+}
+// run r (= inclusive scan of head - 1) -> slot of its first occurrence
+__global__ void k_sub_first_slots(int64_t n, const int* __restrict__ head, const int* __restrict__ run_incl, const int* __restrict__ slots,
+                                  int* first_slot, int* run_id) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (head[i]) { first_slot[run_incl[i] - 1] = slots[i]; run_id[run_incl[i] - 1] = run_incl[i] - 1; }
+}
+// after sorting the runs by first slot: edge id of run run_sorted[e] is e; the edge's endpoints in first-seen order
+__global__ void k_sub_edges(int E, int V, const int* __restrict__ first_sorted, const int* __restrict__ run_sorted, const int* __restrict__ tri,
+                            const float* __restrict__ xyz, int* edge_of_run, float* xyz_out, int* parent1, int* parent2) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        edge_of_run[run_sorted[e]] = e;
+        const int s = first_sorted[e], f = s / 3, k = s % 3;
+        const int a = tri[3 * (int64_t)f + k], b = tri[3 * (int64_t)f + (k + 1) % 3];
+        parent1[V + e] = a; parent2[V + e] = b;
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            xyz_out[3 * ((int64_t)V + e) + d] = (float)(0.5 * ((double)xyz[3 * (int64_t)a + d] + (double)xyz[3 * (int64_t)b + d]));
+    }
+}
+__global__ void k_sub_old_points(int V, const float* __restrict__ xyz, float* xyz_out, int* parent1, int* parent2) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        xyz_out[3 * (int64_t)v] = xyz[3 * (int64_t)v]; xyz_out[3 * (int64_t)v + 1] = xyz[3 * (int64_t)v + 1]; xyz_out[3 * (int64_t)v + 2] = xyz[3 * (int64_t)v + 2];
+        parent1[v] = v; parent2[v] = v;
+    }
+}
+// sorted position -> slot: the edge id of every half-edge slot
+__global__ void k_sub_slot_edges(int64_t n, const unsigned long long* __restrict__ keys, const int* __restrict__ run_incl, const int* __restrict__ slots,
+                                 const int* __restrict__ edge_of_run, int* edge_of_slot) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (keys[i] != ~0ull) edge_of_slot[slots[i]] = edge_of_run[run_incl[i] - 1];
+}
+// faces: 4 per face with three distinct vertices, written at 4 x (rank of the face among those)
+__global__ void k_sub_face_flags(int F, const int* __restrict__ tri, int* flag) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        const int a = tri[3 * f], b = tri[3 * f + 1], c = tri[3 * f + 2];
+        flag[f] = (a != b && b != c && a != c) ? 1 : 0;
+    }
+}
+__global__ void k_sub_faces(int F, int V, const int* __restrict__ tri, const int* __restrict__ flag, const int* __restrict__ rank_incl,
+                            const int* __restrict__ edge_of_slot, int* tri_out) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        if (!flag[f]) continue;
+        const int v1 = tri[3 * f], v2 = tri[3 * f + 1], v3 = tri[3 * f + 2];
+        const int v4 = V + edge_of_slot[3 * (int64_t)f], v5 = V + edge_of_slot[3 * (int64_t)f + 1], v6 = V + edge_of_slot[3 * (int64_t)f + 2];
+        int* o = tri_out + 12 * (int64_t)(rank_incl[f] - 1);
+        o[0] = v1; o[1] = v4; o[2] = v6;
+        o[3] = v4; o[4] = v2; o[5] = v5;
+        o[6] = v5; o[7] = v3; o[8] = v6;
+        o[9] = v4; o[10] = v5; o[11] = v6;
+    }
+}
+
 __global__ void k_max_degree(int V, const int* __restrict__ row_ptr, int* out) {
     int m = 0;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) m = max(m, row_ptr[v + 1] - row_ptr[v]);

@@ -59,6 +59,15 @@ int acvd_set_mesh(acvd_ctx* ctx, int32_t V, int32_t F, const float* xyz, const i
 int acvd_get_num_edges(acvd_ctx* ctx, int64_t* E);
 int acvd_get_csr(acvd_ctx* ctx, int32_t* row_ptr /*V+1*/, int32_t* col /*2E*/);
 
+/* vtkSurface::Subdivide (Common/vtkSurface.cxx:605-677), the pre-pass of vtkDiscreteRemeshing::CheckSubsamplingRatio
+ * (DiscreteRemeshing/vtkDiscreteRemeshing.h:841-875, option -s): 1 -> 4 split of the context's mesh on the device.
+ * Old points first, then one midpoint per edge in the reference's edge-id order (first seen over the faces),
+ * faces (V1,V4,V6) (V4,V2,V5) (V5,V3,V6) (V4,V5,V6) per input face.  The result stays on the device until fetched;
+ * parent1/parent2[v] are the edge endpoints of a midpoint (v itself for old points), as the reference keeps them for
+ * interpolating the curvature indicator (:733-745).  Any pointer of acvd_get_subdivision may be NULL. */
+int acvd_subdivide(acvd_ctx* ctx, int32_t* n_vertices, int32_t* n_faces);
+int acvd_get_subdivision(acvd_ctx* ctx, float* xyz /*3 nv*/, int32_t* tri /*3 nf*/, int32_t* parent1 /*nv*/, int32_t* parent2 /*nv*/);
+
 /* vtkCurvatureMeasure with ComputationMethod 1 (polynomial fitting), ElementsType 1 (vertices) and the n-ring
  * neighbourhood (Common/vtkCurvatureMeasure.cxx:188-508, 625-718; defaults :1175-1196: ring_size 3), as called by
  * vtkDiscreteRemeshing::SamplingPreProcessing (DiscreteRemeshing/vtkDiscreteRemeshing.h:640-653).

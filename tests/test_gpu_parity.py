@@ -475,3 +475,35 @@ def test_curvature_feeds_gradation_run(gpu_ctx_factory, torus):
         hi = ind > np.median(ind)
         res[grad] = len(np.unique(cl[hi]))
     assert res[1.5] > res[0.0]
+
+
+@pytest.mark.parametrize("mesh", ["sphere", "spindle", "torus"])
+def test_subdivide_bit_exact(oracle_mod, gpu_ctx_factory, sphere, spindle, torus, mesh):
+    """acvd_subdivide (vtkSurface::Subdivide, Common/vtkSurface.cxx:605-677) against the numbering the reference produces:
+    old points, then one midpoint per edge in the oracle's (first-seen) edge order, four faces per face; parents = edge
+    end points in first-seen orientation.  Bit-exact, and the result is a valid closed mesh with 4 F faces."""
+    p, t = {"sphere": sphere, "spindle": spindle, "torus": torus[:2]}[mesh]
+    o = oracle_mod.Oracle(p, t)
+    a, b = o.edges()
+    V, E = p.shape[0], a.shape[0]
+    mid = (0.5 * (p[a].astype(np.float64) + p[b].astype(np.float64))).astype(np.float32)
+    key = np.minimum(a, b).astype(np.int64) * V + np.maximum(a, b)
+    order = np.argsort(key)
+
+    def eid(u, v):
+        k = np.minimum(u, v).astype(np.int64) * V + np.maximum(u, v)
+        return order[np.searchsorted(key[order], k)]
+    v4, v5, v6 = V + eid(t[:, 0], t[:, 1]), V + eid(t[:, 1], t[:, 2]), V + eid(t[:, 2], t[:, 0])
+    exp_t = np.stack([t[:, 0], v4, v6, v4, t[:, 1], v5, v5, t[:, 2], v6, v4, v5, v6], axis=1).reshape(-1, 3).astype(np.int32)
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    ps, ts, p1, p2 = g.subdivide()
+    assert ps.shape == (V + E, 3) and ts.shape == (4 * t.shape[0], 3)
+    assert np.array_equal(ps[:V], p) and np.array_equal(ps[V:], mid)
+    assert np.array_equal(ts, exp_t)
+    assert np.array_equal(p1[:V], np.arange(V)) and np.array_equal(p2[:V], np.arange(V))
+    assert np.array_equal(p1[V:], a) and np.array_equal(p2[V:], b)
+    # the subdivided mesh is a mesh: feed it back
+    g2 = gpu_ctx_factory()
+    g2.set_mesh(ps, ts)
+    assert g2.num_edges() == 2 * E + 3 * t.shape[0]
