@@ -131,12 +131,6 @@ extern "C" int acvd_destroy(acvd_ctx* c) {
 
 // ---------------------------------------------------------------------------------------------
 // mesh
-static void build_rows(acvd_ctx* c, unsigned long long* keys, int64_t n_valid, DevBuf<int>& ptr, int* low) {
-    ptr.alloc((size_t)c->V + 1);
-    k_rows_from_sorted<<<grid_for(n_valid + 1), kThreads, 0, c->stream>>>(n_valid, c->V, keys, ptr.p, low);
-    ACVD_LAUNCH_CHECK();
-}
-
 extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz, const int32_t* tri) {
     ACVD_API_BEGIN(c)
     if (V <= 0 || F <= 0 || !xyz || !tri) throw std::runtime_error("acvd_set_mesh: bad arguments");
@@ -145,38 +139,47 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     c->vpad = (((int64_t)V + 31) / 32) * 32;      // per-vertex streams are padded to whole 32-vertex tiles (TMA copies whole tiles)
     c->xyz.alloc(3 * (size_t)c->vpad);
     c->tri.alloc(3 * (size_t)F);
-    ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    const int vbits = bits_for((uint64_t)V);
-    // --- CSR adjacency: 6F directed half-edges -> sort -> unique
     {
-        int64_t n = 6 * (int64_t)F;
-        DevBuf<unsigned long long> keys, alt, uniq;
-        DevBuf<int64_t> d_num;
-        keys.alloc(n); alt.alloc(n); uniq.alloc(n); d_num.alloc(1);
-        k_emit_halfedges<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, keys.p);
+        TraceScope ts(c, "set_mesh: upload");
+        ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    // --- CSR adjacency and vertex -> face incidence (faces ascending per vertex), by counting: see mesh.cuh
+    {
+        TraceScope ts(c, "set_mesh: csr + incidence");
+        const int64_t n3 = 3 * (int64_t)F;
+        DevBuf<int> cnt, cursor, he, deg;
+        cnt.alloc((size_t)V + 1); cursor.alloc(V); he.alloc((size_t)(2 * n3)); deg.alloc((size_t)V + 1);
+        c->vf_ptr.alloc((size_t)V + 1); c->vf_keys.alloc((size_t)n3); c->row_ptr.alloc((size_t)V + 1);
+        ACVD_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+        ACVD_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)V * sizeof(int), c->stream));
+        ACVD_CUDA(cudaMemsetAsync(deg.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+        k_count_corners<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, cnt.p);
         ACVD_LAUNCH_CHECK();
-        sort_keys64(c, keys.p, alt.p, n, 64);   // invalid keys (~0) sort to the end
         size_t tb = 0;
-        ACVD_CUDA(cub::DeviceSelect::Unique(nullptr, tb, keys.p, uniq.p, d_num.p, n, c->stream));
+        ACVD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, c->vf_ptr.p, V + 1, c->stream));
         void* t = cub_temp(c, tb);
-        ACVD_CUDA(cub::DeviceSelect::Unique(t, tb, keys.p, uniq.p, d_num.p, n, c->stream));
-        int64_t nu = 0;
-        ACVD_CUDA(cudaMemcpyAsync(&nu, d_num.p, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cub::DeviceScan::ExclusiveSum(t, tb, cnt.p, c->vf_ptr.p, V + 1, c->stream));
+        k_scatter_corners<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, c->vf_ptr.p, cursor.p, c->vf_keys.p, he.p);
+        ACVD_LAUNCH_CHECK();
+        k_sort_rows<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->vf_ptr.p, c->vf_keys.p, he.p, deg.p);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, deg.p, c->row_ptr.p, V + 1, c->stream));
+        t = cub_temp(c, tb);
+        ACVD_CUDA(cub::DeviceScan::ExclusiveSum(t, tb, deg.p, c->row_ptr.p, V + 1, c->stream));
+        int nu = 0;
+        ACVD_CUDA(cudaMemcpyAsync(&nu, c->row_ptr.p + V, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
-        unsigned long long last = 0;
-        if (nu > 0) {
-            ACVD_CUDA(cudaMemcpy(&last, uniq.p + (nu - 1), sizeof last, cudaMemcpyDeviceToHost));
-            if (last == ~0ull) nu--;
-        }
-        if (nu >= (int64_t)1 << 31) throw std::runtime_error("acvd_set_mesh: more than 2^31 adjacency entries");
+        if (nu < 0) throw std::runtime_error("acvd_set_mesh: more than 2^31 adjacency entries");
         c->nnz = nu;
-        c->col.alloc((size_t)std::max<int64_t>(nu, 1));
-        build_rows(c, uniq.p, nu, c->row_ptr, c->col.p);
+        c->col.alloc((size_t)std::max(nu, 1));
+        k_compact_rows<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->vf_ptr.p, c->row_ptr.p, he.p, c->col.p);
+        ACVD_LAUNCH_CHECK();
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
     }
     // --- ELL copy for the frontier scan (width 6 when no vertex has more neighbours, else 8 + CSR overflow)
     {
+        TraceScope ts(c, "set_mesh: ell");
         int* d_max = reinterpret_cast<int*>(c->scalars.p);
         ACVD_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), c->stream));
         k_max_degree<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->row_ptr.p, d_max);
@@ -191,21 +194,11 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
         ACVD_LAUNCH_CHECK();
     }
     // --- ring adjacency matrices for the connexity predicate of k_evaluate
+    TraceScope ts_rest(c, "set_mesh: ringadj");
     c->ringadj.alloc((size_t)V);
     k_build_ringadj<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->row_ptr.p, c->col.p, c->ringadj.p);
     ACVD_LAUNCH_CHECK();
-    // --- vertex -> face incidence (ascending face id per vertex)
-    {
-        int64_t n = 3 * (int64_t)F;
-        DevBuf<unsigned long long> alt;
-        c->vf_keys.alloc(n); alt.alloc(n);
-        k_emit_incidence<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, c->vf_keys.p);
-        ACVD_LAUNCH_CHECK();
-        sort_keys64(c, c->vf_keys.p, alt.p, n, 64);
-        // inactive faces (key ~0) sort to the end; k_rows_from_sorted clamps their source to V
-        build_rows(c, c->vf_keys.p, n, c->vf_ptr, nullptr);
-        ACVD_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
     ACVD_API_END(c)
 }
 

@@ -11,40 +11,72 @@
 
 namespace acvd {
 
-// 6 directed half-edges per face as (src << 32 | dst); faces whose first two vertices coincide are
-// inactive (vtkSurfaceBase.cxx:1443) and self loops are rejected (:1168-1172): those emit ~0.
-__global__ void k_emit_halfedges(int F, const int* __restrict__ tri, unsigned long long* keys) {
+// ---------------------------------------------------------------------------------------------------
+// CSR adjacency and vertex -> face incidence by counting instead of a global sort of the half-edges:
+// corners per vertex (atomics) -> exclusive scan -> every corner drops its face id and its two ring neighbours into
+// the vertex' segment (atomic cursor) -> one thread per vertex sorts its few entries and removes duplicate
+// neighbours.  The per-row sort makes the result independent of the order the atomics were served in
+// (rows ascending, as the sorted-key build produced them).
+constexpr int kNoNeighbour = 0x7fffffff;
+
+__global__ void k_count_corners(int F, const int* __restrict__ tri, int* cnt) {
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
-        int v[3] = {tri[3 * f], tri[3 * f + 1], tri[3 * f + 2]};
-        bool active = v[0] != v[1];
+        const int v[3] = {tri[3 * (int64_t)f], tri[3 * (int64_t)f + 1], tri[3 * (int64_t)f + 2]};
+        if (v[0] == v[1]) continue;                      // inactive face (vtkSurfaceBase.cxx:1443)
+#pragma unroll
+        for (int k = 0; k < 3; k++) atomicAdd(cnt + v[k], 1);
+    }
+}
+
+__global__ void k_scatter_corners(int F, const int* __restrict__ tri, const int* __restrict__ off, int* cursor,
+                                  unsigned long long* vf_keys, int* he) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        const int v[3] = {tri[3 * (int64_t)f], tri[3 * (int64_t)f + 1], tri[3 * (int64_t)f + 2]};
+        if (v[0] == v[1]) continue;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            unsigned a = (unsigned)v[k], b = (unsigned)v[(k + 1) % 3];
-            bool ok = active && a != b;
-            keys[6 * (int64_t)f + 2 * k] = ok ? (((unsigned long long)a << 32) | b) : ~0ull;
-            keys[6 * (int64_t)f + 2 * k + 1] = ok ? (((unsigned long long)b << 32) | a) : ~0ull;
+            const int u = v[k], nxt = v[(k + 1) % 3], prv = v[(k + 2) % 3];
+            const int64_t pos = (int64_t)off[u] + atomicAdd(cursor + u, 1);
+            vf_keys[pos] = ((unsigned long long)(unsigned)u << 32) | (unsigned)f;
+            he[2 * pos] = nxt != u ? nxt : kNoNeighbour;      // self loops are rejected (:1168-1172)
+            he[2 * pos + 1] = prv != u ? prv : kNoNeighbour;
         }
     }
 }
 
-// (vertex << 32 | face) incidence keys, 3 per face
-__global__ void k_emit_incidence(int F, const int* __restrict__ tri, unsigned long long* keys) {
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
-        bool active = tri[3 * f] != tri[3 * f + 1];
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            keys[3 * (int64_t)f + k] = active ? (((unsigned long long)(unsigned)tri[3 * f + k] << 32) | (unsigned)f) : ~0ull;
+__global__ void k_sort_rows(int V, const int* __restrict__ off, unsigned long long* vf_keys, int* he, int* deg) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const int64_t b = off[v];
+        const int m = off[v + 1] - off[v];
+        unsigned long long* fk = vf_keys + b;
+        for (int i = 1; i < m; i++) {                    // faces ascending
+            const unsigned long long x = fk[i];
+            int j = i - 1;
+            while (j >= 0 && fk[j] > x) { fk[j + 1] = fk[j]; j--; }
+            fk[j + 1] = x;
+        }
+        int* h = he + 2 * b;
+        for (int i = 1; i < 2 * m; i++) {                // neighbours ascending, kNoNeighbour last
+            const int x = h[i];
+            int j = i - 1;
+            while (j >= 0 && h[j] > x) { h[j + 1] = h[j]; j--; }
+            h[j + 1] = x;
+        }
+        int d = 0;
+        for (int i = 0; i < 2 * m; i++) {
+            const int x = h[i];
+            if (x == kNoNeighbour) break;
+            if (d == 0 || h[d - 1] != x) h[d++] = x;
+        }
+        deg[v] = d;
     }
 }
 
-// From sorted keys (src << 32 | x): ptr[s] = first index with src >= s; low[i] = x.  ptr has V+1 entries.
-__global__ void k_rows_from_sorted(int64_t n, int V, const unsigned long long* __restrict__ keys, int* ptr, int* low) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
-        // sources >= V (the ~0 keys of inactive faces, sorted last) are clamped so they close the last row
-        int64_t prev = (i == 0) ? -1 : min((int64_t)(keys[i - 1] >> 32), (int64_t)V);
-        int64_t cur = (i == n) ? (int64_t)V : min((int64_t)(keys[i] >> 32), (int64_t)V);
-        for (int64_t s = prev + 1; s <= cur; s++) ptr[s] = (int)i;
-        if (i < n && low) low[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
+__global__ void k_compact_rows(int V, const int* __restrict__ off, const int* __restrict__ row_ptr, const int* __restrict__ he, int* col) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const int* h = he + 2 * (int64_t)off[v];
+        const int b = row_ptr[v], d = row_ptr[v + 1] - b;
+        for (int i = 0; i < d; i++) col[b + i] = h[i];
     }
 }
 
