@@ -1397,4 +1397,4 @@ extern "C" int acvd_dual_triangles(acvd_ctx* c, int32_t* out, int64_t cap, int64
 }
 
 // ---------------------------------------------------------------------------------------------
-// multi-GPU plumbing lives in acvd_dist.cu
+// multi-GPU plumbing and round drivers: dist.cuh (included above)

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(kThreads) k_cluster_stats(int K, const int* __
 // initialised to the identity; every same-cluster edge (u < v) joins the two trees by atomically hooking
 // the larger root under the smaller one, so a component's root is its minimum vertex id -- which is also the
 // vertex at which the reference's index-ordered BFS discovers the component (:428-437).  One pass over the
-// edges (k_cc_hook) and one flattening pass (k_cc_flatten) replace ~16 label-propagation sweeps.
+// edges (k_cc_hook) between two flattening passes (k_cc_flatten), and only for the clusters whose atomic-free
+// initial forest (k_cc_init) has more than one root.
 __device__ __forceinline__ int cc_find(const int* label, int x) {
     int p = __ldcg(label + x);
     while (p != x) { x = p; p = __ldcg(label + x); }

@@ -80,7 +80,7 @@ struct acvd_ctx {
     unsigned long long* h_scalars = nullptr;      // pinned, 8 entries + one active-tile count per round slot
     std::vector<double> energy_log;
     int stats_constrained = 1, stats_qlevel = 3;
-    // multi-GPU (acvd_dist.cu)
+    // multi-GPU (dist.cuh)
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     bool replicated_tail = false;             // multi-GPU: the tail of a phase runs redundantly on every rank, no exchange

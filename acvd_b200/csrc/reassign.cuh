@@ -580,7 +580,7 @@ template <int EM, int UM>
 __global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
     constexpr int NU = MetricTraits<UM>::NPAD;
     const int K = A.K;
-    const int n_props = (int)A.ctr->proposals;   // written by k_propose of this round
+    const int n_props = (int)A.ctr->proposals;   // written by k_scan / k_evaluate of this round
     unsigned n_mods = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
         const int v = A.plist[i];

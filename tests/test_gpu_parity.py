@@ -507,3 +507,36 @@ def test_subdivide_bit_exact(oracle_mod, gpu_ctx_factory, sphere, spindle, torus
     g2 = gpu_ctx_factory()
     g2.set_mesh(ps, ts)
     assert g2.num_edges() == 2 * E + 3 * t.shape[0]
+
+
+def test_against_committed_golden_fixtures(gpu_ctx_factory):
+    """The CUDA path against the fixtures committed under tests/golden/ (frozen oracle outputs, generator alongside):
+    initial sampling, dual triangles and energy at the frozen clustering (ico6, K = 12); curvature and the subdivision's
+    edge numbering (ridged ellipsoid, 162 vertices)."""
+    import json
+    import os
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(gold_dir, "oracle_ico6_k12.json")))
+    p, t = meshgen.geodesic_icosphere(6)
+    for metric in ("iso", "qem"):
+        gm = gold[metric]
+        g = gpu_ctx_factory()
+        g.set_mesh(p, t)
+        g.build_items(metric)
+        g.set_num_clusters(12)
+        g.initial_sampling()
+        assert g.clustering().tolist() == gm["initial_sampling"]
+        g.set_clustering(np.asarray(gm["clustering"], dtype=np.int32))
+        assert g.dual_triangles().tolist() == gm["dual_triangles"]
+        g.recompute_statistics(1, 3)
+        assert abs(g.global_energy() - gm["energy"]) <= REL * abs(gm["energy"])
+    gold = json.load(open(os.path.join(gold_dir, "oracle_curv_edges_ico4.json")))
+    p, t = meshgen.ridged_ellipsoid(4)
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    ind, info = g.curvature(3)
+    gi = np.asarray(gold["indicator"])
+    assert np.abs(ind - gi).max() <= REL * np.abs(gi).max()
+    ps, ts, p1, p2 = g.subdivide()
+    V = p.shape[0]
+    assert p1[V:].tolist() == gold["edge_v1"] and p2[V:].tolist() == gold["edge_v2"]

@@ -247,6 +247,17 @@ def test_golden_fixture_matches(oracle_mod):
         assert o.report()["loops"] == g["loops"]
 
 
+def test_golden_curvature_and_edge_order(oracle_mod):
+    gold = json.load(open(os.path.join(GOLD, "oracle_curv_edges_ico4.json")))
+    p, t = meshgen.ridged_ellipsoid(4)
+    o = oracle_mod.Oracle(p, t)
+    ind, info = o.curvature(3)
+    assert np.allclose(ind, gold["indicator"], rtol=1e-12, atol=0)
+    assert np.allclose(info, np.asarray(gold["info"], dtype=np.float32), rtol=1e-6, atol=1e-9)
+    a, b = o.edges()
+    assert a.tolist() == gold["edge_v1"] and b.tolist() == gold["edge_v2"]
+
+
 # ---------------------------------------------------------------- C ABI surface (no compute without a GPU)
 def test_capi_exports_every_declared_symbol(capi_mod):
     hdr = open(os.path.join(ROOT, "include", "acvd_b200.h")).read()
