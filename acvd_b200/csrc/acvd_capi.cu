@@ -825,16 +825,14 @@ static void launch_evaluate(acvd_ctx* c, const ReassignArgs& A, bool as_iso, int
 
 static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso, int slot = 0) {
     cudaEvent_t* ev = c->ev + 4 * slot;
-    // proposals of the previous round become the carry list (none survive a phase start: everything is dirty)
-    if (force_all) ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p + 1, 0, sizeof(unsigned long long), c->stream));
-    else ACVD_CUDA(cudaMemcpyAsync(c->round_scalars.p + 1, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    // proposals of the previous round become the carry list (none survive a phase start: everything is dirty); the
+    // counters of the round are opened by k_modbits
     c->plist_cur ^= 1;
     ReassignArgs A = make_args(c, cfg, connexity, force_all);
     ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
-    ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
-    ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, sizeof(unsigned long long), c->stream));
     const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 8, gc = kNumSMs * 4;
-    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, c->ctr.p,
+                                                          c->round_scalars.p, force_all ? 2 : 1);
     ACVD_LAUNCH_CHECK();
     const int n_tiles = (c->V + 31) / 32;
     const bool filtered = plan_scan(c, A, force_all, 0, n_tiles);
@@ -928,9 +926,8 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     ReassignArgs A = make_args(c, cfg, 0, force_all);
     A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 1;
     BulkArgs B = make_bulk_args(c);
-    ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
-    ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, c->ctr.p,
+                                                          c->round_scalars.p, 2);
     ACVD_LAUNCH_CHECK();
     const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 2;
     const int n_tiles = (c->V + 31) / 32;
@@ -1148,7 +1145,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         // quarter of the host synchronisations.
         int batch = 1;
         if ((c->world == 1 || c->replicated_tail) && nconv >= 2 && !force_all && !reeval_all && !p.log_energy && !trace_on() &&
-            last_proposals >= 0 && last_proposals <= kReplicatedTailProposals)
+            last_proposals >= 0 && !c->last_all_tiles)    // sparse rounds only: a dense round re-plans the scan mode after every round
             batch = (int)std::min<int64_t>(p.rounds_per_sync > 0 ? std::min(p.rounds_per_sync, kRoundSlots) : kTailBatch,
                                            std::max<int64_t>(1, p.max_loops - loops));
         if (c->world > 1 && !c->replicated_tail) {

@@ -84,8 +84,19 @@ static __device__ __noinline__ bool connexity_problem(int v, int a, const int* _
 // k_modbits: one bit per cluster, set when the cluster was modified in the previous round (or force_all).
 // K/8 bytes (50 KB at K = 400k): the scan's "recently modified" look-ups hit L1 instead of gathering
 // 4-byte stamps from L2.
+// When `ctr` is given the kernel also opens the round's counters (one launch instead of three small memsets / copies):
+// the proposals of the previous round become the carry count (prev_mode 1) or the carry list is dropped (2), the
+// active-tile count and the round counters are zeroed.
 __global__ void __launch_bounds__(kThreads) k_modbits(int K, const int* __restrict__ mod_round, int rm1, int force_all,
-                                                      unsigned* __restrict__ bits) {
+                                                      unsigned* __restrict__ bits, RoundCounters* ctr = nullptr,
+                                                      unsigned long long* round_scalars = nullptr, int prev_mode = 0) {
+    if (ctr && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (prev_mode == 1) round_scalars[1] = ctr->proposals;
+        else if (prev_mode == 2) round_scalars[1] = 0;
+        round_scalars[0] = 0;
+        ctr->proposals = 0; ctr->mods = 0; ctr->tests = 0; ctr->evaluated = 0; ctr->boundary = 0;
+        ctr->pad[0] = 0; ctr->pad[1] = 0; ctr->pad[2] = 0;
+    }
     const int n_words = (K + 31) >> 5;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_words * 32; c += gridDim.x * blockDim.x) {
         bool m = c < K && (force_all || mod_round[c] >= rm1);
