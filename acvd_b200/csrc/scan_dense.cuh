@@ -49,19 +49,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-// shared-memory counter increment by ONE lane, as a compare-and-swap loop: around atom.shared.add the assembler puts
-// a warp-aggregation sequence (vote, popc, shuffle: a dozen instructions, twice per tile) that is useless when a single
-// lane calls it; with 8 warps per counter the CAS succeeds at the first or second attempt
-__device__ __forceinline__ int smem_fetch_inc(uint32_t addr) {
-    int old;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(old) : "r"(addr) : "memory");
-    while (true) {
-        int prev;
-        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(prev) : "r"(addr), "r"(old), "r"(old + 1) : "memory");
-        if (prev == old) return old;
-        old = prev;
-    }
-}
 // one contiguous global -> shared copy by the TMA engine; `bytes` and both addresses are multiples of 16
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -135,7 +122,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
     const int n_tickets = n_groups * kDenseWarps;
     while (true) {
         int n = 0;
-        if (lane == 0) n = smem_fetch_inc(bar0 + 112);
+        if (lane == 0) n = atomicAdd(ticket, 1);
         n = __shfl_sync(0xffffffffu, n, 0);
         if (n >= n_tickets) break;
         const int g = n / kDenseWarps, slot = n % kDenseWarps;
@@ -272,7 +259,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
-            if (smem_fetch_inc(bar0 + 64 + 4 * s) == kDenseWarps - 1) {
+            if (atomicAdd(&done_cnt[s], 1) == kDenseWarps - 1) {
                 done_cnt[s] = 0;
                 if (g + S < n_groups) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
