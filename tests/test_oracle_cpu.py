@@ -369,3 +369,27 @@ def test_curvature_oracle_known_answers(oracle_mod):
     T = np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]], dtype=np.int32)
     ind, info = oracle_mod.Oracle(P, T).curvature(3)
     assert np.all(ind == 0) and np.all(info == 0)
+
+
+def test_ply_round_trip_and_generators(tmp_path):
+    """On-disk format of the front-ends (binary little-endian PLY, float32 xyz, uchar + int32 face lists) and the closed,
+    consistently oriented synthetic workloads the parity tests and the bench are built on."""
+    from acvd_b200 import meshio
+    for p, t in (meshgen.geodesic_icosphere(5), meshgen.torus_grid(12, 8), meshgen.bipyramid(7, 1), meshgen.ridged_ellipsoid(4)):
+        meshio.write_ply(tmp_path / "m.ply", p, t)
+        q, u = meshio.read_ply(tmp_path / "m.ply")
+        assert q.dtype == np.float32 and u.dtype == np.int32 and np.array_equal(q, p) and np.array_equal(u, t)
+        # closed 2-manifold: every undirected edge twice, once in each direction
+        e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
+        key = e[:, 0].astype(np.int64) * p.shape[0] + e[:, 1]
+        rev = e[:, 1].astype(np.int64) * p.shape[0] + e[:, 0]
+        assert len(np.unique(key)) == len(key) and np.array_equal(np.sort(key), np.sort(rev))
+    # Euler characteristic: sphere 2, torus 0
+    p, t = meshgen.geodesic_icosphere(5)
+    assert p.shape[0] - 3 * t.shape[0] // 2 + t.shape[0] == 2
+    p, t = meshgen.torus_grid(12, 8)
+    assert p.shape[0] - 3 * t.shape[0] // 2 + t.shape[0] == 0
+    # subdivide (numpy helper used by the high-valence generator): V + E vertices, 4 F faces, still closed
+    p, t = meshgen.geodesic_icosphere(3)
+    ps, ts = meshgen.subdivide(p, t)
+    assert ps.shape[0] == p.shape[0] + 3 * t.shape[0] // 2 and ts.shape[0] == 4 * t.shape[0]
