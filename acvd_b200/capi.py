@@ -42,7 +42,7 @@ class Report(C.Structure):
         ("evaluated", C.c_int64), ("ms_device", C.c_double),
         ("kernel_launches", C.c_int64), ("bulk_rounds", C.c_int64),
         ("dense_scan_launches", C.c_int64), ("ms_dense_scan", C.c_double), ("dense_scan_bytes", C.c_int64),
-        ("dense_scan_vertices", C.c_int64),
+        ("dense_scan_vertices", C.c_int64), ("bulk_rollbacks", C.c_int64),
     ]
 
     def asdict(self):
@@ -78,7 +78,8 @@ SYMBOLS = [
     ("acvd_minimize", C.c_int, [_vp, C.POINTER(Params), C.POINTER(Report)]),
     ("acvd_recompute_statistics", C.c_int, [_vp, C.c_int, C.c_int]),
     ("acvd_clean_clustering", C.c_int, [_vp, C.POINTER(_i32)]),
-    ("acvd_fill_holes", C.c_int, [_vp]),
+    ("acvd_fill_holes", C.c_int, [_vp, C.c_int]),
+    ("acvd_connexity_problem", C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     ("acvd_reassign_round", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     ("acvd_get_cluster_stats", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ("acvd_global_energy", C.c_int, [_vp, C.POINTER(_d)]),
@@ -251,8 +252,17 @@ class Context:
         self._ck(self.L.acvd_clean_clustering(self.h, C.byref(d)))
         return d.value
 
-    def fill_holes(self):
-        self._ck(self.L.acvd_fill_holes(self.h))
+    def fill_holes(self, connexity=0):
+        self._ck(self.L.acvd_fill_holes(self.h, int(connexity)))
+
+    def connexity_problem(self, items, clusters, mode=0):
+        """Device connexity predicate on (item, cluster) pairs against the current clustering (uint8 array)."""
+        it = np.ascontiguousarray(items, dtype=np.int32)
+        cl = np.ascontiguousarray(clusters, dtype=np.int32)
+        assert it.shape == cl.shape
+        out = np.zeros(it.size, dtype=np.uint8)
+        self._ck(self.L.acvd_connexity_problem(self.h, it.size, _p(it), _p(cl), int(mode), _p(out)))
+        return out
 
     def reassign_round(self, constrained=1, quadrics_level=3, connexity=0):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

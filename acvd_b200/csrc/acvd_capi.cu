@@ -13,6 +13,7 @@
 
 #include "cleanup.cuh"
 #include "curvature.cuh"
+#include "fill.cuh"
 #include "common.cuh"
 #include "ctx.cuh"
 #include "host_sampling.hpp"
@@ -54,6 +55,20 @@ struct TraceScope {
         fprintf(stderr, "[acvd trace] %-28s %10.3f ms\n", name, ms);
     }
 };
+
+struct EventPair {   // RAII: the events do not leak when a throw leaves the API call
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() { ACVD_CUDA(cudaEventCreate(&a)); if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); throw CudaError{cudaErrorUnknown, "cudaEventCreate", __FILE__, __LINE__}; } }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+};
+
+__global__ void k_check_range(int64_t n, const int* __restrict__ a, int hi, unsigned long long* bad) {
+    unsigned cnt = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) cnt += (a[i] < 0 || a[i] >= hi) ? 1u : 0u;
+    acvd::warp_count_add(bad, cnt);
+}
 
 static void* cub_temp(acvd_ctx* c, size_t bytes) {
     c->cub_temp.alloc(bytes + 16);
@@ -135,7 +150,10 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     ACVD_API_BEGIN(c)
     if (V <= 0 || F <= 0 || !xyz || !tri) throw std::runtime_error("acvd_set_mesh: bad arguments");
     c->V = V; c->F = F;
+    // a new mesh invalidates everything derived from the old one: items, clusters (acvd_set_num_clusters is required
+    // again: the per-vertex buffers are sized by it), saved clustering, tile signatures, fixed-point scale
     c->have_items = false; c->stats_valid = false; c->sub_V = c->sub_F = 0;
+    c->K = 0; c->sig_valid = false; c->fx_scale = 0.0; c->cid_saved.release(); c->has_frozen = c->has_anchor = false; c->fixed.clear();
     c->vpad = (((int64_t)V + 31) / 32) * 32;      // per-vertex streams are padded to whole 32-vertex tiles (TMA copies whole tiles)
     c->xyz.alloc(3 * (size_t)c->vpad);
     c->tri.alloc(3 * (size_t)F);
@@ -143,6 +161,13 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
         TraceScope ts(c, "set_mesh: upload");
         ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        // vertex indices outside [0, V) would index the counting build out of bounds: reject them here
+        ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(unsigned long long), c->stream));
+        k_check_range<<<grid_for(3 * (int64_t)F), kThreads, 0, c->stream>>>(3 * (int64_t)F, c->tri.p, V, c->scalars.p);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->h_scalars[0] != 0) { c->V = c->F = 0; throw std::runtime_error("acvd_set_mesh: triangle vertex index out of range"); }
     }
     // --- CSR adjacency and vertex -> face incidence (faces ascending per vertex), by counting: see mesh.cuh
     {
@@ -365,6 +390,7 @@ extern "C" int acvd_build_items(acvd_ctx* c, int metric, double gradation, const
     if (!custom && ((metric == M_QEM && gradation > 0) || (aniso && gradation != 0)))
         throw std::runtime_error("acvd_build_items: gradation needs custom_weights (curvature indicator)");
     c->metric = metric;
+    c->fx_scale = 0.0;                         // the bulk rounds' fixed-point scale depends on the items
     c->weight.alloc((size_t)c->vpad);
     c->items.alloc((size_t)V * payload_npad(metric));
     compute_areas(c);
@@ -406,6 +432,7 @@ extern "C" int acvd_set_items(acvd_ctx* c, int metric, const double* payload) {
     if (!c->V || !payload || metric < 0 || metric > 3) throw std::runtime_error("acvd_set_items: bad arguments");
     const int V = c->V, np = payload_np(metric), npad = payload_npad(metric);
     c->metric = metric;
+    c->fx_scale = 0.0;
     c->items.alloc((size_t)V * npad);
     c->weight.alloc((size_t)c->vpad);
     DevBuf<double> tmp;
@@ -458,6 +485,7 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
     {
         const size_t n_tiles = ((size_t)V + 31) / 32;
         c->tile_sig.alloc(n_tiles * kSigSlots); c->tile_active.alloc(n_tiles); c->tile_stale.alloc(n_tiles); c->prop_mask.alloc(n_tiles);
+        c->moved_mask.alloc(n_tiles);
         ACVD_CUDA(cudaMemsetAsync(c->prop_mask.p, 0, n_tiles * sizeof(unsigned), c->stream));
         ACVD_CUDA(cudaMemsetAsync(c->tile_stale.p, 1, n_tiles, c->stream)); c->active_tiles.alloc(n_tiles); c->round_scalars.alloc(2);
         ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
@@ -481,9 +509,12 @@ extern "C" int acvd_set_clustering(acvd_ctx* c, const int32_t* cl) {
     ACVD_API_BEGIN(c)
     if (!c->K || !cl) throw std::runtime_error("acvd_set_clustering: set the number of clusters first");
     ACVD_CUDA(cudaMemcpyAsync(c->cid.p, cl, (size_t)c->V * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    // ids outside [0, K) are "not assigned" for the reference (:560-561): one NULL value, K, inside the library
+    k_normalise_null<<<grid_for(c->V), kThreads, 0, c->stream>>>(c->V, c->K, c->cid.p);
+    ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
-    c->stats_valid = false;
+    c->stats_valid = false; c->sig_valid = false;
     ACVD_API_END(c)
 }
 
@@ -652,7 +683,8 @@ static int clean_clustering(acvd_ctx* c) {
     return (int)c->h_scalars[1];
 }
 
-static void fill_holes(acvd_ctx* c) {
+// FillHolesInClustering, order-exact (fill.cuh).  `connexity` = the engine's ConnexityConstraint at the time of the call.
+static void fill_holes(acvd_ctx* c, int connexity) {
     TraceScope ts(c, "fill_holes");
     const int V = c->V, K = c->K;
     c->null_list.alloc(V);
@@ -663,31 +695,77 @@ static void fill_holes(acvd_ctx* c) {
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     const int n = (int)c->h_scalars[0];
     if (n == 0) return;
-    c->pick.alloc(n);
-    // the list order depends on atomics; sort it so the (deterministic) result does not depend on it
-    {
-        c->sort_k0.alloc(V);
-        size_t tb = 0;
-        ACVD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, c->null_list.p, c->sort_k0.p, n, 0, 32, c->stream));
+    if (trace_on()) fprintf(stderr, "[acvd trace]   fill: %d NULL vertices, connexity %d\n", n, connexity);
+    c->stats_valid = false;
+    FillMesh M{V, K, c->row_ptr.p, c->col.p, c->vf_ptr.p, c->vf_keys.p, c->tri.p};
+    size_t tb = 0;
+    if (connexity && n <= kFillSequentialCap) {
+        // ---- replay of the reference's FIFO by one thread on the slot-sorted initial edges
+        DevBuf<unsigned> slot0, slot1;
+        DevBuf<int> idx0, idx1;
+        DevBuf<int2> e0, q;
+        const size_t cap_init = (size_t)n * (size_t)std::max(c->max_deg, 1);
+        slot0.alloc(cap_init); slot1.alloc(cap_init); idx0.alloc(cap_init); idx1.alloc(cap_init); e0.alloc(cap_init);
+        ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
+        k_fill_initial_edges<<<grid_for(n), kThreads, 0, c->stream>>>(M, n, c->null_list.p, c->cid.p, slot0.p, e0.p, c->scalars.p);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        const int n_init = (int)c->h_scalars[0];
+        const long long cap = (long long)n_init + (long long)c->h_scalars[1];
+        if (n_init == 0) return;   // unreachable holes stay NULL, as in the reference (:619-631)
+        k_iota<<<grid_for(n_init), kThreads, 0, c->stream>>>(n_init, idx0.p);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, slot0.p, slot1.p, idx0.p, idx1.p, n_init, 0, 32, c->stream));
         void* t = cub_temp(c, tb);
-        ACVD_CUDA(cub::DeviceRadixSort::SortKeys(t, tb, c->null_list.p, c->sort_k0.p, n, 0, 32, c->stream));
-        ACVD_CUDA(cudaMemcpyAsync(c->null_list.p, c->sort_k0.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, slot0.p, slot1.p, idx0.p, idx1.p, n_init, 0, 32, c->stream));
+        q.alloc((size_t)cap);
+        k_gather_int2<<<grid_for(n_init), kThreads, 0, c->stream>>>(n_init, idx1.p, e0.p, q.p);
+        ACVD_LAUNCH_CHECK();
+        k_fill_sequential<<<1, 32, 0, c->stream>>>(M, n_init, cap, q.p, c->cid.p, connexity, c->scalars.p + 4);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 4, c->scalars.p + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->h_scalars[5] == 0) return;
+        // a ring longer than kMaxRing among the NULL vertices: finish with the level-synchronous passes below
     }
+    // ---- level-synchronous passes (exact while the connexity guard is off)
+    // the list order depends on atomics; sort it so nothing below depends on it
+    c->sort_k0.alloc(V);
+    ACVD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, c->null_list.p, c->sort_k0.p, n, 0, 32, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceRadixSort::SortKeys(t, tb, c->null_list.p, c->sort_k0.p, n, 0, 32, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->null_list.p, c->sort_k0.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    c->pick.alloc(n); c->fill_lvl.alloc(V); c->fill_seq.alloc(V);
+    DevBuf<unsigned long long> key, fkey0, fkey1;
+    DevBuf<int> fv0, fv1;
+    key.alloc(n); fkey0.alloc(n); fkey1.alloc(n); fv0.alloc(n); fv1.alloc(n);
+    ACVD_CUDA(cudaMemsetAsync(c->fill_lvl.p, 0, (size_t)V * sizeof(int), c->stream));
     int64_t remaining = n;
-    if (trace_on()) fprintf(stderr, "[acvd trace]   fill: %d NULL vertices\n", n);
-    while (remaining > 0) {
+    int base = 0;
+    for (int level = 1; remaining > 0; level++) {
         ACVD_CUDA(cudaMemsetAsync(c->scalars.p + 3, 0, sizeof(unsigned long long), c->stream));
-        k_fill_pick<<<grid_for(n), kThreads, 0, c->stream>>>(n, K, c->null_list.p, c->row_ptr.p, c->col.p, c->cid.p, c->pick.p);
-        k_fill_apply<<<grid_for(n), kThreads, 0, c->stream>>>(n, c->null_list.p, c->pick.p, c->cid.p, c->scalars.p + 3);
-        c->launches += 1;
+        // with the guard on every pass looks at all assigned neighbours again (a refused vertex may pass later)
+        k_fill_level_pick<<<grid_for(n), kThreads, 0, c->stream>>>(M, n, c->null_list.p, c->cid.p, c->fill_lvl.p, c->fill_seq.p,
+                                                                   connexity ? 1 : level, connexity, key.p, c->pick.p);
+        ACVD_LAUNCH_CHECK();
+        k_fill_level_apply<<<grid_for(n), kThreads, 0, c->stream>>>(n, c->null_list.p, key.p, c->pick.p, level, c->cid.p, c->fill_lvl.p,
+                                                                    fkey0.p, fv0.p, c->scalars.p + 3);
         ACVD_LAUNCH_CHECK();
         ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 3, c->scalars.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
-        int64_t filled = (int64_t)c->h_scalars[3];
+        const int64_t filled = (int64_t)c->h_scalars[3];
         if (filled == 0) break;   // unreachable holes stay NULL, as in the reference (:619-631)
         remaining -= filled;
+        if (remaining > 0 && !connexity) {   // adoption sequence numbers of this level order the next level's ties
+            ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, fkey0.p, fkey1.p, fv0.p, fv1.p, (int)filled, 0, 64, c->stream));
+            t = cub_temp(c, tb);
+            ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, fkey0.p, fkey1.p, fv0.p, fv1.p, (int)filled, 0, 64, c->stream));
+            k_fill_level_seq<<<grid_for(filled), kThreads, 0, c->stream>>>((int)filled, fv1.p, base, c->fill_seq.p);
+            ACVD_LAUNCH_CHECK();
+            base += (int)filled;
+        }
     }
-    c->stats_valid = false;
 }
 
 extern "C" int acvd_clean_clustering(acvd_ctx* c, int32_t* disconnected) {
@@ -698,10 +776,10 @@ extern "C" int acvd_clean_clustering(acvd_ctx* c, int32_t* disconnected) {
     ACVD_API_END(c)
 }
 
-extern "C" int acvd_fill_holes(acvd_ctx* c) {
+extern "C" int acvd_fill_holes(acvd_ctx* c, int connexity) {
     ACVD_API_BEGIN(c)
     if (!c->K) throw std::runtime_error("acvd_fill_holes: no clustering");
-    fill_holes(c);
+    fill_holes(c, connexity);
     ACVD_API_END(c)
 }
 
@@ -720,7 +798,7 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.anchor = c->has_anchor ? c->anchor.p : nullptr;
     A.xyz = c->xyz.p;
     A.best = c->best.p; A.prop_dst = c->prop_dst.p; A.prop_key = c->prop_key.p; A.prop_e = c->prop_e.p;
-    A.prop_mask = c->prop_mask.p; A.weight = c->weight.p;
+    A.prop_mask = c->prop_mask.p; A.moved_mask = nullptr; A.weight = c->weight.p;
     A.plist = c->plist_cur ? c->plist_b.p : c->plist.p;
     A.plist_prev = c->plist_cur ? c->plist.p : c->plist_b.p;
     A.n_prev_props = c->round_scalars.p + 1;
@@ -737,10 +815,10 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
 // dense bulk rounds: the TMA-staged streaming scan (scan_dense.cuh), one wave of MINB blocks per SM
 template <int W, int S, int MINB>
 static void launch_scan_bulk_dense(acvd_ctx* c, const ReassignArgs& A) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};           // the attribute is per device
+    if (c->device >= 64 || !configured[c->device]) {
         ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense<W, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W, S)));
-        configured = true;
+        if (c->device < 64) configured[c->device] = true;
     }
     const int n_tiles = A.tile_end - A.tile_begin;
     const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
@@ -925,6 +1003,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     c->plist_cur = 0;
     ReassignArgs A = make_args(c, cfg, 0, force_all);
     A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 1;
+    if (stage == 1) A.moved_mask = c->moved_mask.p;      // stage 1 can be undone (energy guard)
     BulkArgs B = make_bulk_args(c);
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, c->ctr.p,
                                                           c->round_scalars.p, 2);
@@ -953,6 +1032,25 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 8, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     c->round++;
     c->stats_valid = false;
+}
+
+// the stage-1 energy guard tripped: the last bulk round is undone (cluster ids only; the statistics are recomputed
+// from the clustering when the bulk rounds end)
+static void bulk_rollback(acvd_ctx* c) {
+    if (c->world > 1) {
+        if (c->last_bulk_total > 0) {
+            k_bulk_rollback_moves<<<kNumSMs * 4, kThreads, 0, c->stream>>>(c->cid.p, c->prop_dst.p, reinterpret_cast<const int2*>(c->moves_all.p),
+                                                                         (int)c->last_bulk_total);
+            ACVD_LAUNCH_CHECK();
+        }
+    } else {
+        EvalCfg cfg = make_cfg(0, 0, 0);
+        ReassignArgs A = make_args(c, cfg, 0, 0);
+        A.moved_mask = c->moved_mask.p;
+        k_bulk_rollback<<<grid_for((int64_t)c->V), kThreads, 0, c->stream>>>(A);
+        ACVD_LAUNCH_CHECK();
+    }
+    c->stats_valid = false; c->sig_valid = false;
 }
 
 static RoundResult finish_round(acvd_ctx* c, int slot = 0, bool last_of_batch = true) {
@@ -1046,11 +1144,8 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     int constrained = (c->metric == M_QEM && p.unconstrained_init) ? 0 : 1;
     int connexity = p.connexity;
     const int qlevel = p.quadrics_level;
-    cudaEvent_t ec0, ec1, et0, et1;
-    ACVD_CUDA(cudaEventCreate(&ec0));
-    ACVD_CUDA(cudaEventCreate(&ec1));
-    ACVD_CUDA(cudaEventCreate(&et0));
-    ACVD_CUDA(cudaEventCreate(&et1));
+    EventPair clean_ev, total_ev;          // destroyed on every exit path
+    cudaEvent_t ec0 = clean_ev.a, ec1 = clean_ev.b, et0 = total_ev.a, et1 = total_ev.b;
     ACVD_CUDA(cudaEventRecord(et0, c->stream));
     const int64_t launches0 = c->launches;
     auto timed_clean = [&](auto&& fn) {
@@ -1063,7 +1158,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         R.ms_clean += ms;
     };
     // prime: FillHoles, ReComputeStatistics, SetAllClustersToModified (:727-730)
-    timed_clean([&] { fill_holes(c); recompute_statistics(c, constrained, qlevel, thr); });
+    timed_clean([&] { fill_holes(c, connexity); recompute_statistics(c, constrained, qlevel, thr); });
     int force_all = 1;
     int64_t last_proposals = -1;
     bool reeval_all = false;   // first replicated round of a multi-GPU tail
@@ -1081,7 +1176,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     int64_t loops = 0;
     const int bulk_cap = p.bulk_rounds < 0 ? 0 : (p.bulk_rounds == 0 ? 1000 : p.bulk_rounds);
     const int env_passes = getenv("ACVD_COMMIT_PASSES") ? std::max(1, atoi(getenv("ACVD_COMMIT_PASSES"))) : 0;
-    c->commit_passes = p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : (c->world > 1 ? 1 : 2));
+    c->commit_passes = p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : 2);   // one default for every world size: N GPUs give the 1-GPU clustering
     while (true) {
         EvalCfg cfg = make_cfg(constrained, qlevel, thr);
         const bool as_iso = qem_as_iso(c, constrained, qlevel);
@@ -1124,11 +1219,21 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                     if (stage == 0) {
                         if (dry) { stage = 1; fa = 1; e_prev = bulk_energy(c); }
                     } else {
+                        // stage 1 applies its moves simultaneously against round-start sums: no monotonicity guarantee,
+                        // hence the guard -- a round that raised the energy is undone, and the exact rounds take over
                         const double e = bulk_energy(c);
-                        if (dry || e > e_prev) break;
+                        if (e > e_prev) {
+                            bulk_rollback(c);
+                            R.modifications -= (int64_t)r.mods; R.bulk_rollbacks++;
+                            if (p.log_energy && !c->energy_log.empty()) c->energy_log.pop_back();
+                            break;
+                        }
+                        if (dry) break;
                         e_prev = e;
                     }
                 }
+                // proposals of the bulk rounds are not proposals of the exact rounds
+                ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
                 timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
             }
         }
@@ -1187,7 +1292,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         nconv++;
         R.convergences++;
         int disc = 0;
-        timed_clean([&] { disc = clean_clustering(c); fill_holes(c); });
+        timed_clean([&] { disc = clean_clustering(c); fill_holes(c, connexity); });
         R.disconnected = disc;
         const bool done = (disc == 0 && mods == 0) || loops >= p.max_loops || nconv >= p.max_convergences;
         // the reference leaves the incremental sums in place on exit; we always export fresh statistics
@@ -1202,10 +1307,6 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     ACVD_CUDA(cudaEventElapsedTime(&ms_dev, et0, et1));
     R.ms_device = ms_dev;
     R.kernel_launches = c->launches - launches0;
-    cudaEventDestroy(ec0);
-    cudaEventDestroy(ec1);
-    cudaEventDestroy(et0);
-    cudaEventDestroy(et1);
     R.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rep) *rep = R;
     ACVD_API_END(c)
@@ -1264,6 +1365,24 @@ extern "C" int acvd_representative_points(acvd_ctx* c, int32_t n, const double* 
     ACVD_API_END(c)
 }
 
+// the device connexity predicate on caller-given pairs (parity hook for ConnexityConstraintProblemLocal)
+extern "C" int acvd_connexity_problem(acvd_ctx* c, int32_t n, const int32_t* items, const int32_t* clusters, int32_t mode, uint8_t* out) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || n < 0 || (n && (!items || !clusters || !out))) throw std::runtime_error("acvd_connexity_problem: bad arguments");
+    if (n == 0) return ACVD_OK;
+    for (int i = 0; i < n; i++) if (items[i] < 0 || items[i] >= c->V) throw std::runtime_error("acvd_connexity_problem: item out of range");
+    DevBuf<int> d_it, d_cl;
+    DevBuf<unsigned char> d_out;
+    d_it.alloc(n); d_cl.alloc(n); d_out.alloc(n);
+    ACVD_CUDA(cudaMemcpyAsync(d_it.p, items, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(d_cl.p, clusters, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_connexity_query<<<grid_for(n), kThreads, 0, c->stream>>>(n, d_it.p, d_cl.p, c->row_ptr.p, c->col.p, c->cid.p, c->ringadj.p, mode, d_out.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel micro-benchmark: times `reps` back-to-back launches of one kernel on the current state (CUDA events on the
 // library stream).  kernel 0: dense bulk scan, `variant` = (stages, blocks/SM) variant, -1 = the list-based k_scan;
@@ -1283,9 +1402,8 @@ extern "C" int acvd_bench_kernel(acvd_ctx* c, int kernel, int variant, int stage
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, 0, c->modbits.p);
     ACVD_LAUNCH_CHECK();
     const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS);
-    cudaEvent_t e0, e1;
-    ACVD_CUDA(cudaEventCreate(&e0));
-    ACVD_CUDA(cudaEventCreate(&e1));
+    EventPair evp;
+    cudaEvent_t e0 = evp.a, e1 = evp.b;
     for (int r = -2; r < reps; r++) {          // two warm-up launches
         if (r == 0) ACVD_CUDA(cudaEventRecord(e0, c->stream));
         ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
@@ -1300,8 +1418,6 @@ extern "C" int acvd_bench_kernel(acvd_ctx* c, int kernel, int variant, int stage
     float ms = 0;
     ACVD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *ms_per_launch = ms / reps;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     ACVD_CUDA(cudaMemsetAsync(c->prop_mask.p, 0, (size_t)((c->V + 31) / 32) * sizeof(unsigned), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->leave_cnt.p, 0, (size_t)c->K * sizeof(int), c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));

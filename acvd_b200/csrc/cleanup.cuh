@@ -219,29 +219,11 @@ __global__ void k_count_ge2(int K, const int* __restrict__ n_comp, unsigned long
     warp_count_add(out, cnt);
 }
 
-// ---------------- hole filling: level-synchronous adoption by NULL vertices ----------------
+// ---------------- hole filling (fill.cuh): list of the NULL vertices ----------------
 __global__ void k_collect_null(int V, int K, const int* __restrict__ cid, int* list, unsigned long long* n) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x)
-        if (cid[v] >= K || cid[v] < 0) { int s = (int)atomicAdd(n, 1ull); list[s] = v; }
+        if (cid[v] >= K || cid[v] < 0) { int s = (int)atomicAdd(n, 1ull); list[s] = v; }   // ids are normalised to [0, K] on upload
 }
-// pick[i] = cluster of the first assigned neighbour (ascending vertex id) of NULL vertex list[i], or -1
-__global__ void k_fill_pick(int n, int K, const int* __restrict__ list, const int* __restrict__ row_ptr,
-                            const int* __restrict__ col, const int* __restrict__ cid, int* pick) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int v = list[i];
-        int p = -1;
-        if (cid[v] >= K || cid[v] < 0)
-            for (int e = row_ptr[v]; e < row_ptr[v + 1] && p < 0; e++) { int b = cid[col[e]]; if (b >= 0 && b < K) p = b; }
-        pick[i] = p;
-    }
-}
-__global__ void k_fill_apply(int n, const int* __restrict__ list, const int* __restrict__ pick, int* cid, unsigned long long* n_filled) {
-    unsigned cnt = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        if (pick[i] >= 0) { cid[list[i]] = pick[i]; cnt++; }
-    warp_count_add(n_filled, cnt);
-}
-
 // ---------------- integer stages ----------------
 __global__ void k_boundary_flags(int V, const int* __restrict__ row_ptr, const int* __restrict__ col,
                                  const int* __restrict__ cid, unsigned char* flags) {

@@ -54,6 +54,8 @@ struct acvd_ctx {
     DevBuf<unsigned long long> best, prop_key;
     DevBuf<int> prop_dst, plist, plist_b, work, tile_sig, active_tiles;
     DevBuf<unsigned char> tile_active, tile_stale;
+    DevBuf<unsigned> moved_mask;                // stage-1 bulk rounds: vertices the last commit moved (rollback)
+    int64_t last_bulk_total = 0;                // multi-GPU: move records of the last bulk round (in moves_all)
     DevBuf<unsigned> prop_mask;                 // bulk rounds: proposing vertices, one bit per vertex
     DevBuf<unsigned long long> round_scalars;   // [0] active tiles, [1] proposals of the previous round
     int plist_cur = 0;
@@ -75,7 +77,7 @@ struct acvd_ctx {
     cudaEvent_t ev[4 * 8] = {};       // 4 events per round slot
     // generic scratch
     DevBuf<char> cub_temp;
-    DevBuf<int> sort_k0, sort_k1, sort_v0, sort_v1, seg, label, comp_size, n_comp, n_roots, null_list, pick;
+    DevBuf<int> sort_k0, sort_k1, sort_v0, sort_v1, seg, label, comp_size, n_comp, n_roots, null_list, pick, fill_lvl, fill_seq;
     DevBuf<unsigned long long> winner, scalars;   // scalars: small device counters
     unsigned long long* h_scalars = nullptr;      // pinned, 8 entries + one active-tile count per round slot
     std::vector<double> energy_log;
@@ -114,6 +116,11 @@ struct AllocScope {   // routes DevBuf allocations of this API call to the conte
                  cudaGetErrorString(e.code), e.file, e.line, e.what);                \
         cudaGetLastError();                                                          \
         return fail((ctx), e.code == cudaErrorMemoryAllocation ? ACVD_ENOMEM : ACVD_ECUDA, buf); \
+    }                                                                                \
+    catch (const NcclError& e) {                                                     \
+        std::string m = std::string("NCCL error in ") + e.what + ": " +             \
+                        (nccl().GetErrorString ? nccl().GetErrorString(e.code) : "?"); \
+        return fail((ctx), ACVD_ENCCL, m);                                           \
     }                                                                                \
     catch (const std::exception& e) { return fail((ctx), ACVD_EINVAL, e.what()); }   \
     catch (...) { return fail((ctx), ACVD_EINVAL, "unknown error"); }                \

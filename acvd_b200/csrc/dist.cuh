@@ -191,6 +191,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     RoundResult r;
     memset(&r, 0, sizeof r);
     const int64_t total = dist_gather_moves(c, sizeof(int2), r);
+    c->last_bulk_total = total;
     if (total > 0) {
         const int2* mv = reinterpret_cast<const int2*>(c->moves_all.p);
         k_bulk_count<<<gc, kThreads, 0, c->stream>>>(c->K, c->cid.p, mv, (int)total, c->leave_cnt.p);

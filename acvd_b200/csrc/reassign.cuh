@@ -432,10 +432,11 @@ __global__ void __launch_bounds__(kThreads) k_evaluate_long(ReassignArgs A) {
         double best_delta = 0.0, best_ea = 0.0, best_eb = 0.0;
         unsigned long long key = 0;
         if (a >= K) {
-            // NULL cluster: adopt the first assigned, non-frozen neighbour cluster; top priority
+            // NULL cluster: adopt the first assigned neighbour cluster, frozen or not -- the reference adopts
+            // (:881-907) before it looks at IsClusterFreezed (:909-920); top priority
             for (int e = beg; e < end && best_b < 0; e++) {
                 int b = A.cid[A.col[e]];
-                if (b < K && !(A.frozen && A.frozen[b])) best_b = b;
+                if (b < K) best_b = b;
             }
             key = (unsigned long long)(unsigned)v;
         } else if (!(A.frozen && A.frozen[a])) {
@@ -517,10 +518,11 @@ __global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) {
         double anchor_pt[3];
         if (active) {
             if (a >= K) {
-                // NULL cluster: adopt the first assigned, non-frozen neighbour cluster; top priority
+                // NULL cluster: adopt the first assigned neighbour cluster, frozen or not (:881-907 come before the
+                // frozen test of :909-920); top priority
 #pragma unroll
                 for (int k = kRingW - 1; k >= 0; k--)
-                    if (nbc[k] < K && !(A.frozen && A.frozen[nbc[k]])) best_b = nbc[k];
+                    if (nbc[k] < K) best_b = nbc[k];
                 key = (unsigned long long)(unsigned)v;
             } else if (!(A.frozen && A.frozen[a])) {
                 unsigned L = 0;
@@ -734,15 +736,22 @@ __global__ void __launch_bounds__(kThreads) k_bulk_commit(ReassignArgs A, BulkAr
         const unsigned m = (base + lane < n_tiles) ? A.prop_mask[t] : 0u;
         if (m) A.prop_mask[t] = 0;
         unsigned nz = __ballot_sync(0xffffffffu, m != 0);
+        unsigned moved_here = 0;        // lane `src` collects the moved bits of its tile
         while (nz) {
             const int src = __ffs(nz) - 1;
             nz &= nz - 1;
             const unsigned mm = __shfl_sync(0xffffffffu, m, src);
-            if (!((mm >> lane) & 1u)) continue;
+            const bool mine = (mm >> lane) & 1u;
             const int v = (A.tile_begin + base + src) * 32 + lane;
-            const int d = A.prop_dst[v];
-            const int a = A.cid[v];
-            if (a < K && B.leave_cnt[a] >= A.csize[a]) continue;
+            const int d = mine ? A.prop_dst[v] : -1;
+            const int a = mine ? A.cid[v] : -1;
+            const bool go = mine && !(a < K && B.leave_cnt[a] >= A.csize[a]);
+            if (A.moved_mask) {          // stage 1 keeps what it takes to undo the round (energy guard)
+                const unsigned mv = __ballot_sync(0xffffffffu, go);
+                if (lane == src) moved_here = mv;
+                if (go) A.prop_dst[v] = a;
+            }
+            if (!go) continue;
             const double* it = A.items + (int64_t)v * stride;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -757,8 +766,27 @@ __global__ void __launch_bounds__(kThreads) k_bulk_commit(ReassignArgs A, BulkAr
             mark_tiles_stale(A, v);
             n_mods++;
         }
+        if (A.moved_mask && base + lane < n_tiles) A.moved_mask[t] = moved_here;
     }
     warp_count_add(&A.ctr->mods, n_mods);
+}
+
+// Undo of the last stage-1 bulk round (its energy guard tripped): every moved vertex goes back to the cluster it came
+// from (k_bulk_commit left it in prop_dst).  Sums, sizes and centroids need no undo: exact statistics are recomputed
+// from the clustering when the bulk rounds end.
+__global__ void __launch_bounds__(kThreads) k_bulk_rollback(ReassignArgs A) {
+    const int n_tiles = A.tile_end - A.tile_begin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles * 32; i += gridDim.x * blockDim.x) {
+        const int t = A.tile_begin + (i >> 5);
+        if ((A.moved_mask[t] >> (i & 31)) & 1u) { const int v = t * 32 + (i & 31); A.cid[v] = A.prop_dst[v]; }
+    }
+}
+// multi-GPU form: the moves are the all-gathered (vertex, destination) records
+__global__ void __launch_bounds__(kThreads) k_bulk_rollback_moves(int* cid, const int* __restrict__ prev, const int2* __restrict__ moves, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = moves[i].x;
+        if (cid[v] == moves[i].y) cid[v] = prev[v];
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_bulk_refresh(int K, int* csize, BulkArgs B) {
@@ -909,6 +937,7 @@ __global__ void __launch_bounds__(kThreads) k_bulk_apply(ReassignArgs A, BulkArg
         A.mod_round[d] = A.round;
         if (a < K) A.mod_round[a] = A.round;
         A.cid[v] = d;
+        A.prop_dst[v] = a;          // what k_bulk_rollback_moves restores
         mark_tiles_stale(A, v);
         n_mods++;
     }

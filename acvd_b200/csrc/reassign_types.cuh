@@ -36,6 +36,7 @@ struct ReassignArgs {
     double2* prop_e;                    // V: (E(a - v), E(b + v)) of the proposal
     int* plist;                         // compact list of proposing vertices this round (exact rounds)
     unsigned* prop_mask;                // n_tiles: proposing vertices of a bulk round, one bit per vertex of the tile
+    unsigned* moved_mask;               // n_tiles or null: vertices k_bulk_commit moved (kept by stage 1 for its rollback)
     const double* __restrict__ weight;  // V: item weights (= items[v][3]), dense copy for the bulk rounds
     int* work;                          // compact list of boundary vertices to (re)evaluate this round
     const int* plist_prev;              // proposing vertices of the previous round

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ACVD_B200_ABI_VERSION 2
+#define ACVD_B200_ABI_VERSION 3
 
 typedef struct acvd_ctx acvd_ctx;
 
@@ -119,7 +119,7 @@ typedef struct acvd_params {
     int32_t rounds_per_sync;      /* rounds launched back to back between host polls in the tail of the last phases, <=0 -> 4, max 8 */
     double sv_threshold;          /* <=0 -> 1e-3 (Common/vtkQuadricTools.h:36) */
     int32_t bulk_rounds;          /* early phases: 0 -> bulk Lloyd-criterion rounds on (cap 1000), <0 -> off, >0 -> cap */
-    int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 2 on one GPU, 1 across GPUs */
+    int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 2 (the same default on any number of GPUs) */
 } acvd_params;
 
 typedef struct acvd_report {
@@ -146,6 +146,7 @@ typedef struct acvd_report {
     double ms_dense_scan;        /* device time in those launches */
     int64_t dense_scan_bytes;    /* algorithmic bytes they moved (SURVEY 8d model: 8 + 8 deg per vertex + the tests' operands) */
     int64_t dense_scan_vertices; /* vertices they scanned */
+    int64_t bulk_rollbacks;      /* stage-1 bulk rounds undone by the energy guard (0 or 1 per phase) */
 } acvd_report;
 
 /* MinimizeEnergy (Common/vtkUniformClustering.h:725-830) with ProcessOneLoop (:833-995) replaced by
@@ -157,7 +158,14 @@ int acvd_minimize(acvd_ctx* ctx, const acvd_params* params, acvd_report* report)
 int acvd_recompute_statistics(acvd_ctx* ctx, int constrained, int quadrics_level);
 /* CleanClustering (:406-549) / FillHolesInClustering (:552-633); *disconnected = clusters cleaned. */
 int acvd_clean_clustering(acvd_ctx* ctx, int32_t* disconnected);
-int acvd_fill_holes(acvd_ctx* ctx);
+/* connexity = the engine's ConnexityConstraint at the time of the call (the :606-607 guard); the adoption order is the
+ * reference's FIFO order (edge ids = first-seen order over the faces), so the result is the reference's bit for bit */
+int acvd_fill_holes(acvd_ctx* ctx, int connexity);
+/* vtkVerticesProcessing::ConnexityConstraintProblemLocal (DiscreteRemeshing/vtkVerticesProcessing.h:168-237) as the
+ * kernels evaluate it, on n caller-given (item, cluster) pairs against the current clustering: out[i] = 1 when taking
+ * items[i] out of clusters[i] would disconnect its ring neighbours in that cluster.  mode 0 = the product's choice (ring
+ * bit matrix for rows <= 8, generic walk for longer rows), 1 = generic walk for every row.  Parity hook for the tests. */
+int acvd_connexity_problem(acvd_ctx* ctx, int32_t n, const int32_t* items, const int32_t* clusters, int32_t mode, uint8_t* out /*n*/);
 /* One reassignment round on the current state (ProcessOneLoop analogue); outputs may be NULL. */
 int acvd_reassign_round(acvd_ctx* ctx, int constrained, int quadrics_level, int connexity,
                         int64_t* proposals, int64_t* modifications, int64_t* tests);

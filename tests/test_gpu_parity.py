@@ -540,3 +540,200 @@ def test_against_committed_golden_fixtures(gpu_ctx_factory):
     ps, ts, p1, p2 = g.subdivide()
     V = p.shape[0]
     assert p1[V:].tolist() == gold["edge_v1"] and p2[V:].tolist() == gold["edge_v2"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: pins at the BASELINE sizes, the connexity predicate itself, FillHoles in the reference's FIFO order
+
+def _scrambled_clustering(o, p, K, seed, n_scatter):
+    cl = o.initial_sampling().copy()
+    o.fill_holes()
+    cl = o.clustering().copy()
+    rng = np.random.default_rng(seed)
+    idx = rng.choice(p.shape[0], n_scatter, replace=False)
+    cl[idx] = rng.integers(0, K, size=n_scatter)
+    return cl
+
+
+@pytest.mark.parametrize("mesh", ["sphere", "spindle"])
+def test_connexity_predicate_matches_oracle(oracle_mod, gpu_ctx_factory, sphere, spindle, mesh):
+    """vtkVerticesProcessing::ConnexityConstraintProblemLocal (DiscreteRemeshing/vtkVerticesProcessing.h:168-237):
+    the device predicate -- ring bit matrix for rows <= 8, generic walk for longer rows -- against the oracle's
+    restatement on (item, cluster) pairs: every vertex with its own cluster and with the clusters of its neighbours,
+    on a clustering with many fragmented clusters; the spindle has two rows of length 24."""
+    p, t = sphere if mesh == "sphere" else spindle
+    K = 60
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K)
+    cl = _scrambled_clustering(o, p, K, 5, p.shape[0] // 6)
+    o.set_clustering(cl)
+    g.set_clustering(cl)
+    o.set_connexity(1)
+    rp, col = g.csr()
+    V = p.shape[0]
+    items = np.concatenate([np.arange(V, dtype=np.int32), np.repeat(np.arange(V, dtype=np.int32), np.diff(rp))])
+    clusters = np.concatenate([cl, cl[col]]).astype(np.int32)
+    want = np.array([o.connexity_problem(int(i), int(c)) for i, c in zip(items, clusters)], dtype=np.uint8)
+    assert want.sum() > 50 and (want == 0).sum() > 50          # both outcomes are exercised
+    for mode in (0, 1):
+        got = g.connexity_problem(items, clusters, mode)
+        assert np.array_equal(got, want), (mode, int((got != want).sum()))
+    long_rows = np.flatnonzero(np.diff(rp) > 8)
+    if mesh == "spindle":
+        assert long_rows.size == 2
+
+
+def _punch_holes(p, cl, K, seed, n_holes, radius):
+    """NULL (id K) patches several rings deep."""
+    rng = np.random.default_rng(seed)
+    cl = cl.copy()
+    centres = p[rng.choice(p.shape[0], n_holes, replace=False)]
+    for c in centres:
+        cl[np.linalg.norm(p - c, axis=1) < radius] = K
+    return cl
+
+
+@pytest.mark.parametrize("mesh", ["sphere", "torus", "spindle"])
+@pytest.mark.parametrize("connexity", [0, 1])
+def test_fill_holes_bit_exact(oracle_mod, gpu_ctx_factory, sphere, torus, spindle, mesh, connexity):
+    """FillHolesInClustering (Common/vtkUniformClustering.h:552-633) in the reference's FIFO order, including the
+    ConnexityConstraintProblem guard of :606-607: same clustering as the oracle's sequential queue, bit for bit --
+    (a) the NULL vertices the initial sampling leaves, (b) holes several rings deep, (c) scattered single holes."""
+    p, t = {"sphere": sphere, "torus": torus[:2], "spindle": spindle}[mesh]
+    K = 80
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K)
+    cl0 = o.initial_sampling().copy()
+    cases = [cl0]
+    o.fill_holes()
+    full = o.clustering().copy()
+    cases.append(_punch_holes(p, full, K, 3, 12, 0.12))
+    sc = full.copy()
+    sc[np.random.default_rng(4).choice(p.shape[0], 300, replace=False)] = K
+    cases.append(sc)
+    cases.append(_punch_holes(p, sc, K, 6, 3, 0.3))
+    n_null = 0
+    for cl in cases:
+        o.set_connexity(connexity)
+        o.set_clustering(cl)
+        g.set_clustering(cl)
+        o.fill_holes()
+        g.fill_holes(connexity)
+        co, cg = o.clustering(), g.clustering()
+        n_null += int((cl == K).sum())
+        assert np.array_equal(co, cg), int((co != cg).sum())
+        if not connexity:
+            assert cg.max() < K
+    assert n_null > 500
+
+
+def test_negative_ids_are_null(gpu_ctx_factory, sphere):
+    """Ids outside [0, K) are "not assigned" (vtkUniformClustering.h:560-561): normalised to the NULL id K on upload."""
+    p, t = sphere
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    g.build_items("iso")
+    g.set_num_clusters(50)
+    g.initial_sampling()
+    g.fill_holes()
+    cl = g.clustering()
+    cl2 = cl.copy()
+    cl2[::7] = -1
+    cl2[3::11] = 50 + 17
+    g.set_clustering(cl2)
+    back = g.clustering()
+    assert np.array_equal(back == 50, (cl2 < 0) | (cl2 >= 50))
+    g.fill_holes()
+    assert g.clustering().max() < 50 and g.clustering().min() >= 0
+
+
+def test_context_reuse_across_meshes_of_different_scale(oracle_mod, gpu_ctx_factory, sphere):
+    """One context, two meshes whose coordinates differ by 1e3: the bulk rounds' fixed-point scale follows the items
+    (it used to be cached for the lifetime of the context), and a new mesh needs a new cluster count."""
+    p, t = sphere
+    g = gpu_ctx_factory()
+    energies = []
+    for scale in (1.0, 1000.0, 0.01):
+        ps = (p * scale).astype(np.float32)
+        g.set_mesh(ps, t)
+        with pytest.raises(Exception):
+            g.clean_clustering()                     # the old clustering died with the old mesh
+        g.build_items("iso")
+        g.set_num_clusters(150)
+        g.initial_sampling()
+        rep = g.minimize()
+        assert rep["bulk_rounds"] > 0 and rep["disconnected"] == 0
+        o = oracle_mod.Oracle(ps, t)
+        o.build_metric("iso")
+        o.set_num_clusters(150)
+        o.initial_sampling()
+        o.minimize()
+        o.recompute_statistics()
+        assert abs(rep["energy"] - o.global_energy()) <= 0.01 * abs(o.global_energy())
+        energies.append(rep["energy"])
+    assert abs(energies[1]) > 1e9 * abs(energies[0]) > 1e9 * abs(energies[2])    # E ~ scale^4
+
+
+def test_set_mesh_rejects_bad_indices(gpu_ctx_factory, sphere):
+    p, t = sphere
+    g = gpu_ctx_factory()
+    bad = t.copy()
+    bad[5, 1] = p.shape[0] + 3
+    with pytest.raises(Exception):
+        g.set_mesh(p, bad)
+    bad[5, 1] = -2
+    with pytest.raises(Exception):
+        g.set_mesh(p, bad)
+    g.set_mesh(p, t)                                  # the context is still usable
+
+
+def _baseline_fixture():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_baseline_runs.json")
+    return json.load(open(path))
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3"])
+def test_baseline_size_energy_vs_oracle(oracle_mod, gpu_ctx_factory, name):
+    """BASELINE.json configs[0..2] at full size: the converged GPU energy is within 1 % of the sequential oracle's
+    (tests/golden/oracle_baseline_runs.json, produced by tests/golden/make_baseline_runs.py from the same generator and
+    the same initial sampling -- its sha256 is checked; C1 is also re-run live), and the oracle's ProcessOneLoop, primed
+    on the GPU's final clustering with the connexity constraint on, finds no improving move."""
+    import hashlib
+    fx = _baseline_fixture()[name]
+    w = meshgen.workload(name)
+    p, t, K = w["points"], w["triangles"], int(w["K"])
+    assert (p.shape[0], K) == (fx["V"], fx["K"])
+    uncon = fx["unconstrained_init"]
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    g.build_items(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
+    g.set_num_clusters(K)
+    g.initial_sampling()
+    cl0 = g.clustering()
+    assert hashlib.sha256(cl0.tobytes()).hexdigest() == fx["sha256_initial_sampling"]
+    rep = g.minimize(unconstrained_init=uncon)
+    cg = g.clustering()
+    e_o = fx["energy"]
+    assert abs(rep["energy"] - e_o) <= 0.01 * abs(e_o), (rep["energy"], e_o)
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
+    o.set_num_clusters(K)
+    if name == "C1":                                  # live re-run of the oracle (0.3 s): the fixture is not stale
+        o.set_clustering(cl0)
+        o.set_params(unconstrained_init=uncon)
+        o.minimize()
+        o.recompute_statistics()
+        assert abs(o.global_energy() - e_o) <= 1e-12 * abs(e_o)
+        assert o.report()["tests"] == fx["tests"] and o.report()["loops"] == fx["loops"]
+        o.set_num_clusters(K)
+    if w["metric"] in ("iso", "qem"):                 # stricter: translation-invariant energy sum w |p - c|^2
+        items = g.items()
+        _, cen, _, sz = g.cluster_stats()
+        assert sz.min() >= 1
+        te = oracle_mod.true_energy(p, items[:, 3], cg, cen)
+        assert te <= 1.01 * fx["true_energy"], (te, fx["true_energy"])
+    o.set_clustering(cg)
+    o.set_connexity(1)
+    o.prime()
+    assert o.process_one_loop() == 0
+    g.close()

@@ -268,7 +268,7 @@ def test_capi_exports_every_declared_symbol(capi_mod):
     assert not missing, missing
     bound = {name for name, _, _ in capi_mod.SYMBOLS}
     assert declared == bound, declared ^ bound
-    assert lib.acvd_abi_version() == 2
+    assert lib.acvd_abi_version() == int(re.search(r"#define ACVD_B200_ABI_VERSION (\d+)", hdr).group(1)) == 3
     assert [lib.acvd_payload_size(m) for m in range(4)] == [4, 13, 13, 22]
 
 
@@ -393,3 +393,28 @@ def test_ply_round_trip_and_generators(tmp_path):
     p, t = meshgen.geodesic_icosphere(3)
     ps, ts = meshgen.subdivide(p, t)
     assert ps.shape[0] == p.shape[0] + 3 * t.shape[0] // 2 and ts.shape[0] == 4 * t.shape[0]
+
+
+def test_baseline_fixture_c1_matches_live_oracle(oracle_mod):
+    """tests/golden/oracle_baseline_runs.json (C1/C2/C3 run to convergence by tests/golden/make_baseline_runs.py) is what
+    the GPU parity tests at the BASELINE sizes compare with: C1 is cheap enough to re-run here, so the fixture cannot
+    drift away from the oracle unnoticed."""
+    import hashlib
+    import json
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_baseline_runs.json")))
+    assert {"C1", "C2", "C3"} <= set(fx)
+    from acvd_b200 import meshgen
+    w = meshgen.workload("C1")
+    o = oracle_mod.Oracle(w["points"], w["triangles"])
+    o.build_metric(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
+    o.set_num_clusters(w["K"])
+    cl0 = o.initial_sampling().copy()
+    assert hashlib.sha256(cl0.tobytes()).hexdigest() == fx["C1"]["sha256_initial_sampling"]
+    o.minimize()
+    r = o.report()
+    assert (r["loops"], r["tests"], r["mods"]) == (fx["C1"]["loops"], fx["C1"]["tests"], fx["C1"]["modifications"])
+    o.recompute_statistics()
+    assert abs(o.global_energy() - fx["C1"]["energy"]) <= 1e-12 * abs(fx["C1"]["energy"])
+    assert hashlib.sha256(o.clustering().tobytes()).hexdigest() == fx["C1"]["sha256_clustering"]
+    for k in ("C2", "C3"):
+        assert fx[k]["convergences"] >= 3 and fx[k]["loops"] > 10 and fx[k]["energy"] < 0
