@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(kThreads) k_carry(ReassignArgs A) {
 // the commits so far is still exact (same sums, same energies, same ring in its source cluster), so it
 // competes again; repeating select + commit a few times approaches a maximal independent set of moves
 // per round without re-scanning the mesh.
-__global__ void __launch_bounds__(kThreads) k_resubmit(ReassignArgs A) {
+__device__ __forceinline__ void resubmit_list(const ReassignArgs& A, int n_props, unsigned long long* n_resubmitted = nullptr) {
     const int K = A.K;
-    const int n_props = (int)A.ctr->proposals;
+    unsigned cnt = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
         const int v = A.plist[i];
         const int d = A.prop_dst[v];
@@ -356,8 +356,11 @@ __global__ void __launch_bounds__(kThreads) k_resubmit(ReassignArgs A) {
         const unsigned long long key = A.prop_key[v];
         if (a < K) atomicMin(&A.best[a], key);
         atomicMin(&A.best[d], key);
+        cnt++;
     }
+    if (n_resubmitted) warp_count_add(n_resubmitted, cnt);
 }
+__global__ void __launch_bounds__(kThreads) k_resubmit(ReassignArgs A) { resubmit_list(A, (int)A.ctr->proposals); }
 
 // ---------------------------------------------------------------------------------------------------
 // k_evaluate: every work-list vertex evaluates its candidate moves.
@@ -418,10 +421,9 @@ __device__ __forceinline__ bool connexity_problem_ring(unsigned L, unsigned long
 // k_evaluate_long: the work-list vertices whose rows are longer than kRingW, one thread per vertex, per-slot walk.
 // Launched only for meshes that have such vertices.
 template <int EM, int STRIDE>
-__global__ void __launch_bounds__(kThreads) k_evaluate_long(ReassignArgs A) {
+static __device__ __noinline__ void evaluate_long_list(const ReassignArgs& A, int n_work) {
     constexpr int NL = MetricTraits<EM>::NPAD;
     const int K = A.K;
-    const int n_work = (int)A.ctr->evaluated;
     unsigned n_tests = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
         const int v = A.work[i];
@@ -488,12 +490,13 @@ __global__ void __launch_bounds__(kThreads) k_evaluate_long(ReassignArgs A) {
     }
     warp_count_add(&A.ctr->tests, n_tests);
 }
+template <int EM, int STRIDE>
+__global__ void __launch_bounds__(kThreads) k_evaluate_long(ReassignArgs A) { evaluate_long_list<EM, STRIDE>(A, (int)A.ctr->evaluated); }
 
 template <int EM, int STRIDE>
-__global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) {
+__device__ __forceinline__ void evaluate_list(const ReassignArgs& A, int n_work) {
     constexpr int NL = MetricTraits<EM>::NPAD;   // doubles loaded per row
     const int K = A.K;
-    const int n_work = (int)A.ctr->evaluated;    // written by k_scan of this round
     const int lane = threadIdx.x & 31;
     unsigned n_tests = 0;
     // warp-uniform trip count: the candidate loop below votes across the warp
@@ -586,14 +589,39 @@ __global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) {
     }
     warp_count_add(&A.ctr->tests, n_tests);
 }
+// n_work = the work list length written by the scan of this round
+template <int EM, int STRIDE>
+__global__ void __launch_bounds__(kThreads) k_evaluate(ReassignArgs A) { evaluate_list<EM, STRIDE>(A, (int)A.ctr->evaluated); }
+
+// Bookkeeping every committed move owes the sparse rounds (sparse.cuh): the per-cluster member arrays (swap-remove
+// from the source, append to the destination) and the list of the clusters modified in this round.  Winners of one
+// commit pass touch pairwise disjoint cluster pairs and a cluster is touched at most once per round, so neither
+// structure needs atomics beyond the list cursor.  Called BEFORE the sizes are updated.
+__device__ __forceinline__ void note_move(const ReassignArgs& A, int v, int a, int d) {
+    if (A.mem.memb) {
+        if (a < A.K) {
+            const int p = A.mem.pos[v];
+            const int last = A.mem.memb[A.mem.off[a] + A.csize[a] - 1];
+            A.mem.memb[p] = last;
+            A.mem.pos[last] = p;
+        }
+        const int q = A.mem.off[d] + A.csize[d];
+        if (q < A.mem.off[d + 1]) { A.mem.memb[q] = v; A.mem.pos[v] = q; }
+        else *A.mem.overflow = 1;                              // array full: the driver rebuilds the arrays before they are read
+    }
+    if (A.modlist) {
+        const int s = (int)atomicAdd(A.n_mod, a < A.K ? 2ull : 1ull);
+        A.modlist[s] = d;
+        if (a < A.K) A.modlist[s + 1] = a;
+    }
+}
 
 // UM: metric of the stored sums (all UM::NPAD doubles of a row are updated);
 // EM: metric used to re-evaluate an adopting cluster's energy.
 template <int EM, int UM>
-__global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
+__device__ __forceinline__ void commit_list(const ReassignArgs& A, int n_props) {
     constexpr int NU = MetricTraits<UM>::NPAD;
     const int K = A.K;
-    const int n_props = (int)A.ctr->proposals;   // written by k_scan / k_evaluate of this round
     unsigned n_mods = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
         const int v = A.plist[i];
@@ -603,6 +631,7 @@ __global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
         const int a = A.cid[v];
         bool win = (A.best[d] == key) && (a >= K || A.best[a] == key);
         if (!win) continue;
+        note_move(A, v, a, d);
         double it[NU], s[NU];
         load_row_ro<NU>(A.items + (int64_t)v * NU, it);
         // destination += item
@@ -634,6 +663,9 @@ __global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) {
     }
     warp_count_add(&A.ctr->mods, n_mods);
 }
+// n_props = proposals submitted by the scan / evaluation of this round
+template <int EM, int UM>
+__global__ void __launch_bounds__(kThreads) k_commit(ReassignArgs A) { commit_list<EM, UM>(A, (int)A.ctr->proposals); }
 
 // ---------------------------------------------------------------------------------------------------
 // Bulk rounds (Lloyd criterion) for the phases that the reference ends by "early convergence"
@@ -851,6 +883,7 @@ __global__ void __launch_bounds__(kThreads) k_apply_moves(ReassignArgs A, const 
         const MoveRec m = moves[i];
         const int v = m.v, d = m.d;
         const int a = A.cid[v];
+        note_move(A, v, a, d);
         double it[NU], s[NU];
         load_row_ro<NU>(A.items + (int64_t)v * NU, it);
         load_row<NU>(A.csum + (int64_t)d * NU, s);

@@ -13,6 +13,15 @@ struct RoundCounters {
     unsigned long long pad[3];
 };
 
+// Per-cluster member arrays (sparse.cuh): cluster c owns the slots [off[c], off[c + 1]) of memb, the first csize[c]
+// of them are its vertices; pos[v] is the slot of v.
+struct Members {
+    const int* __restrict__ off;
+    int* memb;
+    int* pos;
+    int* overflow;
+};
+
 struct ReassignArgs {
     int V, K;
     const int* __restrict__ row_ptr;
@@ -47,6 +56,10 @@ struct ReassignArgs {
     int* active_tiles;                  // compact list of active tiles
     unsigned long long* n_active_tiles;
     RoundCounters* ctr;
+    Members mem;                        // memb == null: not maintained
+    int* modlist;                       // clusters modified in this round (written by the commits), or null
+    unsigned long long* n_mod;
+    int* stamp;                         // V: round in which the vertex entered the work list of a sparse round
     int round;
     int force_all;                      // SetAllClustersToModified (:717-722)
     int bulk;                           // bulk round: no stored proposals; the decision is taken inside k_scan
