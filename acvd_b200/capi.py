@@ -29,7 +29,7 @@ class Params(C.Structure):
         ("unconstrained_init", C.c_int32), ("quadrics_level", C.c_int32), ("connexity", C.c_int32),
         ("max_loops", C.c_int32), ("max_convergences", C.c_int32), ("early_stop_div", C.c_int32),
         ("log_energy", C.c_int32), ("rounds_per_sync", C.c_int32), ("sv_threshold", C.c_double),
-        ("bulk_rounds", C.c_int32), ("commit_passes", C.c_int32),
+        ("bulk_rounds", C.c_int32), ("commit_passes", C.c_int32), ("sparse_rounds", C.c_int32),
     ]
 
 
@@ -42,7 +42,8 @@ class Report(C.Structure):
         ("evaluated", C.c_int64), ("ms_device", C.c_double),
         ("kernel_launches", C.c_int64), ("bulk_rounds", C.c_int64),
         ("dense_scan_launches", C.c_int64), ("ms_dense_scan", C.c_double), ("dense_scan_bytes", C.c_int64),
-        ("dense_scan_vertices", C.c_int64), ("bulk_rollbacks", C.c_int64),
+        ("dense_scan_vertices", C.c_int64), ("bulk_rollbacks", C.c_int64), ("sparse_rounds", C.c_int64),
+        ("ms_sparse", C.c_double),
     ]
 
     def asdict(self):
@@ -85,6 +86,7 @@ SYMBOLS = [
     ("acvd_global_energy", C.c_int, [_vp, C.POINTER(_d)]),
     ("acvd_get_energy_log", C.c_int, [_vp, _vp, _i32, C.POINTER(_i32)]),
     ("acvd_representative_points", C.c_int, [_vp, _i32, _vp, _vp, _i32, _d, _vp]),
+    ("acvd_cluster_quadrics", C.c_int, [_vp, _i32, _vp]),
     ("acvd_boundary_flags", C.c_int, [_vp, _vp]),
     ("acvd_cluster_adjacency", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     ("acvd_dual_triangles", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
@@ -296,6 +298,13 @@ class Context:
         rd = np.zeros(q.shape[0], dtype=np.int32)
         self._ck(self.L.acvd_representative_points(self.h, q.shape[0], _p(q), _p(p), max_sv, sv_threshold, _p(rd)))
         return p, rd
+
+    def cluster_quadrics(self, n_clusters=None):
+        """Per-cluster sums of the quadrics of the input faces around every item (ACVD post-process): [n, 9]."""
+        n = self.K if n_clusters is None else int(n_clusters)
+        out = np.zeros((n, 9))
+        self._ck(self.L.acvd_cluster_quadrics(self.h, n, _p(out)))
+        return out
 
     # ---- integer stages
     def boundary_flags(self):

@@ -21,6 +21,7 @@
 #include "metric.cuh"
 #include "reassign.cuh"
 #include "scan_dense.cuh"
+#include "sparse.cuh"
 
 // blocks per SM requested for the scan grid (grid-stride; more blocks than resident ones balance the tail)
 static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("ACVD_SCAN_BPS")) : 8; return v; }
@@ -39,6 +40,7 @@ static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("AC
 constexpr int64_t kReplicatedTailProposals = 4096;
 constexpr int kRoundSlots = 8;            // exact rounds that may be in flight between two host synchronisations
 constexpr int kTailBatch = 4;             // rounds launched back to back in the long tail of the last phases
+constexpr int kSparseChunkAlloc = 512;    // rounds of one sparse launch (kSparseChunk)
 
 static bool trace_on() {
     static int on = -1;
@@ -490,6 +492,11 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
         ACVD_CUDA(cudaMemsetAsync(c->tile_stale.p, 1, n_tiles, c->stream)); c->active_tiles.alloc(n_tiles); c->round_scalars.alloc(2);
         ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
     } c->prop_e.alloc(V);
+    c->best2.alloc(K); c->stamp.alloc(V); c->modlist0.alloc((size_t)K + 64); c->modlist1.alloc((size_t)K + 64);
+    c->sp_nmod.alloc(kSparseChunkAlloc + 2); c->memb_overflow.alloc(1);
+    ACVD_CUDA(cudaMemsetAsync(c->stamp.p, 0, (size_t)V * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->memb_overflow.p, 0, sizeof(int), c->stream));
+    c->members_valid = false; c->modlist_valid = false; c->mod_par = 0;
     ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)V * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->mod_round.p, 0, (size_t)K * sizeof(int), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->anchor.p, 0xff, (size_t)K * sizeof(int), c->stream));
@@ -514,7 +521,7 @@ extern "C" int acvd_set_clustering(acvd_ctx* c, const int32_t* cl) {
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
-    c->stats_valid = false; c->sig_valid = false;
+    c->stats_valid = false; c->sig_valid = false; c->members_valid = false; c->modlist_valid = false;
     ACVD_API_END(c)
 }
 
@@ -541,7 +548,7 @@ extern "C" int acvd_restore_clustering(acvd_ctx* c) {
     ACVD_CUDA(cudaMemcpyAsync(c->cid.p, c->cid_saved.p, (size_t)c->V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
-    c->stats_valid = false;
+    c->stats_valid = false; c->sig_valid = false; c->members_valid = false; c->modlist_valid = false;
     ACVD_API_END(c)
 }
 
@@ -586,7 +593,7 @@ extern "C" int acvd_initial_sampling(acvd_ctx* c) {
     initial_random_sampling(c->V, c->K, rings, w.data(), c->fixed, out);
     ACVD_CUDA(cudaMemcpy(c->cid.p, out.data(), (size_t)c->V * sizeof(int), cudaMemcpyHostToDevice));
     ACVD_CUDA(cudaMemset(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int)));
-    c->stats_valid = false;
+    c->stats_valid = false; c->sig_valid = false; c->members_valid = false; c->modlist_valid = false;
     ACVD_API_END(c)
 }
 
@@ -603,38 +610,60 @@ static bool qem_as_iso(const acvd_ctx* c, int constrained, int qlevel) {
     return c->metric == M_QEM && !c->has_anchor && (!constrained || !qlevel);
 }
 
-static void recompute_statistics(acvd_ctx* c, int constrained, int qlevel, double thr) {
-    TraceScope ts(c, "recompute_statistics");
+// ---- per-cluster member arrays (sparse.cuh): counting build, no sort
+static void members_build(acvd_ctx* c) {
     const int V = c->V, K = c->K;
-    c->sort_k0.alloc(V); c->sort_k1.alloc(V); c->sort_v0.alloc(V); c->sort_v1.alloc(V); c->seg.alloc((size_t)K + 2);
-    ACVD_CUDA(cudaMemcpyAsync(c->sort_k0.p, c->cid.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->sort_v0.p);
+    c->memb_off.alloc((size_t)K + 2); c->memb_cap.alloc((size_t)K + 2); c->memb_pos.alloc(V);
+    ACVD_CUDA(cudaMemsetAsync(c->memb_cap.p, 0, ((size_t)K + 2) * sizeof(int), c->stream));
+    k_members_count<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->memb_cap.p);
+    ACVD_LAUNCH_CHECK();
+    k_members_cap<<<grid_for(K + 1), kThreads, 0, c->stream>>>(K, c->memb_cap.p, c->memb_cap.p);
     ACVD_LAUNCH_CHECK();
     size_t tb = 0;
-    const int end_bit = bits_for((uint64_t)K + 1);
-    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, c->sort_k0.p, c->sort_k1.p, c->sort_v0.p, c->sort_v1.p, V, 0, end_bit, c->stream));
+    ACVD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, c->memb_cap.p, c->memb_off.p, K + 1, c->stream));
     void* t = cub_temp(c, tb);
-    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, c->sort_k0.p, c->sort_k1.p, c->sort_v0.p, c->sort_v1.p, V, 0, end_bit, c->stream));
-    k_segments<<<grid_for(K + 2), kThreads, 0, c->stream>>>(V, K, c->sort_k1.p, c->seg.p);
+    ACVD_CUDA(cub::DeviceScan::ExclusiveSum(t, tb, c->memb_cap.p, c->memb_off.p, K + 1, c->stream));
+    // total slots <= V + K * 16 + V / 2: allocate the bound, no host round trip
+    const size_t slots = (size_t)V + (size_t)V / 2 + 16 * (size_t)K + 64;
+    c->memb.alloc(slots); c->memb_tmp.alloc(slots); c->cc_par.alloc(slots); c->cc_sz.alloc(slots);
+    ACVD_CUDA(cudaMemsetAsync(c->csize.p, 0, (size_t)K * sizeof(int), c->stream));
+    k_members_scatter<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->memb_off.p, c->csize.p, c->memb.p, c->memb_pos.p);
     ACVD_LAUNCH_CHECK();
-    EvalCfg cfg = make_cfg(constrained, qlevel, thr);
-    const int* anchor = c->has_anchor ? c->anchor.p : nullptr;
-    const int blocks = grid_for((int64_t)K * 32);
-#define STATS(MM, EE) k_cluster_stats<MM, EE><<<blocks, kThreads, 0, c->stream>>>(K, c->seg.p, c->sort_v1.p, c->items.p, c->csum.p, \
-                                                                        c->cenergy.p, c->ccentroid.p, c->csize.p, anchor, c->xyz.p, cfg)
+    ACVD_CUDA(cudaMemsetAsync(c->memb_overflow.p, 0, sizeof(int), c->stream));
+    c->members_valid = true;
+}
+
+// one pass over the clusters: sort members [+ connected components / cleaning] [+ statistics]
+static void cluster_pass(acvd_ctx* c, bool do_cc, bool do_stats, int constrained, int qlevel, double thr) {
+    ClusterPassArgs P;
+    P.V = c->V; P.K = c->K; P.off = c->memb_off.p; P.memb = c->memb.p; P.memb_tmp = c->memb_tmp.p; P.pos = c->memb_pos.p;
+    P.cid = c->cid.p; P.csize = c->csize.p; P.row_ptr = c->row_ptr.p; P.col = c->col.p; P.items = c->items.p;
+    P.csum = c->csum.p; P.cenergy = c->cenergy.p; P.ccentroid = c->ccentroid.p;
+    P.anchor = c->has_anchor ? c->anchor.p : nullptr; P.xyz = c->xyz.p;
+    P.cc_par = c->cc_par.p; P.cc_sz = c->cc_sz.p; P.counters = c->scalars.p + 1;
+    P.do_sort = 1; P.do_cc = do_cc ? 1 : 0; P.do_stats = do_stats ? 1 : 0;
+    P.cfg = make_cfg(constrained, qlevel, thr);
+    const int blocks = grid_for((int64_t)c->K * 32);
+#define PASS(MM, EE) k_cluster_pass<MM, EE><<<blocks, kThreads, 0, c->stream>>>(P)
     switch (c->metric) {
-        case M_ISO: STATS(M_ISO, M_ISO); break;
+        case M_ISO: PASS(M_ISO, M_ISO); break;
         case M_QEM:
-            if (qem_as_iso(c, constrained, qlevel)) STATS(M_QEM, M_ISO);   // same formula as the rounds use in this phase
-            else STATS(M_QEM, M_QEM);
+            if (qem_as_iso(c, constrained, qlevel)) PASS(M_QEM, M_ISO);   // same formula as the rounds use in this phase
+            else PASS(M_QEM, M_QEM);
             break;
-        case M_ANISO: STATS(M_ANISO, M_ANISO); break;
-        default: STATS(M_ANISOQ, M_ANISOQ); break;
+        case M_ANISO: PASS(M_ANISO, M_ANISO); break;
+        default: PASS(M_ANISOQ, M_ANISOQ); break;
     }
-#undef STATS
+#undef PASS
     ACVD_LAUNCH_CHECK();
-    c->stats_valid = true;
-    c->stats_constrained = constrained; c->stats_qlevel = qlevel;
+    if (do_stats) { c->stats_valid = true; c->stats_constrained = constrained; c->stats_qlevel = qlevel; }
+}
+
+// ReComputeStatistics (:376-403) + ReComputeClustersSize (:353-373)
+static void recompute_statistics(acvd_ctx* c, int constrained, int qlevel, double thr) {
+    TraceScope ts(c, "recompute_statistics");
+    members_build(c);
+    cluster_pass(c, false, true, constrained, qlevel, thr);
 }
 
 extern "C" int acvd_recompute_statistics(acvd_ctx* c, int constrained, int qlevel) {
@@ -645,42 +674,19 @@ extern "C" int acvd_recompute_statistics(acvd_ctx* c, int constrained, int qleve
     ACVD_API_END(c)
 }
 
-static int clean_clustering(acvd_ctx* c) {
+// CleanClustering (:406-549) inside the cluster pass.  With `with_stats` the same pass also leaves fresh statistics,
+// valid when nothing had to be cleaned (n_reset == 0: the caller checks stats_valid).
+static int clean_clustering(acvd_ctx* c, bool with_stats = false, int constrained = 1, int qlevel = 3, double thr = 0) {
     TraceScope ts(c, "clean_clustering");
-    const int V = c->V, K = c->K;
-    c->label.alloc(V); c->comp_size.alloc(V); c->n_comp.alloc(K); c->winner.alloc(K); c->n_roots.alloc(K);
-    ACVD_CUDA(cudaMemsetAsync(c->n_roots.p, 0, (size_t)K * sizeof(int), c->stream));
-    if (c->ell_w == 6)
-        k_cc_init<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
-    else
-        k_cc_init<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
-    ACVD_LAUNCH_CHECK();
-    // flatten the initial chains first: the hooking pass then finds every representative in one or two hops
-    k_cc_flatten<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->n_roots.p, c->label.p);
-    ACVD_LAUNCH_CHECK();
-    if (c->ell_w == 6)
-        k_cc_hook<6><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
-    else
-        k_cc_hook<8><<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->vpad, c->ell.p, c->row_ptr.p, c->col.p, c->cid.p, c->label.p, c->n_roots.p);
-    ACVD_LAUNCH_CHECK();
-    k_cc_flatten<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->n_roots.p, c->label.p);
-    ACVD_LAUNCH_CHECK();
-    ACVD_CUDA(cudaMemsetAsync(c->comp_size.p, 0, (size_t)V * sizeof(int), c->stream));
-    ACVD_CUDA(cudaMemsetAsync(c->n_comp.p, 0, (size_t)K * sizeof(int), c->stream));
-    ACVD_CUDA(cudaMemsetAsync(c->winner.p, 0, (size_t)K * sizeof(unsigned long long), c->stream));
+    if (!c->members_valid) members_build(c);
     ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
-    const int* anchor = c->has_anchor ? c->anchor.p : nullptr;
-    k_cc_sizes<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, anchor, c->n_roots.p);
-    k_cc_winner<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->comp_size.p, c->n_comp.p, c->winner.p, c->n_roots.p);
-    k_count_ge2<<<grid_for(K), kThreads, 0, c->stream>>>(K, c->n_comp.p, c->scalars.p + 1);
-    k_cc_apply<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->label.p, c->n_comp.p, c->winner.p, c->scalars.p + 2);
-    c->launches += 3;
-    ACVD_LAUNCH_CHECK();
+    cluster_pass(c, true, with_stats, constrained, qlevel, thr);
     ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
-    c->stats_valid = false;
-    if (trace_on()) fprintf(stderr, "[acvd trace]   disconnected %d, reset %d\n", (int)c->h_scalars[1], (int)c->h_scalars[2]);
-    return (int)c->h_scalars[1];
+    const int disc = (int)c->h_scalars[1], n_reset = (int)c->h_scalars[2];
+    if (n_reset > 0) { c->stats_valid = false; c->members_valid = false; c->sig_valid = false; }
+    if (trace_on()) fprintf(stderr, "[acvd trace]   disconnected %d, reset %d\n", disc, n_reset);
+    return disc;
 }
 
 // FillHolesInClustering, order-exact (fill.cuh).  `connexity` = the engine's ConnexityConstraint at the time of the call.
@@ -696,7 +702,7 @@ static void fill_holes(acvd_ctx* c, int connexity) {
     const int n = (int)c->h_scalars[0];
     if (n == 0) return;
     if (trace_on()) fprintf(stderr, "[acvd trace]   fill: %d NULL vertices, connexity %d\n", n, connexity);
-    c->stats_valid = false;
+    c->stats_valid = false; c->members_valid = false; c->sig_valid = false;
     FillMesh M{V, K, c->row_ptr.p, c->col.p, c->vf_ptr.p, c->vf_keys.p, c->tri.p};
     size_t tb = 0;
     if (connexity && n <= kFillSequentialCap) {
@@ -785,7 +791,7 @@ extern "C" int acvd_fill_holes(acvd_ctx* c, int connexity) {
 
 // ---------------------------------------------------------------------------------------------
 // reassignment rounds
-struct RoundResult { unsigned long long proposals, mods, tests, evaluated, boundary, active_tiles; float ms_scan, ms_eval, ms_commit; };
+struct RoundResult { unsigned long long proposals, mods, tests, evaluated, boundary, active_tiles, members; float ms_scan, ms_eval, ms_commit; bool overflow, sparse; };
 
 static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all) {
     ReassignArgs A;
@@ -809,6 +815,9 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.bulk_stage = 0; A.bulk_count_leave = 0; A.bulk_cen = c->bulk_cen.p; A.bulk_leave = c->leave_cnt.p;
     A.item_stride = payload_npad(c->metric);
     A.all_tiles = 0; A.tile_begin = 0; A.tile_end = (c->V + 31) / 32; A.sig_mode = 0; A.track_stale = 1;
+    if (c->members_valid) A.mem = Members{c->memb_off.p, c->memb.p, c->memb_pos.p, c->memb_overflow.p};
+    else A.mem = Members{nullptr, nullptr, nullptr, nullptr};
+    A.modlist = nullptr; A.n_mod = nullptr; A.stamp = c->stamp.p;
     return A;
 }
 
@@ -824,8 +833,21 @@ static void launch_scan_bulk_dense(acvd_ctx* c, const ReassignArgs& A) {
     const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
     k_scan_bulk_dense<W, S, MINB><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
 }
-// (stages, blocks per SM) variants kept for the kernel micro-benchmark (acvd_bench_kernel); variant 0 is the product default
-static int g_dense_variant = getenv("ACVD_DENSE_VARIANT") ? atoi(getenv("ACVD_DENSE_VARIANT")) : 0;
+template <int W, int S, int MINB>
+static void launch_scan_bulk_dense2(acvd_ctx* c, const ReassignArgs& A) {
+    static bool configured[64] = {};
+    if (c->device >= 64 || !configured[c->device]) {
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense2<W, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W, S)));
+        if (c->device < 64) configured[c->device] = true;
+    }
+    const int n_tiles = A.tile_end - A.tile_begin;
+    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
+    k_scan_bulk_dense2<W, S, MINB><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
+}
+// (stages, blocks per SM) variants kept for the kernel micro-benchmark (acvd_bench_kernel); variants >= 10 are the
+// second generation of the kernel (static tile assignment, two tiles in flight per warp)
+constexpr int kDenseDefaultVariant = 0;
+static int dense_variant() { const char* e = getenv("ACVD_DENSE_VARIANT"); return e ? atoi(e) : kDenseDefaultVariant; }   // read per launch (tests switch it)
 template <int W>
 static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, int variant) {
     switch (variant) {
@@ -835,6 +857,12 @@ static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, i
         case 4: launch_scan_bulk_dense<W, 3, 5>(c, A); break;
         case 5: launch_scan_bulk_dense<W, 2, 6>(c, A); break;
         case 6: launch_scan_bulk_dense<W, 3, 3>(c, A); break;
+        case 10: launch_scan_bulk_dense2<W, 3, 4>(c, A); break;
+        case 11: launch_scan_bulk_dense2<W, 3, 3>(c, A); break;
+        case 12: launch_scan_bulk_dense2<W, 2, 4>(c, A); break;
+        case 13: launch_scan_bulk_dense2<W, 4, 3>(c, A); break;
+        case 14: launch_scan_bulk_dense2<W, 2, 5>(c, A); break;
+        case 15: launch_scan_bulk_dense2<W, 4, 4>(c, A); break;
         default: launch_scan_bulk_dense<W, 3, 4>(c, A); break;
     }
 }
@@ -843,7 +871,7 @@ static void launch_scan(acvd_ctx* c, const ReassignArgs& A, int grid) {
     c->last_dense_kernel = false;
     if (A.bulk && A.all_tiles && A.sig_mode == 1 && !getenv("ACVD_NO_DENSE_SCAN")) {
         c->last_dense_kernel = true;
-        if (c->ell_w == 6) launch_scan_bulk_dense_variant<6>(c, A, g_dense_variant); else launch_scan_bulk_dense_variant<8>(c, A, g_dense_variant);
+        if (c->ell_w == 6) launch_scan_bulk_dense_variant<6>(c, A, dense_variant()); else launch_scan_bulk_dense_variant<8>(c, A, dense_variant());
         return;
     }
     if (A.bulk) {
@@ -907,6 +935,12 @@ static void launch_round(acvd_ctx* c, const EvalCfg& cfg, int connexity, int for
     // counters of the round are opened by k_modbits
     c->plist_cur ^= 1;
     ReassignArgs A = make_args(c, cfg, connexity, force_all);
+    // the clusters this round modifies, for a sparse launch that may follow (sparse.cuh)
+    c->mod_par ^= 1;
+    A.modlist = c->mod_par ? c->modlist1.p : c->modlist0.p;
+    A.n_mod = c->sp_nmod.p;
+    ACVD_CUDA(cudaMemsetAsync(c->sp_nmod.p, 0, sizeof(unsigned long long), c->stream));
+    c->modlist_valid = true;
     ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
     const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 8, gc = kNumSMs * 4;
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, c->ctr.p,
@@ -1001,6 +1035,7 @@ static double bulk_energy(acvd_ctx* c) {
 static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     EvalCfg cfg = make_cfg(0, 0, 0);
     c->plist_cur = 0;
+    c->members_valid = false; c->modlist_valid = false;     // bulk commits do not maintain the member arrays
     ReassignArgs A = make_args(c, cfg, 0, force_all);
     A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 1;
     if (stage == 1) A.moved_mask = c->moved_mask.p;      // stage 1 can be undone (energy guard)
@@ -1060,11 +1095,116 @@ static RoundResult finish_round(acvd_ctx* c, int slot = 0, bool last_of_batch = 
     RoundResult r;
     r.proposals = h->proposals; r.mods = h->mods; r.tests = h->tests;
     r.evaluated = h->evaluated + h->pad[0]; r.boundary = h->boundary; r.active_tiles = c->h_scalars[8 + slot];
+    r.members = 0; r.overflow = h->pad[2] != 0; r.sparse = false;
+    if (r.overflow) c->members_valid = false;
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, ev[0], ev[3]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, ev[3], ev[1]));
     ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, ev[1], ev[2]));
     if (last_of_batch) update_density(c, r);
     return r;
+}
+
+// ---- sparse rounds (sparse.cuh): one cooperative launch runs up to `max_rounds` rounds; returns the rounds executed
+constexpr int kSparseChunk = 512;
+static bool sparse_enabled() { static int v = getenv("ACVD_NO_SPARSE") ? 0 : 1; return v == 1; }
+
+template <int EM, int STRIDE, int UM>
+static void launch_sparse(acvd_ctx* c, ReassignArgs& A, SparseCtl& S) {
+    static int blocks_per_sm[64] = {};
+    int& bps = blocks_per_sm[c->device < 64 ? c->device : 0];
+    if (bps == 0) {
+        ACVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sparse_rounds<EM, STRIDE, UM>, kThreads, 0));
+        if (bps < 1) throw std::runtime_error("k_sparse_rounds does not fit an SM");
+        if (bps > 4) bps = 4;
+    }
+    int n_sm = kNumSMs;
+    ACVD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+    void* args[] = {&A, &S};
+    ACVD_CUDA(cudaLaunchCooperativeKernel((void*)k_sparse_rounds<EM, STRIDE, UM>, dim3(n_sm * bps), dim3(kThreads), args, 0, c->stream));
+}
+
+static int run_sparse_rounds(acvd_ctx* c, const EvalCfg& cfg, int connexity, bool as_iso, int max_rounds, long long stop_props,
+                             int64_t n_prev_props, std::vector<RoundResult>& out) {
+    const int K = c->K;
+    max_rounds = std::max(1, std::min(max_rounds, kSparseChunk));
+    c->sp_rc.alloc(kSparseChunk); c->sp_resub.alloc((size_t)kSparseChunk * kMaxPasses); c->sp_ts.alloc((size_t)kSparseChunk * 4);
+    c->sp_done.alloc(4);
+    if (!c->h_sp_rc) {
+        ACVD_CUDA(cudaMallocHost(&c->h_sp_rc, kSparseChunk * sizeof(RoundCounters)));
+        ACVD_CUDA(cudaMallocHost(&c->h_sp_ts, (size_t)kSparseChunk * 4 * sizeof(unsigned long long) + 64));
+    }
+    ReassignArgs A = make_args(c, cfg, connexity, 0);
+    A.track_stale = 0;                    // tile signatures are not maintained by the sparse rounds
+    c->sig_valid = false;
+    SparseCtl S;
+    S.rc = c->sp_rc.p; S.n_mod = c->sp_nmod.p; S.resub = c->sp_resub.p; S.ts = c->sp_ts.p;
+    S.modlist0 = c->mod_par ? c->modlist1.p : c->modlist0.p;        // written by the previous round
+    S.modlist1 = c->mod_par ? c->modlist0.p : c->modlist1.p;
+    S.plist1 = c->plist_cur ? c->plist_b.p : c->plist.p;            // proposals of the previous round
+    S.plist0 = c->plist_cur ? c->plist.p : c->plist_b.p;
+    S.best0 = c->best.p; S.best1 = c->best2.p;
+    S.n_prev_props = (unsigned long long)std::max<int64_t>(0, n_prev_props);
+    S.par0 = 0; S.max_rounds = max_rounds; S.passes = std::min(c->commit_passes, kMaxPasses);
+    S.has_long_rows = c->max_deg > kRingW ? 1 : 0;
+    S.stop_props = stop_props;
+    S.done = c->sp_done.p;
+    ACVD_CUDA(cudaMemsetAsync(c->sp_rc.p, 0, (size_t)max_rounds * sizeof(RoundCounters), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->sp_nmod.p + 1, 0, (size_t)max_rounds * sizeof(unsigned long long), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->sp_resub.p, 0, (size_t)max_rounds * kMaxPasses * sizeof(unsigned long long), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->sp_done.p, 0, 4 * sizeof(int), c->stream));
+    ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    switch (c->metric) {
+        case M_ISO: launch_sparse<M_ISO, 4, M_ISO>(c, A, S); break;
+        case M_QEM:
+            if (as_iso) launch_sparse<M_ISO, 14, M_QEM>(c, A, S);
+            else launch_sparse<M_QEM, 14, M_QEM>(c, A, S);
+            break;
+        case M_ANISO: launch_sparse<M_ANISO, 14, M_ANISO>(c, A, S); break;
+        default: launch_sparse<M_ANISOQ, 22, M_ANISOQ>(c, A, S); break;
+    }
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    int n_done = 0;
+    ACVD_CUDA(cudaMemcpyAsync(c->h_sp_rc, c->sp_rc.p, (size_t)max_rounds * sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_sp_ts, c->sp_ts.p, (size_t)max_rounds * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_sp_ts + (size_t)kSparseChunk * 4, c->sp_done.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    n_done = *reinterpret_cast<int*>(c->h_sp_ts + (size_t)kSparseChunk * 4);
+    if (n_done < 1 || n_done > max_rounds) throw std::runtime_error("sparse rounds: bad round count from the device");
+    float ms_total = 0;
+    ACVD_CUDA(cudaEventElapsedTime(&ms_total, c->ev[0], c->ev[1]));
+    // the list of the clusters the last round modified becomes the input of the next launch
+    if (n_done & 1) { c->mod_par ^= 1; c->plist_cur ^= 1; }
+    ACVD_CUDA(cudaMemcpyAsync(c->sp_nmod.p, c->sp_nmod.p + n_done, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    c->round += n_done;
+    out.clear();
+    double ns_sum = 0;
+    for (int i = 0; i < n_done; i++) {
+        const RoundCounters& h = c->h_sp_rc[i];
+        const unsigned long long* ts = c->h_sp_ts + 4 * i;
+        RoundResult r;
+        r.proposals = h.proposals; r.mods = h.mods; r.tests = h.tests; r.evaluated = h.evaluated; r.boundary = h.evaluated;
+        r.active_tiles = 0; r.members = h.pad[1]; r.overflow = h.pad[2] != 0; r.sparse = true;
+        const unsigned long long t_begin = i > 0 ? c->h_sp_ts[4 * (i - 1) + 2] : ts[0];
+        r.ms_scan = (float)((double)(ts[0] - t_begin) * 1e-6);
+        r.ms_eval = (float)((double)(ts[1] - ts[0]) * 1e-6);
+        r.ms_commit = (float)((double)(ts[2] - ts[1]) * 1e-6);
+        ns_sum += (double)(ts[2] - t_begin);
+        out.push_back(r);
+    }
+    if (getenv("ACVD_SPARSE_TRACE")) {
+        fprintf(stderr, "[acvd sparse] launch of %d rounds: %.1f us by events, %.1f us between stamps\n", n_done, 1e3 * ms_total, ns_sum * 1e-3);
+        for (int i = 0; i < n_done; i++)
+            fprintf(stderr, "[acvd sparse]   round %4d members %8llu evaluated %8llu tests %8llu proposals %7llu mods %6llu  enum %.1f eval %.1f commit %.1f us\n",
+                    c->round - n_done + i, out[i].members, out[i].evaluated, out[i].tests, out[i].proposals, out[i].mods,
+                    1e3 * out[i].ms_scan, 1e3 * out[i].ms_eval, 1e3 * out[i].ms_commit);
+    }
+    // the first enumerate is not bracketed by device time stamps: give it what the events saw beyond the stamps
+    if (!out.empty()) out[0].ms_scan += std::max(0.0f, ms_total - (float)(ns_sum * 1e-6));
+    if (out.back().overflow) c->members_valid = false;
+    c->last_all_tiles = 0; c->last_bulk = 0; c->last_dense_kernel = false; c->dense_next = false;
+    c->launches += 1;
+    return n_done;
 }
 
 #include "dist.cuh"
@@ -1090,6 +1230,11 @@ static int64_t scan_bytes(const acvd_ctx* c, const RoundResult& r) {
     const int64_t n_tiles = ((int64_t)c->V + 31) / 32;
     const double deg = c->V ? (double)c->nnz / c->V : 0.0;
     return 33 * n_tiles + (int64_t)r.active_tiles * (4 + 32 + (int64_t)(32.0 * (8.0 + 8.0 * deg))) + 4 * (int64_t)r.evaluated;
+}
+// sparse round: per visited member its list entry 4 + row_ptr 8 + deg * (col 4 + cid 4); per work-list entry stamp 4 + entry 4
+static int64_t sparse_scan_bytes(const acvd_ctx* c, const RoundResult& r) {
+    const double deg = c->V ? (double)c->nnz / c->V : 0.0;
+    return (int64_t)((double)r.members * (12.0 + 8.0 * deg)) + 8 * (int64_t)r.evaluated;
 }
 static int64_t eval_bytes(const acvd_ctx* c, const RoundResult& r, bool as_iso) {
     const int64_t nl = 8 * (int64_t)(as_iso ? 4 : payload_npad(c->metric));
@@ -1176,7 +1321,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     int64_t loops = 0;
     const int bulk_cap = p.bulk_rounds < 0 ? 0 : (p.bulk_rounds == 0 ? 1000 : p.bulk_rounds);
     const int env_passes = getenv("ACVD_COMMIT_PASSES") ? std::max(1, atoi(getenv("ACVD_COMMIT_PASSES"))) : 0;
-    c->commit_passes = p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : 2);   // one default for every world size: N GPUs give the 1-GPU clustering
+    c->commit_passes = std::min(kMaxPasses, p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : 2));   // one default for every world size: N GPUs give the 1-GPU clustering
     while (true) {
         EvalCfg cfg = make_cfg(constrained, qlevel, thr);
         const bool as_iso = qem_as_iso(c, constrained, qlevel);
@@ -1243,44 +1388,62 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         // the same state, so the replicas stay identical without any communication.  The first such round
         // re-evaluates every boundary vertex, because stored proposals are only known to the rank that owns them.
         RoundResult r;
+        memset(&r, 0, sizeof r);
         if (force_all) c->replicated_tail = false;
+        auto account = [&](const RoundResult& q) {
+            loops++;
+            R.rounds++; R.tests += (int64_t)q.tests; R.modifications += (int64_t)q.mods; R.proposals += (int64_t)q.proposals;
+            R.ms_scan += q.ms_scan; R.ms_evaluate += q.ms_eval; R.ms_commit += q.ms_commit;
+            R.round_launches++; R.evaluate_bytes += eval_bytes(c, q, as_iso); R.evaluated += (int64_t)q.evaluated;
+            if (q.sparse) {
+                R.sparse_rounds++; R.ms_sparse += q.ms_scan + q.ms_eval + q.ms_commit;
+                R.scan_bytes += sparse_scan_bytes(c, q);
+            } else R.scan_bytes += scan_bytes(c, q);
+            if (p.log_energy) c->energy_log.push_back(global_energy(c));
+            if (trace_on())
+                fprintf(stderr, "[acvd trace] %s %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
+                        q.sparse ? "sprnd" : "round", (long long)loops, nconv, q.active_tiles, q.boundary, q.evaluated, q.tests, q.proposals, q.mods,
+                        1e3 * q.ms_scan, 1e3 * q.ms_eval, 1e3 * q.ms_commit);
+        };
+        // Sparse rounds (sparse.cuh): after the opening round of a phase the rounds run inside one persistent cooperative
+        // kernel that enumerates the dirty vertices from the member arrays of the modified clusters and decides
+        // convergence on the device.  Across GPUs they are used once the phase is in its replicated tail.
+        const bool sparse_ok = sparse_enabled() && p.sparse_rounds >= 0 && !force_all && !reeval_all && c->modlist_valid && last_proposals >= 0 &&
+                               (c->world == 1 || c->replicated_tail);
+        if (sparse_ok && !c->members_valid) members_build(c);       // an append overflowed a member array: rebuild (no sort needed)
         // In the long tail of the last phases (connexity on: the phase can only end with a round without moves) a few
-        // rounds are launched back to back and their counters read together: a round after the one that made no move
-        // finds no modified cluster and changes nothing, so the result is the one of round-by-round polling, with a
-        // quarter of the host synchronisations.
+        // rounds of the tile-filter path are launched back to back and their counters read together (ACVD_NO_SPARSE=1).
         int batch = 1;
-        if ((c->world == 1 || c->replicated_tail) && nconv >= 2 && !force_all && !reeval_all && !p.log_energy && !trace_on() &&
+        if (!sparse_ok && (c->world == 1 || c->replicated_tail) && nconv >= 2 && !force_all && !reeval_all && !p.log_energy && !trace_on() &&
             last_proposals >= 0 && !c->last_all_tiles)    // sparse rounds only: a dense round re-plans the scan mode after every round
             batch = (int)std::min<int64_t>(p.rounds_per_sync > 0 ? std::min(p.rounds_per_sync, kRoundSlots) : kTailBatch,
                                            std::max<int64_t>(1, p.max_loops - loops));
-        if (c->world > 1 && !c->replicated_tail) {
+        if (sparse_ok) {
+            const bool per_round = p.log_energy || trace_on();     // the host wants to look at every round
+            const int64_t budget = std::max<int64_t>(1, p.max_loops - loops + 1);
+            const long long stop_props = nconv <= 1 ? (long long)(early_items / p.early_stop_div) : -1;
+            std::vector<RoundResult> rr;
+            const int n = run_sparse_rounds(c, cfg, connexity, as_iso, per_round ? 1 : (int)std::min<int64_t>(budget, kSparseChunk),
+                                            stop_props, last_proposals, rr);
+            for (int j = 0; j + 1 < n; j++) account(rr[j]);
+            r = rr[n - 1];
+        } else if (c->world > 1 && !c->replicated_tail) {
             r = run_round_dist(c, cfg, connexity, force_all, as_iso);
+            c->modlist_valid = false;
             if ((int64_t)r.proposals <= kReplicatedTailProposals && r.mods > 0) { c->replicated_tail = true; reeval_all = true; }
         } else {
             for (int j = 0; j < batch; j++) launch_round(c, cfg, connexity, (j == 0 && (force_all || reeval_all)) ? 1 : 0, as_iso, j);
+            if (batch > 1) c->modlist_valid = false;      // the list holds the last round of the batch only if all of them ran to the end
             for (int j = 0; j < batch; j++) {
                 r = finish_round(c, j, j == batch - 1);
                 if (j == batch - 1 || r.mods == 0) break;
-                // an intermediate round of the batch: account for it like any other round
-                loops++;
-                R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;
-                R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;
-                R.round_launches++; R.scan_bytes += scan_bytes(c, r); R.evaluate_bytes += eval_bytes(c, r, as_iso);
-                R.evaluated += (int64_t)r.evaluated;
+                account(r);   // an intermediate round of the batch
             }
             reeval_all = false;
         }
         last_proposals = (int64_t)r.proposals;
         force_all = 0;
-        loops++;
-        R.rounds++; R.tests += (int64_t)r.tests; R.modifications += (int64_t)r.mods; R.proposals += (int64_t)r.proposals;
-        R.ms_scan += r.ms_scan; R.ms_evaluate += r.ms_eval; R.ms_commit += r.ms_commit;
-        R.round_launches++; R.scan_bytes += scan_bytes(c, r); R.evaluate_bytes += eval_bytes(c, r, as_iso);
-        R.evaluated += (int64_t)r.evaluated;
-        if (p.log_energy) c->energy_log.push_back(global_energy(c));
-        if (trace_on())
-            fprintf(stderr, "[acvd trace] round %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
-                    (long long)loops, nconv, r.active_tiles, r.boundary, r.evaluated, r.tests, r.proposals, r.mods, 1e3 * r.ms_scan, 1e3 * r.ms_eval, 1e3 * r.ms_commit);
+        account(r);
         const int64_t mods = (int64_t)r.mods;
         // convergence event (:773-776); a round commits a conflict-free subset, so the analogue of the
         // reference's "modifications in one sweep" is the number of live improving proposals
@@ -1292,11 +1455,13 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         nconv++;
         R.convergences++;
         int disc = 0;
-        timed_clean([&] { disc = clean_clustering(c); fill_holes(c, connexity); });
+        // one pass over the clusters checks connectivity AND leaves fresh statistics (valid unless something was cleaned / filled)
+        timed_clean([&] { disc = clean_clustering(c, true, constrained, qlevel, thr); fill_holes(c, connexity); });
         R.disconnected = disc;
         const bool done = (disc == 0 && mods == 0) || loops >= p.max_loops || nconv >= p.max_convergences;
         // the reference leaves the incremental sums in place on exit; we always export fresh statistics
-        timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
+        if (!c->stats_valid || c->stats_constrained != constrained || c->stats_qlevel != qlevel)
+            timed_clean([&] { recompute_statistics(c, constrained, qlevel, thr); });
         if (done) break;
         force_all = 1;
     }
@@ -1361,6 +1526,23 @@ extern "C" int acvd_representative_points(acvd_ctx* c, int32_t n, const double* 
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaMemcpyAsync(P3, p.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (rank_def) ACVD_CUDA(cudaMemcpyAsync(rank_def, rd.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+// ACVD's quadric post-process, accumulation part (ACVD.cxx:237-262)
+extern "C" int acvd_cluster_quadrics(acvd_ctx* c, int32_t n_clusters, double* Q9) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !Q9 || n_clusters < 0 || n_clusters > c->K) throw std::runtime_error("acvd_cluster_quadrics: bad arguments");
+    if (n_clusters == 0) return ACVD_OK;
+    members_build(c);
+    cluster_pass(c, false, false, 1, 3, 0);          // sort only: the summation order is the item order
+    DevBuf<double> d_q;
+    d_q.alloc(9 * (size_t)n_clusters);
+    k_cluster_quadrics<<<grid_for((int64_t)n_clusters * 32), kThreads, 0, c->stream>>>(n_clusters, c->memb_off.p, c->memb.p, c->csize.p, c->vf_ptr.p,
+                                                                                       c->vf_keys.p, c->xyz.p, c->tri.p, d_q.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(Q9, d_q.p, 9 * (size_t)n_clusters * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     ACVD_API_END(c)
 }

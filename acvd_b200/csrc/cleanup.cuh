@@ -1,9 +1,6 @@
-// Per-cluster statistic accumulation, cluster cleaning (connected components), hole filling, and the
-// integer stages that follow the hot path.
+// Small helpers and the integer stages that follow the hot path.
+// (Statistic accumulation and CleanClustering live in sparse.cuh: k_cluster_pass; FillHoles in fill.cuh.)
 //
-//   ReComputeStatistics / ReComputeClustersSize  reference Common/vtkUniformClustering.h:353-403
-//   CleanClustering                              :406-549
-//   FillHolesInClustering                        :552-633
 //   boundary detection / cluster adjacency / dual triangles  DiscreteRemeshing/vtkDiscreteRemeshing.h:1003-1133
 #pragma once
 #include "metric.cuh"
@@ -15,208 +12,6 @@ __global__ void k_fill(int n, int value, int* out) {
 }
 __global__ void k_iota(int n, int* out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
-}
-
-// seg[c] = first index i with sorted_keys[i] >= c, for c in [0, K+1]; seg[K+1] = V
-__global__ void k_segments(int V, int K, const int* __restrict__ sorted_keys, int* seg) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= K + 1; c += gridDim.x * blockDim.x) {
-        int lo = 0, hi = V;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted_keys[mid] < c) lo = mid + 1; else hi = mid; }
-        seg[c] = (c == K + 1) ? V : lo;
-    }
-}
-
-// One warp per cluster: lanes stride over the cluster's items (sorted by vertex id, so the summation
-// order is fixed), each payload component is reduced with warp shuffles; lane 0 stores sums, size,
-// representative point and energy.  Deterministic.  M: metric of the stored rows; EM: metric whose
-// energy formula is evaluated (QEM's unconstrained phase uses the isotropic one).
-template <int M, int EM>
-__global__ void __launch_bounds__(kThreads) k_cluster_stats(int K, const int* __restrict__ seg, const int* __restrict__ sorted_v,
-                                                            const double* __restrict__ items, double* csum, double* cenergy,
-                                                            double* ccentroid, int* csize, const int* __restrict__ anchor,
-                                                            const float* __restrict__ xyz, EvalCfg cfg) {
-    constexpr int NPAD = MetricTraits<M>::NPAD;
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    for (int c = blockIdx.x * warps_per_block + (threadIdx.x >> 5); c < K; c += gridDim.x * warps_per_block) {
-        const int b = seg[c], e = seg[c + 1];
-        double acc[NPAD];
-#pragma unroll
-        for (int k = 0; k < NPAD; k++) acc[k] = 0.0;
-        for (int i = b + lane; i < e; i += 32) {
-            double it[NPAD];
-            load_row_ro<NPAD>(items + (int64_t)sorted_v[i] * NPAD, it);
-#pragma unroll
-            for (int k = 0; k < NPAD; k++) acc[k] += it[k];
-        }
-#pragma unroll
-        for (int k = 0; k < NPAD; k++) acc[k] = warp_sum(acc[k]);
-        if (lane == 0) {
-            store_row<NPAD>(csum + (int64_t)c * NPAD, acc);
-            csize[c] = e - b;
-            double cen[3], apt[3];
-            const double* ap = nullptr;
-            if (EM == M_QEM && anchor && anchor[c] >= 0) {
-                int av = anchor[c];
-                apt[0] = xyz[3 * av]; apt[1] = xyz[3 * av + 1]; apt[2] = xyz[3 * av + 2];
-                ap = apt;
-            }
-            cenergy[c] = cluster_energy<EM>(acc, cfg, cen, ap);
-            ccentroid[3 * c] = cen[0]; ccentroid[3 * c + 1] = cen[1]; ccentroid[3 * c + 2] = cen[2];
-        }
-    }
-}
-
-// ---------------- connected components of every cluster (label = min vertex id of the component) ----------------
-// Connected components of every cluster by hooking (union-find on the GPU): label[] is a parent array
-// initialised to the identity; every same-cluster edge (u < v) joins the two trees by atomically hooking
-// the larger root under the smaller one, so a component's root is its minimum vertex id -- which is also the
-// vertex at which the reference's index-ordered BFS discovers the component (:428-437).  One pass over the
-// edges (k_cc_hook) between two flattening passes (k_cc_flatten), and only for the clusters whose atomic-free
-// initial forest (k_cc_init) has more than one root.
-__device__ __forceinline__ int cc_find(const int* label, int x) {
-    int p = __ldcg(label + x);
-    while (p != x) { x = p; p = __ldcg(label + x); }
-    return x;
-}
-// find with path halving; the shortcut is written with atomicMin so parents only ever decrease
-__device__ __forceinline__ int cc_find_compress(int* label, int x) {
-    while (true) {
-        const int p = __ldcg(label + x);
-        if (p == x) return x;
-        const int gp = __ldcg(label + p);
-        if (gp == p) return p;
-        atomicMin(label + x, gp);
-        x = gp;
-    }
-}
-
-// joins the trees rooted at (or above) ru and rv; returns the smaller representative reached.  A failed CAS hands
-// back the parent somebody else installed, which is closer to the root: the walk continues from there (ECL-CC).
-__device__ __forceinline__ int cc_hook_roots(int* label, int ru, int rv) {
-    while (ru != rv) {
-        if (rv < ru) {
-            const int ret = atomicCAS(label + ru, ru, rv);
-            if (ret == ru) return rv;
-            ru = ret;
-        } else {
-            const int ret = atomicCAS(label + rv, rv, ru);
-            if (ret == rv) return ru;
-            rv = ret;
-        }
-    }
-    return rv;
-}
-
-// Initial forest without atomics (the first step of ECL-CC): every vertex points at its smallest same-cluster
-// neighbour with a smaller id, or at itself.  parent <= self everywhere and every link is a real same-cluster edge,
-// so the hooking pass that follows only has to join the few trees this leaves per cluster; n_roots[c] counts them.
-template <int W>
-__global__ void __launch_bounds__(kThreads) k_cc_init(int V, int K, int64_t vpad, const int* __restrict__ ell,
-                                                      const int* __restrict__ row_ptr, const int* __restrict__ col,
-                                                      const int* __restrict__ cid, int* label, int* n_roots) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-        const int c = cid[v];
-        int best = v;
-        if (c < K) {
-            int nb[W];
-#pragma unroll
-            for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);
-            const bool overflow = nb[W - 1] == -2;
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                const int u = nb[k];
-                if (u >= 0 && u < best && cid[u] == c) best = u;
-            }
-            if (overflow)
-                for (int e = row_ptr[v] + W - 1; e < row_ptr[v + 1]; e++) {
-                    const int u = col[e];
-                    if (u < best && cid[u] == c) best = u;
-                }
-        }
-        label[v] = best;
-        // a cluster whose initial forest has a single root is connected (one tree spans it): only the clusters with
-        // several roots go through the hooking and the component bookkeeping
-        if (c < K && best == v) atomicAdd(n_roots + c, 1);
-    }
-}
-
-template <int W>
-__global__ void __launch_bounds__(kThreads) k_cc_hook(int V, int K, int64_t vpad, const int* __restrict__ ell,
-                                                      const int* __restrict__ row_ptr, const int* __restrict__ col,
-                                                      const int* __restrict__ cid, int* label, const int* __restrict__ n_roots) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-        const int c = cid[v];
-        if (c >= K || n_roots[c] <= 1) continue;
-        int nb[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) nb[k] = __ldg(ell + (int64_t)k * vpad + v);
-        const bool overflow = nb[W - 1] == -2;
-        int rv = cc_find_compress(label, v);          // own representative: found once, updated by every hook
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-            const int u = nb[k];
-            if (u >= 0 && u < v && cid[u] == c) rv = cc_hook_roots(label, cc_find_compress(label, u), rv);
-        }
-        if (overflow)
-            for (int e = row_ptr[v] + W - 1; e < row_ptr[v + 1]; e++) {
-                const int u = col[e];
-                if (u < v && cid[u] == c) rv = cc_hook_roots(label, cc_find_compress(label, u), rv);
-            }
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) k_cc_flatten(int V, int K, const int* __restrict__ cid, const int* __restrict__ n_roots, int* label) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-        const int c = cid[v];
-        if (c >= K || n_roots[c] <= 1) continue;
-        label[v] = cc_find(label, v);
-    }
-}
-
-__global__ void k_cc_sizes(int V, int K, const int* __restrict__ cid, const int* __restrict__ label, int* comp_size,
-                           const int* __restrict__ anchor, const int* __restrict__ n_roots) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-        int c = cid[v];
-        if (c >= K || n_roots[c] <= 1) continue;
-        // an anchored item weighs 1e9 so that its component always wins (:440-447)
-        int w = (anchor && anchor[c] == v) ? 1000000000 : 1;
-        atomicAdd(&comp_size[label[v]], w);
-    }
-}
-
-// Per cluster: number of recorded components and the winner (largest; first-discovered wins ties, :503).
-// Reference quirk kept: the component discovered at item 0 is never recorded because 0 doubles as the
-// "unvisited" sentinel of VisitedCluster (:463-467), so it is neither counted nor ever reset.
-__global__ void k_cc_winner(int V, int K, const int* __restrict__ cid, const int* __restrict__ label,
-                            const int* __restrict__ comp_size, int* n_comp, unsigned long long* winner, const int* __restrict__ n_roots) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-        int c = cid[v];
-        if (c >= K || n_roots[c] <= 1 || label[v] != v || v == 0) continue;
-        atomicAdd(&n_comp[c], 1);
-        unsigned long long key = ((unsigned long long)(unsigned)comp_size[v] << 32) | (unsigned)(0xffffffffu - (unsigned)v);
-        atomicMax(&winner[c], key);
-    }
-}
-
-__global__ void k_cc_apply(int V, int K, int* cid, const int* __restrict__ label, const int* __restrict__ n_comp,
-                           const unsigned long long* __restrict__ winner, unsigned long long* n_reset) {
-    unsigned cnt = 0;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-        int c = cid[v];
-        if (c >= K) continue;
-        int root = label[v];
-        if (root == 0 || n_comp[c] < 2) continue;
-        unsigned win_root = 0xffffffffu - (unsigned)(winner[c] & 0xffffffffull);
-        if ((unsigned)root != win_root) { cid[v] = K; cnt++; }
-    }
-    warp_count_add(n_reset, cnt);
-}
-
-__global__ void k_count_ge2(int K, const int* __restrict__ n_comp, unsigned long long* out) {
-    unsigned cnt = 0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x) cnt += n_comp[c] >= 2;
-    warp_count_add(out, cnt);
 }
 
 // ---------------- hole filling (fill.cuh): list of the NULL vertices ----------------

@@ -63,6 +63,15 @@ struct acvd_ctx {
     bool dense_next = true;           // next round scans all tiles (activity was high)
     int last_all_tiles = 0, last_tile_count = 0, last_bulk = 0;
     bool last_dense_kernel = false;   // the last scan launch was k_scan_bulk_dense
+    // per-cluster member arrays and sparse rounds (sparse.cuh)
+    DevBuf<int> memb_off, memb_cap, memb, memb_tmp, memb_pos, cc_par, cc_sz, memb_overflow, stamp, modlist0, modlist1, sp_done;
+    DevBuf<unsigned long long> best2, sp_nmod, sp_resub, sp_ts;
+    DevBuf<RoundCounters> sp_rc;
+    bool members_valid = false;
+    int mod_par = 0;                  // which modlist the last round wrote (0 / 1)
+    bool modlist_valid = false;       // ... and whether it describes the last round completely
+    RoundCounters* h_sp_rc = nullptr; // pinned mirrors of the per-round records of one sparse launch
+    unsigned long long* h_sp_ts = nullptr;
     // bulk (Lloyd-criterion) rounds
     DevBuf<long long> isum;
     DevBuf<double> bulk_cen, bulk_energy, bulk_energy_sum;

@@ -81,6 +81,7 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
     if (force_all) ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p + 1, 0, sizeof(unsigned long long), c->stream));
     else ACVD_CUDA(cudaMemcpyAsync(c->round_scalars.p + 1, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
     c->plist_cur ^= 1;
+    c->members_valid = false; c->modlist_valid = false;    // rebuilt when the phase enters its replicated tail
     ReassignArgs A = make_args(c, cfg, connexity, force_all);
     ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
@@ -160,6 +161,7 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
 static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     EvalCfg cfg = make_cfg(0, 0, 0);
     c->plist_cur = 0;
+    c->members_valid = false; c->modlist_valid = false;
     ReassignArgs A = make_args(c, cfg, 0, force_all);
     A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 0;
     BulkArgs B = make_bulk_args(c);

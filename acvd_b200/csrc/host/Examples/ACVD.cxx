@@ -2,6 +2,7 @@
 // DiscreteRemeshing/Examples/ACVD.cxx (file nvertices gradation [-key value]...), same output files
 // (smooth_<outputfile> before the quadric post-process, then <outputfile>, default simplification.ply).
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <iostream>
 #include <string>
@@ -82,40 +83,23 @@ int main(int argc, char* argv[]) {
         // vertices and move the output vertex to the representative point of that quadric
         vtkIntArray* Clustering = Remesh->GetClustering();
         Remesh->GetOutput()->WriteToFile((dir + "smooth_" + outputfile).c_str());
+        // accumulation on the device (acvd_cluster_quadrics: a warp per cluster over its items' faces), then the batched
+        // representative-point solve (vtkQuadricTools::ComputeRepresentativePoint); as in the reference the arrays are
+        // sized by NumberOfSamples, so items of clusters appended by the -m loop count as misclassed (ACVD.cxx:237-249)
+        const int nq = std::min(NumberOfSamples, Remesh->GetNumberOfClusters());
         std::vector<double> Q((size_t)NumberOfSamples * 9, 0.0);
-        vtkSurface* In = Remesh->GetInput();
-        vtkIdList* FList = vtkIdList::New();
         int misclassed = 0;
         for (int i = 0; i < Remesh->GetNumberOfItems(); i++) {
             const int c = Clustering->GetValue(i);
-            if (c < 0 || c >= NumberOfSamples) { misclassed++; continue; }
-            In->GetVertexNeighbourFaces(i, FList);
-            for (vtkIdType j = 0; j < FList->GetNumberOfIds(); j++) {
-                vtkIdType a, b, d;
-                In->GetFaceVertices(FList->GetId(j), a, b, d);
-                double x1[3], x2[3], x3[3];
-                In->GetPoint(a, x1); In->GetPoint(b, x2); In->GetPoint(d, x3);
-                const double n[3] = {(x1[1] * x2[2] - x1[2] * x2[1]) + (x2[1] * x3[2] - x2[2] * x3[1]) + (x3[1] * x1[2] - x3[2] * x1[1]),
-                                     (x1[2] * x2[0] - x1[0] * x2[2]) + (x2[2] * x3[0] - x2[0] * x3[2]) + (x3[2] * x1[0] - x3[0] * x1[2]),
-                                     (x1[0] * x2[1] - x1[1] * x2[0]) + (x2[0] * x3[1] - x2[1] * x3[0]) + (x3[0] * x1[1] - x3[1] * x1[0])};
-                const double dd = -(x1[0] * x2[1] * x3[2] + x2[0] * x3[1] * x1[2] + x3[0] * x1[1] * x2[2] - x1[0] * x3[1] * x2[2] -
-                                    x2[0] * x1[1] * x3[2] - x3[0] * x2[1] * x1[2]);
-                double* q = &Q[(size_t)c * 9];
-                q[0] += n[0] * n[0]; q[1] += n[0] * n[1]; q[2] += n[0] * n[2]; q[3] += n[0] * dd;
-                q[4] += n[1] * n[1]; q[5] += n[1] * n[2]; q[6] += n[1] * dd; q[7] += n[2] * n[2]; q[8] += n[2] * dd;
-            }
+            if (c < 0 || c >= NumberOfSamples) misclassed++;
         }
-        FList->Delete();
         if (misclassed) cout << misclassed << " Items with wrong cluster association" << endl;
-        // batched representative-point solve on the device (vtkQuadricTools::ComputeRepresentativePoint)
         std::vector<double> P((size_t)NumberOfSamples * 3);
         for (int i = 0; i < NumberOfSamples; i++) Remesh->GetOutput()->GetPoint(i, &P[(size_t)i * 3]);
-        acvd_ctx* ctx = nullptr;
-        if (acvd_create(&ctx, -1) == ACVD_OK) {
-            if (acvd_representative_points(ctx, NumberOfSamples, Q.data(), P.data(), QuadricsOptimizationLevel, 1e-3, nullptr) != ACVD_OK)
-                cout << "ERROR : " << acvd_last_error(ctx) << endl;
-            acvd_destroy(ctx);
-        } else cout << "ERROR : " << acvd_last_error(nullptr) << endl;
+        acvd_ctx* ctx = Remesh->GetContext();
+        if (!ctx || acvd_cluster_quadrics(ctx, nq, Q.data()) != ACVD_OK ||
+            acvd_representative_points(ctx, NumberOfSamples, Q.data(), P.data(), QuadricsOptimizationLevel, 1e-3, nullptr) != ACVD_OK)
+            cout << "ERROR : " << acvd_last_error(ctx) << endl;
         for (int i = 0; i < NumberOfSamples; i++) Remesh->GetOutput()->SetPointCoordinates(i, &P[(size_t)i * 3]);
         cout << "After Quadrics Post-processing : " << endl;
         Remesh->GetOutput()->DisplayMeshProperties();

@@ -77,6 +77,7 @@ public:
     void SetPrincipalDirections(const float* values, vtkIdType n6) { PrincipalDirections.assign(values, values + n6); }
     void SetDevice(int d) { Device = d; }
     const acvd_report& GetReport() const { return Report; }
+    acvd_ctx* GetContext() { return Ctx; }                      // the engine's context (mesh + final clustering stay resident)
 
 protected:
     explicit vtkDiscreteRemeshingB200(int metric_kind);

@@ -607,7 +607,7 @@ __device__ __forceinline__ void note_move(const ReassignArgs& A, int v, int a, i
         }
         const int q = A.mem.off[d] + A.csize[d];
         if (q < A.mem.off[d + 1]) { A.mem.memb[q] = v; A.mem.pos[v] = q; }
-        else *A.mem.overflow = 1;                              // array full: the driver rebuilds the arrays before they are read
+        else { *A.mem.overflow = 1; A.ctr->pad[2] = 1; }      // array full: the driver rebuilds the arrays before they are read
     }
     if (A.modlist) {
         const int s = (int)atomicAdd(A.n_mod, a < A.K ? 2ull : 1ull);

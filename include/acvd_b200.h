@@ -119,7 +119,10 @@ typedef struct acvd_params {
     int32_t rounds_per_sync;      /* rounds launched back to back between host polls in the tail of the last phases, <=0 -> 4, max 8 */
     double sv_threshold;          /* <=0 -> 1e-3 (Common/vtkQuadricTools.h:36) */
     int32_t bulk_rounds;          /* early phases: 0 -> bulk Lloyd-criterion rounds on (cap 1000), <0 -> off, >0 -> cap */
-    int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 2 (the same default on any number of GPUs) */
+    int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 2 (the same default on any number of GPUs), max 8 */
+    int32_t sparse_rounds;        /* 0 -> rounds after a phase's opening round run in the persistent sparse-round kernel
+                                     (dirty set enumerated from the modified clusters' member arrays); <0 -> tile-filter
+                                     path for every round (same decisions: the A/B partner of the tests) */
 } acvd_params;
 
 typedef struct acvd_report {
@@ -147,6 +150,8 @@ typedef struct acvd_report {
     int64_t dense_scan_bytes;    /* algorithmic bytes they moved (SURVEY 8d model: 8 + 8 deg per vertex + the tests' operands) */
     int64_t dense_scan_vertices; /* vertices they scanned */
     int64_t bulk_rollbacks;      /* stage-1 bulk rounds undone by the energy guard (0 or 1 per phase) */
+    int64_t sparse_rounds;       /* exact rounds run inside the persistent sparse-round kernel (k_sparse_rounds) */
+    double ms_sparse;            /* device time of those rounds (enumerate + evaluate + commit, %globaltimer inside the kernel) */
 } acvd_report;
 
 /* MinimizeEnergy (Common/vtkUniformClustering.h:725-830) with ProcessOneLoop (:833-995) replaced by
@@ -179,6 +184,11 @@ int acvd_get_energy_log(acvd_ctx* ctx, double* out, int32_t cap, int32_t* n);
  * n quadrics (9 doubles each) and points (3 doubles each, updated in place), rank deficiency out. */
 int acvd_representative_points(acvd_ctx* ctx, int32_t n, const double* quadrics9, double* points3,
                                int32_t max_sv, double sv_threshold, int32_t* rank_deficiency);
+
+/* Accumulation step of ACVD's quadric post-process (DiscreteRemeshing/Examples/ACVD.cxx:237-262): for the first
+ * n_clusters clusters, the sum over the cluster's items of the quadrics of the input faces around each item
+ * (vtkQuadricTools::AddTriangleQuadric, 9 coefficients).  Followed on the host side by acvd_representative_points. */
+int acvd_cluster_quadrics(acvd_ctx* ctx, int32_t n_clusters, double* quadrics9 /*9 n_clusters*/);
 
 /* ---- integer stages after the hot path (vtkDiscreteRemeshing.h:1003-1133) ---------------- */
 /* boundary flag per vertex (has a neighbour in another cluster) */

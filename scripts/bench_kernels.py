@@ -9,7 +9,8 @@ import sys
 sys.path.insert(0, ".")
 from acvd_b200 import capi, meshgen  # noqa: E402
 
-VARIANTS = {-1: "k_scan<W,true> (list)", 0: "S=3 B=4", 1: "S=2 B=4", 2: "S=4 B=4", 3: "S=2 B=5", 4: "S=3 B=5", 5: "S=2 B=6", 6: "S=3 B=3"}
+VARIANTS = {-1: "k_scan<W,true> (list)", 0: "S=3 B=4", 1: "S=2 B=4", 2: "S=4 B=4", 3: "S=2 B=5", 4: "S=3 B=5", 5: "S=2 B=6", 6: "S=3 B=3",
+            10: "gen2 S=3 B=4", 11: "gen2 S=3 B=3", 12: "gen2 S=2 B=4", 13: "gen2 S=4 B=3", 14: "gen2 S=2 B=5", 15: "gen2 S=4 B=4"}
 
 if __name__ == "__main__":
     wl = sys.argv[1] if len(sys.argv) > 1 else "C4"

@@ -320,7 +320,8 @@ def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle,
     else:
         (p, t), ind, K, grad = spindle, None, 150, 0.0
     res = []
-    for no_dense in ("", "1"):
+    for no_dense, variant in (("", "0"), ("1", "0"), ("", "10"), ("", "11")):   # 10, 11: second-generation kernel (two tiles in flight)
+        monkeypatch.setenv("ACVD_DENSE_VARIANT", variant)
         if no_dense:
             monkeypatch.setenv("ACVD_NO_DENSE_SCAN", "1")
         else:
@@ -332,12 +333,13 @@ def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle,
         g.initial_sampling()
         rep = g.minimize(unconstrained_init=1)
         res.append((g.clustering().copy(), rep))
-    (c0, r0), (c1, r1) = res
-    assert r0["bulk_rounds"] > 0
-    for k in ("rounds", "bulk_rounds", "tests", "proposals", "modifications", "evaluated"):
-        assert r0[k] == r1[k], k
-    assert np.array_equal(c0, c1)
-    assert r0["energy"] == r1["energy"]
+    c0, r0 = res[0]
+    assert r0["bulk_rounds"] > 0 and r0["dense_scan_launches"] > 0 and res[1][1]["dense_scan_launches"] == 0
+    for c1, r1 in res[1:]:
+        for k in ("rounds", "bulk_rounds", "tests", "proposals", "modifications", "evaluated"):
+            assert r0[k] == r1[k], k
+        assert np.array_equal(c0, c1)
+        assert r0["energy"] == r1["energy"]
 
 
 @pytest.mark.parametrize("name", ["C2", "C3", "C4"])
@@ -740,3 +742,46 @@ def test_baseline_size_energy_vs_oracle(oracle_mod, gpu_ctx_factory, name):
     o.prime()
     assert o.process_one_loop() == 0
     g.close()
+
+
+@pytest.mark.parametrize("case", ["torus-qem", "sphere-iso", "spindle-qem", "ellipsoid-anisoq", "sphere-qem-passes4"])
+def test_sparse_rounds_equal_tile_filter_rounds(gpu_ctx_factory, sphere, torus, spindle, case):
+    """The persistent sparse-round kernel (dirty set enumerated from the member arrays of the modified clusters,
+    convergence decided on the device) takes the decisions of the tile-filter path round for round: same clustering,
+    same number of rounds, vertex tests, proposals and moves, same energy -- the "recently modified" rule of
+    Common/vtkUniformClustering.h:909-920 is preserved."""
+    kw = {}
+    if case == "torus-qem":
+        p, t, ind = torus
+        args, K, uncon = ("qem", 1.5, ind, None), 500, 1
+    elif case == "sphere-iso":
+        p, t = sphere
+        args, K, uncon = ("iso", 0.0, None, None), 300, 0
+    elif case == "spindle-qem":
+        p, t = spindle
+        args, K, uncon = ("qem", 0.0, None, None), 150, 1
+    elif case == "sphere-qem-passes4":
+        p, t = sphere
+        args, K, uncon = ("qem", 0.0, None, None), 250, 1
+        kw = dict(commit_passes=4)
+    else:
+        p, t = meshgen.ridged_ellipsoid(40)
+        pd, ind = meshgen.ellipsoid_principal_directions(p)
+        args, K, uncon = ("anisoq", 1.5, ind, pd), 200, 0
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    g.build_items(*args)
+    g.set_num_clusters(K)
+    g.initial_sampling()
+    g.save_clustering()
+    out = {}
+    for sparse in (0, -1):
+        g.restore_clustering()
+        rep = g.minimize(unconstrained_init=uncon, sparse_rounds=sparse, **kw)
+        out[sparse] = (g.clustering().copy(), rep)
+    (c0, r0), (c1, r1) = out[0], out[-1]
+    assert r0["sparse_rounds"] > 0 and r1["sparse_rounds"] == 0
+    assert np.array_equal(c0, c1)
+    for k in ("rounds", "tests", "proposals", "modifications", "convergences", "evaluated", "energy"):
+        assert r0[k] == r1[k], (k, r0[k], r1[k])
+    assert g.clean_clustering() == 0
