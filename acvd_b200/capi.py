@@ -90,6 +90,10 @@ SYMBOLS = [
     ("acvd_boundary_flags", C.c_int, [_vp, _vp]),
     ("acvd_cluster_adjacency", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     ("acvd_dual_triangles", C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    ("acvd_input_manifold_flags", C.c_int, [_vp, _vp]),
+    ("acvd_output_manifold_flags", C.c_int, [_vp, _i32, _vp]),
+    ("acvd_detect_non_manifold", C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    ("acvd_get_frozen", C.c_int, [_vp, _vp]),
     ("acvd_bench_kernel", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("acvd_dist_unique_id", C.c_int, [_vp]),
     ("acvd_dist_init", C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -325,6 +329,28 @@ class Context:
         out = np.zeros((n.value, 3), dtype=np.int32)
         if n.value:
             self._ck(self.L.acvd_dual_triangles(self.h, _p(out), n.value, C.byref(n)))
+        return out
+
+    def input_manifold_flags(self):
+        out = np.zeros(self.V, dtype=np.uint8)
+        self._ck(self.L.acvd_input_manifold_flags(self.h, _p(out)))
+        return out
+
+    def output_manifold_flags(self, force_manifold_edges=1):
+        out = np.zeros(self.K, dtype=np.uint8)
+        self._ck(self.L.acvd_output_manifold_flags(self.h, int(force_manifold_edges), _p(out)))
+        return out
+
+    def detect_non_manifold(self, force_manifold_edges=1):
+        """One DetectNonManifoldOutputVertices step; returns the number of issues, self.K follows the grown count."""
+        n, k = _i32(), _i32()
+        self._ck(self.L.acvd_detect_non_manifold(self.h, int(force_manifold_edges), C.byref(n), C.byref(k)))
+        self.K = k.value
+        return n.value
+
+    def frozen(self):
+        out = np.zeros(self.K, dtype=np.uint8)
+        self._ck(self.L.acvd_get_frozen(self.h, _p(out)))
         return out
 
     # ---- multi-GPU

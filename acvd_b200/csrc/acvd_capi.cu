@@ -5,7 +5,9 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
+#include <functional>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -14,6 +16,7 @@
 #include "cleanup.cuh"
 #include "curvature.cuh"
 #include "fill.cuh"
+#include "manifold.cuh"
 #include "common.cuh"
 #include "ctx.cuh"
 #include "host_sampling.hpp"
@@ -473,8 +476,7 @@ extern "C" int acvd_get_vertex_areas(acvd_ctx* c, double* areas) {
 
 // ---------------------------------------------------------------------------------------------
 // clusters
-extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
-    ACVD_API_BEGIN(c)
+static void set_num_clusters_impl(acvd_ctx* c, int32_t K) {
     if (K <= 0) throw std::runtime_error("acvd_set_num_clusters: K must be positive");
     if (!c->have_items) throw std::runtime_error("acvd_set_num_clusters: build or set the items first");
     const int V = c->V, npad = payload_npad(c->metric);
@@ -509,6 +511,11 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
     c->fixed.clear();
     c->round = 1;
     c->stats_valid = false;
+}
+
+extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
+    ACVD_API_BEGIN(c)
+    set_num_clusters_impl(c, K);
     ACVD_API_END(c)
 }
 
@@ -562,6 +569,13 @@ extern "C" int acvd_set_frozen(acvd_ctx* c, const uint8_t* frozen) {
         ACVD_CUDA(cudaMemset(c->frozen.p, 0, (size_t)c->K));
         c->has_frozen = false;
     }
+    ACVD_API_END(c)
+}
+
+extern "C" int acvd_get_frozen(acvd_ctx* c, uint8_t* frozen) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !frozen) throw std::runtime_error("acvd_get_frozen: no clustering");
+    ACVD_CUDA(cudaMemcpy(frozen, c->frozen.p, (size_t)c->K, cudaMemcpyDeviceToHost));
     ACVD_API_END(c)
 }
 
@@ -1621,11 +1635,10 @@ extern "C" int acvd_boundary_flags(acvd_ctx* c, uint8_t* flags) {
     ACVD_API_END(c)
 }
 
-extern "C" int acvd_cluster_adjacency(acvd_ctx* c, int64_t* out, int64_t cap, int64_t* n_out) {
-    ACVD_API_BEGIN(c)
-    if (!c->K || !n_out) throw std::runtime_error("acvd_cluster_adjacency: bad arguments");
+// sorted unique (lo << 32 | hi) pairs of clusters joined by a mesh edge, left on the device; returns the count
+static int64_t cluster_adjacency_device(acvd_ctx* c, DevBuf<unsigned long long>& uniq) {
     const int64_t n = c->nnz;
-    DevBuf<unsigned long long> keys, alt, uniq;
+    DevBuf<unsigned long long> keys, alt;
     DevBuf<int64_t> d_num;
     keys.alloc(n); alt.alloc(n); uniq.alloc(n); d_num.alloc(1);
     k_adjacency_keys<<<grid_for(c->V), kThreads, 0, c->stream>>>(c->V, c->K, c->row_ptr.p, c->col.p, c->cid.p, keys.p);
@@ -1643,51 +1656,339 @@ extern "C" int acvd_cluster_adjacency(acvd_ctx* c, int64_t* out, int64_t cap, in
         ACVD_CUDA(cudaMemcpy(&last, uniq.p + (nu - 1), sizeof last, cudaMemcpyDeviceToHost));
         if (last == ~0ull) nu--;
     }
+    return nu;
+}
+
+extern "C" int acvd_cluster_adjacency(acvd_ctx* c, int64_t* out, int64_t cap, int64_t* n_out) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !n_out) throw std::runtime_error("acvd_cluster_adjacency: bad arguments");
+    DevBuf<unsigned long long> uniq;
+    const int64_t nu = cluster_adjacency_device(c, uniq);
     *n_out = nu;
     if (out && nu > 0) ACVD_CUDA(cudaMemcpy(out, uniq.p, (size_t)std::min(nu, cap) * sizeof(int64_t), cudaMemcpyDeviceToHost));
     ACVD_API_END(c)
 }
 
-extern "C" int acvd_dual_triangles(acvd_ctx* c, int32_t* out, int64_t cap, int64_t* n_out) {
-    ACVD_API_BEGIN(c)
-    if (!c->K || !n_out) throw std::runtime_error("acvd_dual_triangles: bad arguments");
-    if (c->K >= (1 << 21)) throw std::runtime_error("acvd_dual_triangles: K must be below 2^21");
+// Dual triangles in first-occurrence order over the input faces, left on the device (d_out: 3 ints per triangle).
+// A face qualifies when its three clusters are distinct and assigned; faces are ordered by their sorted cluster triple
+// with two stable radix sorts -- (mid, hi) as one 64-bit key, then lo -- so equal triples keep ascending face order and
+// no cluster-count limit applies; the first face of every run is the triple's first occurrence.
+static int dual_triangles_device(acvd_ctx* c, DevBuf<int>& d_out) {
     const int F = c->F;
     DevBuf<unsigned long long> k0, k1;
-    DevBuf<int> f0, f1, first, first_sorted;
-    k0.alloc(F); k1.alloc(F); f0.alloc(F); f1.alloc(F); first.alloc(F); first_sorted.alloc(F);
-    k_dual_keys<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->K, c->tri.p, c->cid.p, k0.p, f0.p);
+    DevBuf<unsigned> lo, lo_perm, lo_sorted;
+    DevBuf<int> f0, f1, f2, first, first_sorted;
+    k0.alloc(F); k1.alloc(F); lo.alloc(F); lo_perm.alloc(F); lo_sorted.alloc(F);
+    f0.alloc(F); f1.alloc(F); f2.alloc(F); first.alloc(F); first_sorted.alloc(F);
+    k_dual_keys<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->K, c->tri.p, c->cid.p, k0.p, lo.p, f0.p);
     ACVD_LAUNCH_CHECK();
-    size_t tb = 0;   // stable: equal keys keep ascending face order
+    size_t tb = 0;
     ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, f0.p, f1.p, F, 0, 64, c->stream));
     void* t = cub_temp(c, tb);
     ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, k0.p, k1.p, f0.p, f1.p, F, 0, 64, c->stream));
-    k_dual_first<<<grid_for(F), kThreads, 0, c->stream>>>(F, k1.p, f1.p, first.p);
+    k_gather_u32<<<grid_for(F), kThreads, 0, c->stream>>>(F, f1.p, lo.p, lo_perm.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, lo_perm.p, lo_sorted.p, f1.p, f2.p, F, 0, 32, c->stream));
+    t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, lo_perm.p, lo_sorted.p, f1.p, f2.p, F, 0, 32, c->stream));
+    ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(unsigned long long), c->stream));
+    k_dual_first<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->K, f2.p, c->tri.p, c->cid.p, first.p, c->scalars.p);
     ACVD_LAUNCH_CHECK();
     // ascending first-face ids = first-occurrence order over the input faces; sentinels sort to the end
     ACVD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, first.p, first_sorted.p, F, 0, 32, c->stream));
     t = cub_temp(c, tb);
     ACVD_CUDA(cub::DeviceRadixSort::SortKeys(t, tb, first.p, first_sorted.p, F, 0, 32, c->stream));
-    // count = first index holding the sentinel
-    std::vector<int> h;   // binary search on the device-sorted array through small copies
-    int lo = 0, hi = F;
-    while (lo < hi) {
-        int mid = (lo + hi) / 2, val = 0;
-        ACVD_CUDA(cudaMemcpyAsync(&val, first_sorted.p + mid, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        ACVD_CUDA(cudaStreamSynchronize(c->stream));
-        if (val == 0x7fffffff) hi = mid; else lo = mid + 1;
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    const int n = (int)c->h_scalars[0];
+    d_out.alloc(3 * (size_t)std::max(n, 1));
+    if (n > 0) {
+        k_dual_emit<<<grid_for(n), kThreads, 0, c->stream>>>(n, first_sorted.p, c->tri.p, c->cid.p, d_out.p);
+        ACVD_LAUNCH_CHECK();
     }
-    const int n = lo;
+    return n;
+}
+
+extern "C" int acvd_dual_triangles(acvd_ctx* c, int32_t* out, int64_t cap, int64_t* n_out) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !n_out) throw std::runtime_error("acvd_dual_triangles: bad arguments");
+    DevBuf<int> d_out;
+    const int n = dual_triangles_device(c, d_out);
     *n_out = n;
     if (out && n > 0) {
-        int m = (int)std::min<int64_t>(n, cap);
-        DevBuf<int> d_out;
-        d_out.alloc(3 * (size_t)m);
-        k_dual_emit<<<grid_for(m), kThreads, 0, c->stream>>>(m, first_sorted.p, c->tri.p, c->cid.p, d_out.p);
-        ACVD_LAUNCH_CHECK();
+        const int m = (int)std::min<int64_t>(n, cap);
         ACVD_CUDA(cudaMemcpyAsync(out, d_out.p, 3 * (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
     }
+    ACVD_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------
+// manifoldness (the -m 1 loop): vtkSurfaceBase::IsVertexManifold on the device (manifold.cuh)
+static void exclusive_sum(acvd_ctx* c, const int* in, int* out, int64_t n) {
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceScan::ExclusiveSum(t, tb, in, out, n, c->stream));
+}
+
+extern "C" int acvd_input_manifold_flags(acvd_ctx* c, uint8_t* flags) {
+    ACVD_API_BEGIN(c)
+    if (!c->V || !flags) throw std::runtime_error("acvd_input_manifold_flags: set the mesh first");
+    DevBuf<unsigned char> d;
+    d.alloc(c->V);
+    FanMesh M{c->V, c->row_ptr.p, c->col.p, c->vf_ptr.p, nullptr, c->vf_keys.p, c->tri.p};
+    k_vertex_manifold<<<grid_for(c->V, 128, 16), 128, 0, c->stream>>>(M, d.p);
+    ACVD_LAUNCH_CHECK();
+    ACVD_CUDA(cudaMemcpyAsync(flags, d.p, (size_t)c->V, cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+// the dual (output) mesh of the current clustering with its incidence, on the device
+struct OutputMesh {
+    DevBuf<int> tri, f_ptr, f_ids, e_ptr, e_nb;
+    int n_tri = 0;
+    int64_t n_pairs = 0;
+};
+
+static void build_output_mesh(acvd_ctx* c, int force_manifold_edges, OutputMesh& O) {
+    const int K = c->K;
+    DevBuf<int> f_cnt, f_cur, e_cnt, e_cur;
+    const int n_tri = O.n_tri = dual_triangles_device(c, O.tri);
+    f_cnt.alloc((size_t)K + 1); O.f_ptr.alloc((size_t)K + 1); f_cur.alloc(K); O.f_ids.alloc(3 * (size_t)std::max(n_tri, 1));
+    ACVD_CUDA(cudaMemsetAsync(f_cnt.p, 0, ((size_t)K + 1) * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(f_cur.p, 0, (size_t)K * sizeof(int), c->stream));
+    if (n_tri > 0) { k_count_tri_corners<<<grid_for(3 * (int64_t)n_tri), kThreads, 0, c->stream>>>(n_tri, O.tri.p, f_cnt.p); ACVD_LAUNCH_CHECK(); }
+    exclusive_sum(c, f_cnt.p, O.f_ptr.p, K + 1);
+    if (n_tri > 0) { k_scatter_tri_corners<<<grid_for(3 * (int64_t)n_tri), kThreads, 0, c->stream>>>(n_tri, O.tri.p, O.f_ptr.p, f_cur.p, O.f_ids.p); ACVD_LAUNCH_CHECK(); }
+    // edges: with ForceManifold every pair of clusters joined by a mesh edge (:1114-1133), else the triangles' edges
+    DevBuf<unsigned long long> pairs;
+    int64_t n_pairs = 0;
+    if (force_manifold_edges) n_pairs = cluster_adjacency_device(c, pairs);
+    else if (n_tri > 0) {
+        const int64_t n3 = 3 * (int64_t)n_tri;
+        DevBuf<unsigned long long> keys, alt;
+        DevBuf<int64_t> d_num;
+        keys.alloc(n3); alt.alloc(n3); pairs.alloc(n3); d_num.alloc(1);
+        k_tri_edge_keys<<<grid_for(n3), kThreads, 0, c->stream>>>(n_tri, O.tri.p, keys.p);
+        ACVD_LAUNCH_CHECK();
+        sort_keys64(c, keys.p, alt.p, n3, 64);
+        size_t tb = 0;
+        ACVD_CUDA(cub::DeviceSelect::Unique(nullptr, tb, keys.p, pairs.p, d_num.p, n3, c->stream));
+        void* t = cub_temp(c, tb);
+        ACVD_CUDA(cub::DeviceSelect::Unique(t, tb, keys.p, pairs.p, d_num.p, n3, c->stream));
+        ACVD_CUDA(cudaMemcpyAsync(&n_pairs, d_num.p, sizeof n_pairs, cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    O.n_pairs = n_pairs;
+    e_cnt.alloc((size_t)K + 1); O.e_ptr.alloc((size_t)K + 1); e_cur.alloc(K); O.e_nb.alloc(2 * (size_t)std::max<int64_t>(n_pairs, 1));
+    ACVD_CUDA(cudaMemsetAsync(e_cnt.p, 0, ((size_t)K + 1) * sizeof(int), c->stream));
+    ACVD_CUDA(cudaMemsetAsync(e_cur.p, 0, (size_t)K * sizeof(int), c->stream));
+    if (n_pairs > 0) { k_count_pair_ends<<<grid_for(n_pairs), kThreads, 0, c->stream>>>(n_pairs, pairs.p, e_cnt.p); ACVD_LAUNCH_CHECK(); }
+    exclusive_sum(c, e_cnt.p, O.e_ptr.p, K + 1);
+    if (n_pairs > 0) { k_scatter_pair_ends<<<grid_for(n_pairs), kThreads, 0, c->stream>>>(n_pairs, pairs.p, O.e_ptr.p, e_cur.p, O.e_nb.p); ACVD_LAUNCH_CHECK(); }
+}
+
+static void output_manifold_flags_device(acvd_ctx* c, const OutputMesh& O, DevBuf<unsigned char>& d) {
+    d.alloc(c->K);
+    FanMesh M{c->K, O.e_ptr.p, O.e_nb.p, O.f_ptr.p, O.f_ids.p, nullptr, O.tri.p};
+    k_vertex_manifold<<<grid_for(c->K, 128, 16), 128, 0, c->stream>>>(M, d.p);
+    ACVD_LAUNCH_CHECK();
+}
+
+extern "C" int acvd_output_manifold_flags(acvd_ctx* c, int32_t force_manifold_edges, uint8_t* flags) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !flags) throw std::runtime_error("acvd_output_manifold_flags: no clustering");
+    OutputMesh O;
+    build_output_mesh(c, force_manifold_edges, O);
+    DevBuf<unsigned char> d;
+    output_manifold_flags_device(c, O, d);
+    ACVD_CUDA(cudaMemcpyAsync(flags, d.p, (size_t)c->K, cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    ACVD_API_END(c)
+}
+
+// the host form of the predicate for the vertices the kernel leaves open (more than kMaxRing edges)
+static bool host_vertex_manifold(const std::vector<int>& nb, const std::vector<std::array<int, 3>>& faces, int v) {
+    const int ne = (int)nb.size();
+    if (ne < 2) return false;
+    std::vector<int> cnt((size_t)ne, 0), par((size_t)ne);
+    for (int j = 0; j < ne; j++) par[(size_t)j] = j;
+    auto slot = [&](int u) { for (int j = 0; j < ne; j++) if (nb[(size_t)j] == u) return j; return -1; };
+    std::function<int(int)> find = [&](int x) { while (par[(size_t)x] != x) { par[(size_t)x] = par[(size_t)par[(size_t)x]]; x = par[(size_t)x]; } return x; };
+    for (const auto& t : faces) {
+        int o[2], m = 0;
+        for (int k = 0; k < 3; k++) if (t[(size_t)k] != v) { if (m < 2) o[m] = t[(size_t)k]; m++; }
+        if (m != 2 || o[0] == o[1]) continue;
+        const int ja = slot(o[0]), jb = slot(o[1]);
+        if (ja < 0 || jb < 0) return false;
+        cnt[(size_t)ja]++; cnt[(size_t)jb]++;
+        const int ra = find(ja), rb = find(jb);
+        if (ra != rb) par[(size_t)std::max(ra, rb)] = std::min(ra, rb);
+    }
+    const int r0 = find(0);
+    for (int j = 0; j < ne; j++) if (cnt[(size_t)j] != 2 || find(j) != r0) return false;
+    return true;
+}
+
+template <typename T>
+static std::vector<T> download(acvd_ctx* c, const T* d, size_t n) {
+    std::vector<T> h(n);
+    if (n) ACVD_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    return h;
+}
+
+// DetectNonManifoldOutputVertices (DiscreteRemeshing/vtkDiscreteRemeshing.h:166-383), one step of the -m 1 loop.
+// The manifold tests run on the device; the bookkeeping the reference does on its per-cluster item lists (a handful of
+// clusters) is done here on the host side of the library.  On return every cluster is frozen except the offending ones
+// and their output neighbours, one new cluster per issue has been appended (seeded with the first item of the offending
+// cluster or, for a one-item cluster, the first ring neighbour whose cluster has more than one item), the clustering
+// and the cluster tables are those of the grown cluster count.
+extern "C" int acvd_detect_non_manifold(acvd_ctx* c, int32_t force_manifold_edges, int32_t* n_issues, int32_t* new_num_clusters) {
+    ACVD_API_BEGIN(c)
+    if (!c->K || !n_issues || !new_num_clusters) throw std::runtime_error("acvd_detect_non_manifold: bad arguments");
+    const int V = c->V, K0 = c->K;
+    OutputMesh O;
+    build_output_mesh(c, force_manifold_edges, O);
+    DevBuf<unsigned char> d_flags;
+    output_manifold_flags_device(c, O, d_flags);
+    std::vector<unsigned char> oflag = download(c, d_flags.p, (size_t)K0);
+    std::vector<int> e_ptr = download(c, O.e_ptr.p, (size_t)K0 + 1), f_ptr = download(c, O.f_ptr.p, (size_t)K0 + 1);
+    std::vector<int> e_nb, f_ids, otri;         // fetched only when something is flagged
+    std::vector<int> cl;
+    std::vector<unsigned char> frozen((size_t)K0, 1);
+    std::vector<int> suspects;
+    for (int k = 0; k < K0; k++) if (oflag[(size_t)k] != 1) suspects.push_back(k);
+    std::vector<int> issues;
+    std::vector<std::vector<int>> items;         // per suspect cluster (and later per touched cluster): its items, ascending
+    std::vector<int> size_of;
+    if (!suspects.empty()) {
+        e_nb = download(c, O.e_nb.p, (size_t)e_ptr[(size_t)K0]);
+        f_ids = download(c, O.f_ids.p, (size_t)f_ptr[(size_t)K0]);
+        otri = download(c, O.tri.p, 3 * (size_t)O.n_tri);
+        cl = download(c, c->cid.p, (size_t)V);
+        size_of.assign((size_t)K0, 0);
+        for (int v = 0; v < V; v++) if (cl[(size_t)v] >= 0 && cl[(size_t)v] < K0) size_of[(size_t)cl[(size_t)v]]++;
+        // input-vertex manifoldness on the device, only now that it is needed
+        DevBuf<unsigned char> d_in;
+        d_in.alloc(V);
+        FanMesh M{V, c->row_ptr.p, c->col.p, c->vf_ptr.p, nullptr, c->vf_keys.p, c->tri.p};
+        k_vertex_manifold<<<grid_for(V, 128, 16), 128, 0, c->stream>>>(M, d_in.p);
+        ACVD_LAUNCH_CHECK();
+        std::vector<unsigned char> iflag = download(c, d_in.p, (size_t)V);
+        std::vector<char> is_suspect((size_t)K0, 0);
+        for (int k : suspects) is_suspect[(size_t)k] = 1;
+        std::vector<std::vector<int>> sus_items((size_t)K0);
+        for (int v = 0; v < V; v++) { const int k = cl[(size_t)v]; if (k >= 0 && k < K0 && is_suspect[(size_t)k]) sus_items[(size_t)k].push_back(v); }
+        auto input_manifold = [&](int v) {
+            if (iflag[(size_t)v] != 2) return iflag[(size_t)v] == 1;
+            int rp[2];
+            ACVD_CUDA(cudaMemcpy(rp, c->row_ptr.p + v, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+            std::vector<int> nb = download(c, c->col.p + rp[0], (size_t)(rp[1] - rp[0]));
+            int fp[2];
+            ACVD_CUDA(cudaMemcpy(fp, c->vf_ptr.p + v, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+            std::vector<unsigned long long> fk = download(c, c->vf_keys.p + fp[0], (size_t)(fp[1] - fp[0]));
+            std::vector<std::array<int, 3>> faces;
+            for (auto k : fk) { int t[3]; ACVD_CUDA(cudaMemcpy(t, c->tri.p + 3 * (size_t)(k & 0xffffffffull), 3 * sizeof(int), cudaMemcpyDeviceToHost)); faces.push_back({t[0], t[1], t[2]}); }
+            return host_vertex_manifold(nb, faces, v);
+        };
+        for (int k : suspects) {
+            bool manifold = oflag[(size_t)k] == 1;
+            if (oflag[(size_t)k] == 2) {
+                std::vector<int> nb(e_nb.begin() + e_ptr[(size_t)k], e_nb.begin() + e_ptr[(size_t)k + 1]);
+                std::vector<std::array<int, 3>> faces;
+                for (int i = f_ptr[(size_t)k]; i < f_ptr[(size_t)k + 1]; i++) { const int f = f_ids[(size_t)i]; faces.push_back({otri[3 * (size_t)f], otri[3 * (size_t)f + 1], otri[3 * (size_t)f + 2]}); }
+                manifold = host_vertex_manifold(nb, faces, k);
+            }
+            if (manifold) continue;
+            if (sus_items[(size_t)k].empty()) continue;                 // ".... but empty. Skipping"
+            bool problem = true;
+            for (int it : sus_items[(size_t)k]) if (!input_manifold(it)) { problem = false; break; }   // the input has the issue too
+            if (!problem) continue;
+            issues.push_back(k);
+            frozen[(size_t)k] = 0;
+            for (int i = e_ptr[(size_t)k]; i < e_ptr[(size_t)k + 1]; i++) frozen[(size_t)e_nb[(size_t)i]] = 0;
+        }
+        // ---- one new cluster per issue (:262-372)
+        int K = K0;
+        // ring of an item in the reference's order (edge creation order = ascending first half-edge slot)
+        auto ring_of = [&](int v) {
+            int rp[2], fp[2];
+            ACVD_CUDA(cudaMemcpy(rp, c->row_ptr.p + v, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+            ACVD_CUDA(cudaMemcpy(fp, c->vf_ptr.p + v, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+            std::vector<int> nb = download(c, c->col.p + rp[0], (size_t)(rp[1] - rp[0]));
+            std::vector<unsigned long long> fk = download(c, c->vf_keys.p + fp[0], (size_t)(fp[1] - fp[0]));
+            std::vector<std::pair<unsigned, int>> order;
+            std::vector<std::array<int, 4>> faces;
+            for (auto k : fk) { const int f = (int)(k & 0xffffffffull); int t[3]; ACVD_CUDA(cudaMemcpy(t, c->tri.p + 3 * (size_t)f, 3 * sizeof(int), cudaMemcpyDeviceToHost)); faces.push_back({t[0], t[1], t[2], f}); }
+            for (int u : nb) {
+                unsigned best = 0xffffffffu;
+                for (const auto& t : faces) {
+                    const int ia = t[0] == v ? 0 : (t[1] == v ? 1 : 2);
+                    const int ib = t[0] == u ? 0 : (t[1] == u ? 1 : (t[2] == u ? 2 : -1));
+                    if (ib < 0 || ib == ia) continue;
+                    const int lo = std::min(ia, ib), hi = std::max(ia, ib);
+                    const int side = (lo == 0 && hi == 1) ? 0 : (lo == 1 ? 1 : 2);
+                    best = std::min(best, 3u * (unsigned)t[3] + (unsigned)side);
+                }
+                order.push_back({best, u});
+            }
+            std::sort(order.begin(), order.end());
+            std::vector<int> out;
+            for (auto& p : order) out.push_back(p.second);
+            return out;
+        };
+        // unassigned items carry the NULL id = the cluster count, which is about to grow: park them at -1 meanwhile
+        // (the reference leaves them at the old count, where they would silently join the first appended cluster)
+        if (!issues.empty()) for (int v = 0; v < V; v++) if (cl[(size_t)v] == K0) cl[(size_t)v] = -1;
+        for (int k : issues) {
+            const int fresh = K;
+            auto& mine = sus_items[(size_t)k];
+            bool found = false;
+            if (mine.size() > 1) {
+                const int it = mine.front();
+                cl[(size_t)it] = fresh;
+                mine.erase(mine.begin());
+                size_of[(size_t)k]--;
+                found = true;
+            } else if (mine.size() == 1) {
+                for (int u : ring_of(mine.front())) {
+                    const int cu = cl[(size_t)u];
+                    if (cu < 0 || cu >= K0) continue;                  // NULL, or a cluster created by this very pass (one item)
+                    if (size_of[(size_t)cu] > 1) {
+                        cl[(size_t)u] = fresh;
+                        size_of[(size_t)cu]--;
+                        if (is_suspect[(size_t)cu]) { auto& o = sus_items[(size_t)cu]; o.erase(std::find(o.begin(), o.end(), u)); }
+                        found = true;
+                        break;
+                    }
+                }
+            }
+            if (found) { K++; frozen.push_back(0); }
+        }
+        if (!issues.empty()) for (int v = 0; v < V; v++) if (cl[(size_t)v] < 0) cl[(size_t)v] = K;
+        *new_num_clusters = K;
+    } else *new_num_clusters = K0;
+    *n_issues = (int32_t)issues.size();
+    // ---- apply: frozen flags, and (if clusters were appended) the grown tables with the edited clustering
+    const int K = *new_num_clusters;
+    if (K != K0) {
+        std::vector<int64_t> fixed = c->fixed;
+        set_num_clusters_impl(c, K);
+        if (!fixed.empty()) {
+            std::vector<int> a((size_t)K, -1);
+            c->fixed = fixed;
+            for (size_t i = 0; i < fixed.size(); i++) a[i] = (int)fixed[i];
+            ACVD_CUDA(cudaMemcpy(c->anchor.p, a.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
+            c->has_anchor = true;
+        }
+        ACVD_CUDA(cudaMemcpy(c->cid.p, cl.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    ACVD_CUDA(cudaMemcpy(c->frozen.p, frozen.data(), (size_t)K, cudaMemcpyHostToDevice));
+    c->has_frozen = true;
+    c->stats_valid = false; c->sig_valid = false; c->members_valid = false; c->modlist_valid = false;
     ACVD_API_END(c)
 }
 

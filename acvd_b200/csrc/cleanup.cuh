@@ -46,26 +46,46 @@ __global__ void k_adjacency_keys(int V, int K, const int* __restrict__ row_ptr, 
         }
     }
 }
-// per face: sorted cluster triple packed 3 x 21 bits when the three clusters are distinct and valid, else ~0
+// per face: the sorted cluster triple when the three clusters are distinct and valid -- (mid << 32 | hi) as the first
+// sort key, lo as the second -- else all-ones sentinels (they sort to the end)
 __global__ void k_dual_keys(int F, int K, const int* __restrict__ tri, const int* __restrict__ cid,
-                            unsigned long long* keys, int* face_id) {
+                            unsigned long long* key_mid_hi, unsigned* key_lo, int* face_id) {
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
-        int a = cid[tri[3 * f]], b = cid[tri[3 * f + 1]], c = cid[tri[3 * f + 2]];
+        const int a = cid[tri[3 * (int64_t)f]], b = cid[tri[3 * (int64_t)f + 1]], c = cid[tri[3 * (int64_t)f + 2]];
         unsigned long long k = ~0ull;
+        unsigned l = 0xffffffffu;
         if (a >= 0 && b >= 0 && c >= 0 && a < K && b < K && c < K && a != b && a != c && b != c) {
-            int lo = min(a, min(b, c)), hi = max(a, max(b, c)), mid = a + b + c - lo - hi;
-            k = ((unsigned long long)lo << 42) | ((unsigned long long)mid << 21) | (unsigned long long)hi;
+            const int lo = min(a, min(b, c)), hi = max(a, max(b, c)), mid = a + b + c - lo - hi;
+            k = ((unsigned long long)(unsigned)mid << 32) | (unsigned)hi;
+            l = (unsigned)lo;
         }
-        keys[f] = k;
+        key_mid_hi[f] = k;
+        key_lo[f] = l;
         face_id[f] = f;
     }
 }
-// after a stable sort by key: flag[i] = 1 for the first face of every distinct valid key
-__global__ void k_dual_first(int F, const unsigned long long* __restrict__ keys, const int* __restrict__ face_id, int* first_face) {
+__global__ void k_gather_u32(int n, const int* __restrict__ idx, const unsigned* __restrict__ in, unsigned* out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[idx[i]];
+}
+// faces ordered by (lo, mid, hi), equal triples in ascending face order: the first face of every run of a valid triple
+__global__ void k_dual_first(int F, int K, const int* __restrict__ face_sorted, const int* __restrict__ tri, const int* __restrict__ cid,
+                             int* first_face, unsigned long long* n_first) {
+    unsigned cnt = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) {
-        bool first = keys[i] != ~0ull && (i == 0 || keys[i - 1] != keys[i]);
-        first_face[i] = first ? face_id[i] : 0x7fffffff;
+        auto triple = [&](int f, int* t) {
+            const int a = cid[tri[3 * (int64_t)f]], b = cid[tri[3 * (int64_t)f + 1]], c = cid[tri[3 * (int64_t)f + 2]];
+            if (!(a >= 0 && b >= 0 && c >= 0 && a < K && b < K && c < K && a != b && a != c && b != c)) return false;
+            t[0] = min(a, min(b, c)); t[2] = max(a, max(b, c)); t[1] = a + b + c - t[0] - t[2];
+            return true;
+        };
+        int t[3], u[3];
+        const int f = face_sorted[i];
+        bool first = triple(f, t);
+        if (first && i > 0 && triple(face_sorted[i - 1], u)) first = !(t[0] == u[0] && t[1] == u[1] && t[2] == u[2]);
+        first_face[i] = first ? f : 0x7fffffff;
+        cnt += first ? 1u : 0u;
     }
+    warp_count_add(n_first, cnt);
 }
 __global__ void k_dual_emit(int n, const int* __restrict__ faces, const int* __restrict__ tri, const int* __restrict__ cid, int* out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

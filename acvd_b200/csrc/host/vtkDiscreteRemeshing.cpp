@@ -215,71 +215,21 @@ void vtkDiscreteRemeshingB200::BuildDelaunayTriangulation() {
 
 // :166-383.  Every cluster is frozen; a non-manifold output vertex whose input vertices are all manifold
 // is a topology issue: it and its output neighbours are unfrozen and one new cluster is seeded next to it
-// with an item taken from it (or, if it has a single item, from a neighbouring cluster).
+// with an item taken from it (or, if it has a single item, from a neighbouring cluster).  The manifold tests
+// (vtkSurfaceBase::IsVertexManifold on the dual mesh and on the input) run on the device: acvd_detect_non_manifold.
 int vtkDiscreteRemeshingB200::DetectNonManifoldOutputVertices() {
     cout << "Starting detection of non-manifold vertices" << endl;
-    const vtkIdType nv = Input->GetNumberOfPoints();
-    int K = NumberOfClusters;
-    std::vector<std::vector<int>> items((size_t)K);
-    int* cl = Clustering->GetPointer(0);
-    int wrong = 0;
-    for (vtkIdType i = 0; i < nv; i++) {
-        if (cl[i] < 0 || cl[i] >= K) { wrong++; cl[i] = -1; }   // NULL items: re-labelled with the new NULL id below
-        else items[(size_t)cl[i]].push_back((int)i);
-    }
-    if (wrong) cout << wrong << " uncorrectly associated items" << endl;
-    Frozen.assign((size_t)K, 1);
-    std::vector<int> issues;
-    vtkIdList* nb = vtkIdList::New();
-    for (int c = 0; c < K; c++) {
-        if (Output->IsVertexManifold(c)) continue;
-        cout << "Cluster " << c << " is non manifold" << endl;
-        if (items[(size_t)c].empty()) { cout << ".... but empty. Skipping" << endl; continue; }
-        cout << items[(size_t)c].size() << " items inside" << endl;
-        bool problem = true;
-        for (int it : items[(size_t)c]) if (!Input->IsVertexManifold(it)) {
-            problem = false;
-            cout << "discarding this topology issue as the input mesh also has a topology issue here" << endl;
-            break;
+    int32_t issues = 0, newK = NumberOfClusters;
+    if (!Check(acvd_detect_non_manifold(Ctx, 1, &issues, &newK), "acvd_detect_non_manifold")) return 0;
+    if (issues) {
+        if (!Check(acvd_get_clustering(Ctx, Clustering->GetPointer(0)), "acvd_get_clustering")) return 0;
+        if (newK != NumberOfClusters) {
+            cout << newK - NumberOfClusters << " clusters added next to non-manifold output vertices" << endl;
+            NumberOfClusters = newK;
+            Clusters.resize((size_t)newK, vtkClusterInfo{{0, 0, 0}, 0, 0, -1});
         }
-        if (!problem) continue;
-        issues.push_back(c);
-        Frozen[(size_t)c] = 0;
-        Output->GetVertexNeighbours(c, nb);
-        for (vtkIdType i = 0; i < nb->GetNumberOfIds(); i++) Frozen[(size_t)nb->GetId(i)] = 0;
     }
-    for (int c : issues) {
-        const int fresh = K;
-        bool placed = false;
-        auto& mine = items[(size_t)c];
-        if (mine.size() > 1) {
-            cl[mine.front()] = fresh;
-            items.push_back({mine.front()});
-            mine.erase(mine.begin());
-            placed = true;
-        } else {
-            Input->GetVertexNeighbours(mine.front(), nb);
-            for (vtkIdType j = 0; j < nb->GetNumberOfIds() && !placed; j++) {
-                const int u = (int)nb->GetId(j), cu = cl[u];
-                if (cu < 0 || cu >= (int)items.size() || items[(size_t)cu].size() <= 1) continue;
-                cl[u] = fresh;
-                auto& other = items[(size_t)cu];
-                other.erase(std::find(other.begin(), other.end(), u));
-                items.push_back({u});
-                placed = true;
-            }
-            if (!placed) cout << "Could not find a place to add cluster " << fresh << " near cluster " << c << endl;
-        }
-        if (placed) { K++; Frozen.push_back(0); }
-    }
-    nb->Delete();
-    // unassigned items carry the NULL id, which is the (possibly grown) cluster count
-    for (vtkIdType i = 0; i < nv; i++) if (cl[i] < 0) cl[i] = K;
-    if (K != NumberOfClusters) {
-        NumberOfClusters = K;
-        Clusters.resize((size_t)K, vtkClusterInfo{{0, 0, 0}, 0, 0, -1});
-    }
-    return (int)issues.size();
+    return issues;
 }
 
 void vtkDiscreteRemeshingB200::Remesh() {
@@ -321,15 +271,7 @@ void vtkDiscreteRemeshingB200::Remesh() {
     if (ForceManifold) {
         while (int issues = DetectNonManifoldOutputVertices()) {
             cout << issues << " topology issues, restarting minimization" << endl;
-            // the cluster count may have grown: re-create the cluster tables, keep the clustering, freeze the rest
-            std::vector<int> keep(Clustering->v);
-            if (!Check(acvd_set_num_clusters(Ctx, NumberOfClusters), "acvd_set_num_clusters")) return;
-            if (!FixedClusters.empty()) {
-                std::vector<int64_t> fx(FixedClusters.begin(), FixedClusters.end());
-                Check(acvd_set_fixed_clusters(Ctx, fx.data(), (int32_t)fx.size()), "acvd_set_fixed_clusters");
-            }
-            if (!Check(acvd_set_clustering(Ctx, keep.data()), "acvd_set_clustering")) return;
-            if (!Check(acvd_set_frozen(Ctx, Frozen.data()), "acvd_set_frozen")) return;
+            // the library holds the grown cluster tables, the edited clustering and the frozen flags
             MinimizeEnergy(0);   // ConnexityConstraint = 0 (:942)
             BuildDelaunayTriangulation();
         }

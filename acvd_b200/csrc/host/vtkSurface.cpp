@@ -251,9 +251,9 @@ void vtkSurface::GetVertexNeighbours(vtkIdType v, vtkIdList* out) {
     for (int i = ve_ptr[v]; i < ve_ptr[v + 1]; i++) { const auto& e = edges[(size_t)ve[i]]; out->InsertNextId(e[0] == v ? e[1] : e[0]); }
 }
 
-// A vertex is manifold when it has at least two edges, none of them carries more than two faces, and its
-// incident faces form one fan (open or closed) that reaches every incident edge
-// (same predicate as the fan walk at reference Common/vtkSurfaceBase.cxx:259-317).
+// A vertex is manifold when it has at least two edges, every one of them carries exactly two faces (the reference's
+// IsEdgeManifold, vtkSurfaceBase.h:521-528, refuses boundary edges too) and its incident faces form one closed fan that
+// reaches every incident edge (same predicate as the fan walk at reference Common/vtkSurfaceBase.cxx:259-317).
 bool vtkSurface::IsVertexManifold(vtkIdType v) {
     BuildTopology();
     const int ne = ve_ptr[v + 1] - ve_ptr[v];
@@ -261,7 +261,7 @@ bool vtkSurface::IsVertexManifold(vtkIdType v) {
     std::vector<int> nb((size_t)ne);
     for (int i = 0; i < ne; i++) {
         const int e = ve[(size_t)ve_ptr[v] + i];
-        if (edge_nfaces[(size_t)e] > 2) return false;
+        if (edge_nfaces[(size_t)e] != 2) return false;
         nb[(size_t)i] = edges[(size_t)e][0] == v ? edges[(size_t)e][1] : edges[(size_t)e][0];
     }
     // link graph: neighbours a, b are joined when the face (v, a, b) exists

@@ -151,37 +151,68 @@ __global__ void __launch_bounds__(kThreads) k_cluster_pass(ClusterPassArgs P) {
         if (P.do_cc && n > 1) {
             int* par = small ? s_a[w] : P.cc_par + b;
             int* sz = small ? s_b[w] : P.cc_sz + b;
-            for (int i = lane; i < n; i += 32) par[i] = i;
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) {
-                const int v = mv[i];
-                const int beg = P.row_ptr[v], deg = P.row_ptr[v + 1] - beg;
-                // staged gathers: neighbours, then their cluster ids, then the slots of the same-cluster ones
-                int nb[kRingW], pu[kRingW];
-#pragma unroll
-                for (int k = 0; k < kRingW; k++) { const int u = k < deg ? P.col[beg + k] : v; nb[k] = u < v ? u : -1; }
-#pragma unroll
-                for (int k = 0; k < kRingW; k++) pu[k] = (nb[k] >= 0 && P.cid[nb[k]] == c) ? nb[k] : -1;
-#pragma unroll
-                for (int k = 0; k < kRingW; k++) pu[k] = pu[k] >= 0 ? P.pos[pu[k]] - b : -1;
-#pragma unroll
-                for (int k = 0; k < kRingW; k++) if (pu[k] >= 0) lcc_union(par, i, pu[k]);
-                for (int e = beg + kRingW; e < beg + deg; e++) {       // rows longer than kRingW
-                    const int u = P.col[e];
-                    if (u < v && P.cid[u] == c) lcc_union(par, i, P.pos[u] - b);
-                }
-            }
-            __syncwarp();
-            int n_roots = 0;
+            // (a) initial forest without atomics: every member points at its smallest same-cluster neighbour with a
+            //     smaller id, or at itself.  Every link is a real edge, so a forest with a single root spans the cluster:
+            //     connected, nothing else to do -- the common case.
+            int n_local_min = 0;
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
-                int r = -1;
-                if (i < n) r = lcc_find(par, i);
-                __syncwarp();
-                if (i < n) { par[i] = r; sz[i] = 0; }
-                n_roots += __popc(__ballot_sync(0xffffffffu, i < n && r == i));
+                int best = i;
+                if (i < n) {
+                    const int v = mv[i];
+                    const int beg = P.row_ptr[v], deg = P.row_ptr[v + 1] - beg;
+                    int nb[kRingW], pu[kRingW];
+#pragma unroll
+                    for (int k = 0; k < kRingW; k++) { const int u = k < deg ? P.col[beg + k] : v; nb[k] = u < v ? u : -1; }
+#pragma unroll
+                    for (int k = 0; k < kRingW; k++) pu[k] = (nb[k] >= 0 && P.cid[nb[k]] == c) ? nb[k] : -1;
+#pragma unroll
+                    for (int k = 0; k < kRingW; k++) pu[k] = pu[k] >= 0 ? P.pos[pu[k]] - b : i;
+#pragma unroll
+                    for (int k = 0; k < kRingW; k++) best = min(best, pu[k]);
+                    for (int e = beg + kRingW; e < beg + deg; e++) {       // rows longer than kRingW
+                        const int u = P.col[e];
+                        if (u < v && P.cid[u] == c) best = min(best, P.pos[u] - b);
+                    }
+                    par[i] = best;
+                }
+                n_local_min += __popc(__ballot_sync(0xffffffffu, i < n && best == i));
             }
             __syncwarp();
+            // (b) several local minima: join the trees over all same-cluster edges (union-find on the local indices)
+            if (n_local_min > 1) {
+                for (int i = lane; i < n; i += 32) {
+                    const int v = mv[i];
+                    const int beg = P.row_ptr[v], deg = P.row_ptr[v + 1] - beg;
+                    int nb[kRingW], pu[kRingW];
+#pragma unroll
+                    for (int k = 0; k < kRingW; k++) { const int u = k < deg ? P.col[beg + k] : v; nb[k] = u < v ? u : -1; }
+#pragma unroll
+                    for (int k = 0; k < kRingW; k++) pu[k] = (nb[k] >= 0 && P.cid[nb[k]] == c) ? nb[k] : -1;
+#pragma unroll
+                    for (int k = 0; k < kRingW; k++) pu[k] = pu[k] >= 0 ? P.pos[pu[k]] - b : -1;
+#pragma unroll 1
+                    for (int k = 0; k < kRingW; k++) if (pu[k] >= 0) lcc_union(par, i, pu[k]);
+                    for (int e = beg + kRingW; e < beg + deg; e++) {
+                        const int u = P.col[e];
+                        if (u < v && P.cid[u] == c) lcc_union(par, i, P.pos[u] - b);
+                    }
+                }
+                __syncwarp();
+            }
+            int n_roots = 1;
+            if (n_local_min > 1) {
+                n_roots = 0;
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
+                    int r = -1;
+                    if (i < n) r = lcc_find(par, i);
+                    __syncwarp();
+                    if (i < n) { par[i] = r; sz[i] = 0; }
+                    n_roots += __popc(__ballot_sync(0xffffffffu, i < n && r == i));
+                }
+                __syncwarp();
+            }
             if (n_roots > 1) {
                 // sizes; an anchored item weighs 1e9 so that its component always wins (:440-447)
                 const int anchored = P.anchor ? P.anchor[c] : -1;

@@ -98,6 +98,7 @@ int acvd_get_clustering(acvd_ctx* ctx, int32_t* clustering /*V*/);
 int acvd_save_clustering(acvd_ctx* ctx);
 int acvd_restore_clustering(acvd_ctx* ctx);
 int acvd_set_frozen(acvd_ctx* ctx, const uint8_t* frozen /*K, NULL clears*/);
+int acvd_get_frozen(acvd_ctx* ctx, uint8_t* frozen /*K*/);
 int acvd_set_fixed_clusters(acvd_ctx* ctx, const int64_t* anchor_items, int32_t n);
 
 /* ---- initial sampling: ComputeInitialRandomSampling (Common/vtkUniformClustering.h:1178-1316).
@@ -197,6 +198,20 @@ int acvd_boundary_flags(acvd_ctx* ctx, uint8_t* flags /*V*/);
 int acvd_cluster_adjacency(acvd_ctx* ctx, int64_t* out, int64_t cap, int64_t* n);
 /* dual-mesh triangles in first-occurrence order over input faces; out=NULL queries the count */
 int acvd_dual_triangles(acvd_ctx* ctx, int32_t* out /*3*cap*/, int64_t cap, int64_t* n);
+
+/* vtkSurfaceBase::IsVertexManifold (Common/vtkSurfaceBase.cxx:259-317) as DetectNonManifoldOutputVertices uses it
+ * (DiscreteRemeshing/vtkDiscreteRemeshing.h:166-383, the -m 1 loop): per input vertex, and per output vertex of the dual
+ * mesh of the current clustering (with force_manifold_edges the dual edges between adjacent clusters that share no
+ * triangle are part of the mesh, :1114-1133).  flags: 1 manifold, 0 not, 2 = more than 64 edges (caller's fallback). */
+int acvd_input_manifold_flags(acvd_ctx* ctx, uint8_t* flags /*V*/);
+int acvd_output_manifold_flags(acvd_ctx* ctx, int32_t force_manifold_edges, uint8_t* flags /*K*/);
+/* vtkDiscreteRemeshing::DetectNonManifoldOutputVertices (DiscreteRemeshing/vtkDiscreteRemeshing.h:166-383), one step of
+ * the -m 1 loop on the current clustering: every cluster is frozen except the non-manifold output vertices (whose items
+ * are all manifold input vertices) and their output neighbours; one new cluster is appended per issue, seeded with the
+ * first item of the offending cluster or, for a one-item cluster, with its first ring neighbour whose cluster has more
+ * than one item.  The context's cluster count, clustering and frozen flags are updated (fetch them with
+ * acvd_get_clustering); the caller then re-enters acvd_minimize with connexity 0 (:942-943). */
+int acvd_detect_non_manifold(acvd_ctx* ctx, int32_t force_manifold_edges, int32_t* n_issues, int32_t* new_num_clusters);
 
 /* ---- measurement hook ---------------------------------------------------------------------- */
 /* Times `reps` back-to-back launches of one kernel on the current state with CUDA events on the library's

@@ -254,7 +254,7 @@ struct Ctx {
     int V = 0, F = 0, E = 0;
     std::vector<float> xyz;
     std::vector<int> tri;
-    std::vector<int> ev1, ev2, ep1, ep2;     // Edges[e].Vertex1/2, Poly1/2
+    std::vector<int> ev1, ev2, ep1, ep2, enm; // Edges[e].Vertex1/2, Poly1/2, size of NonManifoldFaces
     std::vector<int64_t> ring_ptr;           // V+1, capacity slots
     std::vector<int> ring_len, ring;         // edge ids in insertion order (vtkSurfaceBase.cxx:1057-1068)
     // ---- metric ----
@@ -293,7 +293,7 @@ struct Ctx {
         for (int v = 0; v < V; v++) ring_ptr[v + 1] = ring_ptr[v] + cap[v];
         ring.assign(ring_ptr[V], -1);
         ring_len.assign(V, 0);
-        ev1.clear(); ev2.clear(); ep1.clear(); ep2.clear();
+        ev1.clear(); ev2.clear(); ep1.clear(); ep2.clear(); enm.clear();
         ev1.reserve(3 * (size_t)F / 2 + 16); ev2.reserve(3 * (size_t)F / 2 + 16);
         ep1.reserve(3 * (size_t)F / 2 + 16); ep2.reserve(3 * (size_t)F / 2 + 16);
         for (int f = 0; f < F; f++) {
@@ -310,10 +310,11 @@ struct Ctx {
                 if (found >= 0) {
                     if (ep1[found] < 0) ep1[found] = f;
                     else if (ep2[found] < 0) ep2[found] = f;
-                    continue;            // non-manifold extra faces ignored by this path
+                    else enm[found]++;   // NonManifoldFaces list (:1187-1196): only IsEdgeManifold looks at it
+                    continue;
                 }
                 int e = (int)ev1.size();
-                ev1.push_back(a); ev2.push_back(b); ep1.push_back(f); ep2.push_back(-1);
+                ev1.push_back(a); ev2.push_back(b); ep1.push_back(f); ep2.push_back(-1); enm.push_back(0);
                 ring[ring_ptr[a] + ring_len[a]++] = e;
                 ring[ring_ptr[b] + ring_len[b]++] = e;
             }
@@ -1032,6 +1033,184 @@ struct Ctx {
 
 }  // namespace
 
+int orc_dual_triangles_impl(const Ctx* c, int* out, int cap);
+
+// ---------------------------------------------------------------------------------------------------------
+// The slice of vtkSurfaceBase the -m 1 loop walks on: edge table with Poly1 / Poly2 / NonManifoldFaces and vertex
+// rings in creation order (AddEdge Common/vtkSurfaceBase.cxx:1166-1221, AddPolygon :1235-1300, IsEdge
+// vtkSurfaceBase.h:543-557, GetThirdPoint :384-400, Conquer :402-425, IsEdgeManifold :521-528,
+// IsVertexManifold vtkSurfaceBase.cxx:259-317), restated literally.
+struct MiniSurf {
+    std::vector<int> v1, v2, p1, p2, nm;
+    std::vector<std::vector<int>> ring;
+    std::vector<std::array<int, 3>> faces;
+    explicit MiniSurf(int nv) : ring(nv) {}
+    int is_edge(int a, int b) const {
+        const auto& r = ring[a];
+        for (int i = (int)r.size() - 1; i >= 0; i--) { int e = r[i]; if (v1[e] == b || v2[e] == b) return e; }
+        return -1;
+    }
+    int add_edge(int a, int b, int f) {
+        if (a == b) return -1;
+        int e = is_edge(a, b);
+        if (e >= 0) {
+            if (p1[e] < 0) { p1[e] = f; return e; }
+            if (p2[e] >= 0) { nm[e]++; return e; }
+            p2[e] = f; return e;
+        }
+        e = (int)v1.size();
+        v1.push_back(a); v2.push_back(b); p1.push_back(f); p2.push_back(-1); nm.push_back(0);
+        ring[a].push_back(e); ring[b].push_back(e);
+        return e;
+    }
+    int add_face(int a, int b, int c) {
+        int f = (int)faces.size();
+        faces.push_back({a, b, c});
+        add_edge(a, b, f); add_edge(b, c, f); add_edge(c, a, f);
+        return f;
+    }
+    int third_point(int f, int a, int b) const {
+        const auto& t = faces[f];
+        if (a != t[0] && b != t[0]) return t[0];
+        if (a != t[1] && b != t[1]) return t[1];
+        return t[2];
+    }
+    void conquer(int f1, int a, int b, int& f2, int& v3) const {
+        int e = is_edge(a, b);
+        if (e < 0) { f2 = -1; v3 = -1; return; }
+        f2 = p2[e];
+        if (f2 == -1) { v3 = -1; return; }
+        if (f2 == f1) f2 = p1[e];
+        v3 = third_point(f2, a, b);
+    }
+    bool edge_manifold(int e) const { return !(p2[e] < 0 || nm[e] != 0); }
+    bool vertex_manifold(int iv) const {
+        const auto& r = ring[iv];
+        int remaining = (int)r.size();
+        if (remaining < 2) return false;
+        for (int e : r) if (!edge_manifold(e)) return false;
+        int first_edge = r[0];
+        int first_vertex = v1[first_edge], a = v2[first_edge];
+        if (first_vertex == iv) first_vertex = a;
+        a = first_vertex;
+        remaining--;
+        int f1 = p1[first_edge], f2 = p2[first_edge], f3;
+        int b = third_point(f1, iv, first_vertex);
+        do {
+            if (--remaining == 0) return true;
+            conquer(f1, iv, b, f3, a);
+            f1 = f3; b = a;
+        } while (f1 >= 0 && b != first_vertex);
+        if (f2 < 0 || b == first_vertex) return false;
+        a = first_vertex;
+        b = third_point(f2, iv, first_vertex);
+        do {
+            if (--remaining == 0) return true;
+            conquer(f2, iv, b, f3, a);
+            f2 = f3; b = a;
+        } while (f2 >= 0 && b != first_vertex);
+        return false;
+    }
+    void neighbours(int v, std::vector<int>& out) const {
+        out.clear();
+        for (int e : ring[v]) out.push_back(v1[e] == v ? v2[e] : v1[e]);
+    }
+};
+
+// the input mesh as a MiniSurf (same face order as Ctx::build_edges, degenerate faces skipped)
+static MiniSurf input_surface(const Ctx* c) {
+    MiniSurf s(c->V);
+    for (int f = 0; f < c->F; f++) {
+        const int* t = &c->tri[3 * f];
+        if (t[0] == t[1]) { s.faces.push_back({t[0], t[1], t[2]}); continue; }
+        s.add_face(t[0], t[1], t[2]);
+    }
+    return s;
+}
+
+// BuildDelaunayTriangulation, vertex mode (DiscreteRemeshing/vtkDiscreteRemeshing.h:1003-1133): one output face per
+// input face whose three clusters are distinct (first occurrence), and under ForceManifold the dual edges between
+// adjacent clusters that share no output face (:1114-1133)
+static MiniSurf output_surface(const Ctx* c, int force_manifold) {
+    MiniSurf s(c->K);
+    std::vector<int> tri(3 * (size_t)(4 * c->K + 64));
+    int n = orc_dual_triangles_impl(c, tri.data(), (int)(tri.size() / 3));
+    if (n > (int)(tri.size() / 3)) { tri.resize(3 * (size_t)n); n = orc_dual_triangles_impl(c, tri.data(), n); }
+    for (int i = 0; i < n; i++) s.add_face(tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]);
+    if (force_manifold)
+        for (int e = 0; e < c->E; e++) {
+            int a = c->clustering[c->ev1[e]], b = c->clustering[c->ev2[e]];
+            if (a != b && a >= 0 && a < c->K && b >= 0 && b < c->K && s.is_edge(a, b) < 0) s.add_edge(a, b, -1);
+        }
+    return s;
+}
+
+// DetectNonManifoldOutputVertices (DiscreteRemeshing/vtkDiscreteRemeshing.h:166-383): freezes every cluster, unfreezes
+// the non-manifold output vertices (whose items are all manifold input vertices) and their output neighbours, and
+// appends one new cluster per issue, seeded with the first item of the offending cluster or, for a single-item
+// cluster, with the first ring neighbour whose cluster has more than one item.  Grows K; returns the issue count.
+static int detect_non_manifold(Ctx* c, int force_manifold, std::vector<int>* flagged) {
+    MiniSurf out = output_surface(c, force_manifold);
+    MiniSurf in = input_surface(c);
+    int K = c->K;
+    std::vector<std::vector<int>> items(K);
+    c->frozen.assign(K, 1);
+    for (int i = 0; i < c->V; i++) { int cl = c->clustering[i]; if (cl >= 0 && cl < K) items[cl].push_back(i); }
+    std::vector<int> issues, nb;
+    for (int cl = 0; cl < K; cl++) {
+        if (out.vertex_manifold(cl)) continue;
+        if (items[cl].empty()) continue;
+        bool problem = true;
+        for (int it : items[cl]) if (!in.vertex_manifold(it)) { problem = false; break; }
+        if (!problem) continue;
+        issues.push_back(cl);
+        c->frozen[cl] = 0;
+        out.neighbours(cl, nb);
+        for (int x : nb) c->frozen[x] = 0;
+    }
+    if (flagged) *flagged = issues;
+    // unassigned items carry the NULL id = the cluster count, which is about to grow: parked at -1 meanwhile (the
+    // reference leaves them at the old count, where they would silently join the first appended cluster; fixed on
+    // both sides, SURVEY A.4 "fix in both and say so")
+    const int null_old = K;
+    if (!issues.empty()) for (int i = 0; i < c->V; i++) if (c->clustering[i] == null_old) c->clustering[i] = -1;
+    for (int cl : issues) {
+        const int fresh = K;
+        items.emplace_back();
+        bool found = false;
+        if (items[cl].size() > 1) {
+            int it = items[cl][0];
+            c->clustering[it] = fresh;
+            items[fresh].push_back(it);
+            items[cl].erase(items[cl].begin());
+            found = true;
+        } else {
+            int it = items[cl][0];
+            for (int k = 0; k < c->ring_len[it] && !found; k++) {
+                int u = c->other(c->ring[c->ring_ptr[it] + k], it);
+                int cu = c->clustering[u];
+                if (cu < 0 || cu >= null_old) continue;     // NULL, or a cluster created by this very pass (one item)
+                if (items[cu].size() > 1) {
+                    c->clustering[u] = fresh;
+                    items[cu].erase(std::find(items[cu].begin(), items[cu].end(), u));
+                    items[fresh].push_back(u);
+                    found = true;
+                }
+            }
+        }
+        if (found) { K++; c->frozen.push_back(0); }
+        else items.pop_back();
+    }
+    if (!issues.empty()) for (int i = 0; i < c->V; i++) if (c->clustering[i] < 0) c->clustering[i] = K;
+    if (K != c->K) {
+        int oldK = c->K;
+        c->clusters.resize(K); c->sizes.resize(K, 0); c->last_mod.resize(K, c->n_loops);
+        for (int cl = oldK; cl < K; cl++) { c->reset_cluster(c->clusters[cl]); c->clusters[cl].anchor = -1; c->clusters[cl].rank_def = 0; }
+        c->K = K;
+    }
+    return (int)issues.size();
+}
+
 extern "C" {
 
 void* orc_create(int V, int F, const float* xyz, const int* tri) {
@@ -1126,8 +1305,9 @@ void orc_mt19937_first(unsigned* out, int n) { std::mt19937 r; r.seed(0); for (i
 // Dual-mesh triangle extraction, vertex mode (vtkDiscreteRemeshing.h:1003-1100, 956-1000):
 // per input face in order, the clusters of its 3 vertices (unique, < K); exactly 3 -> AddFace
 // unless an output face with the same vertex set exists.  Returns number of output triangles.
-int orc_dual_triangles(void* h, int* out, int cap) {
-    Ctx* c = (Ctx*)h;
+int orc_dual_triangles(void* h, int* out, int cap) { return orc_dual_triangles_impl((const Ctx*)h, out, cap); }
+}  // extern "C"
+int orc_dual_triangles_impl(const Ctx* c, int* out, int cap) {
     std::vector<std::array<int, 3>> keys;
     keys.reserve(4 * (size_t)c->K);
     std::vector<uint64_t> seen;  // sorted-triple hash set via std::sort at the end is order-destroying; use open addressing
@@ -1153,6 +1333,28 @@ int orc_dual_triangles(void* h, int* out, int cap) {
     }
     return n;
 }
+extern "C" {
+// per output vertex (cluster): vtkSurfaceBase::IsVertexManifold on the dual mesh; force_manifold adds the -m edges
+void orc_output_vertex_manifold(void* h, int force_manifold, unsigned char* out) {
+    Ctx* c = (Ctx*)h;
+    MiniSurf s = output_surface(c, force_manifold);
+    for (int k = 0; k < c->K; k++) out[k] = s.vertex_manifold(k) ? 1 : 0;
+}
+void orc_input_vertex_manifold(void* h, unsigned char* out) {
+    Ctx* c = (Ctx*)h;
+    MiniSurf s = input_surface(c);
+    for (int v = 0; v < c->V; v++) out[v] = s.vertex_manifold(v) ? 1 : 0;
+}
+// one DetectNonManifoldOutputVertices step; flagged (may be null) receives up to cap offending cluster ids
+int orc_detect_non_manifold(void* h, int force_manifold, int* flagged, int cap) {
+    Ctx* c = (Ctx*)h;
+    std::vector<int> fl;
+    int n = detect_non_manifold(c, force_manifold, &fl);
+    for (int i = 0; i < n && i < cap && flagged; i++) flagged[i] = fl[i];
+    return n;
+}
+int orc_num_clusters(void* h) { return ((Ctx*)h)->K; }
+void orc_get_frozen(void* h, unsigned char* out) { Ctx* c = (Ctx*)h; for (int i = 0; i < c->K; i++) out[i] = c->frozen[i]; }
 // boundary flag per vertex: has a ring neighbour in another cluster (bit-exact integer stage)
 void orc_boundary_flags(void* h, unsigned char* out) {
     Ctx* c = (Ctx*)h;

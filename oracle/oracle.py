@@ -54,6 +54,8 @@ def lib():
             ("orc_dual_triangles", [vp, vp, i], i), ("orc_boundary_flags", [vp, vp], None),
             ("orc_cluster_adjacency", [vp, vp, C.c_int64], C.c_int64),
             ("orc_curvature", [vp, i, vp, vp], None),
+            ("orc_output_vertex_manifold", [vp, i, vp], None), ("orc_input_vertex_manifold", [vp, vp], None),
+            ("orc_detect_non_manifold", [vp, i, vp, i], i), ("orc_num_clusters", [vp], i), ("orc_get_frozen", [vp, vp], None),
         ]:
             f = getattr(L, name)
             f.argtypes = args
@@ -235,6 +237,31 @@ class Oracle:
     def boundary_flags(self):
         out = np.zeros(self.V, dtype=np.uint8)
         lib().orc_boundary_flags(self.h, _p(out))
+        return out
+
+    # ---- the -m 1 loop (DiscreteRemeshing/vtkDiscreteRemeshing.h:166-383, Common/vtkSurfaceBase.cxx:259-317)
+    def output_vertex_manifold(self, force_manifold=1):
+        out = np.zeros(self.K, dtype=np.uint8)
+        lib().orc_output_vertex_manifold(self.h, int(force_manifold), _p(out))
+        return out
+
+    def input_vertex_manifold(self):
+        out = np.zeros(self.V, dtype=np.uint8)
+        lib().orc_input_vertex_manifold(self.h, _p(out))
+        return out
+
+    def detect_non_manifold(self, force_manifold=1):
+        """One DetectNonManifoldOutputVertices step: returns the offending cluster ids; K, clustering and the frozen
+        flags of the oracle are updated (one new cluster per issue that found an item to take)."""
+        cap = self.K + 1
+        fl = np.zeros(cap, dtype=np.int32)
+        n = lib().orc_detect_non_manifold(self.h, int(force_manifold), _p(fl), cap)
+        self.K = lib().orc_num_clusters(self.h)
+        return fl[:n].copy()
+
+    def frozen(self):
+        out = np.zeros(self.K, dtype=np.uint8)
+        lib().orc_get_frozen(self.h, _p(out))
         return out
 
     def cluster_adjacency(self):

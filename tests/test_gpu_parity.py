@@ -785,3 +785,109 @@ def test_sparse_rounds_equal_tile_filter_rounds(gpu_ctx_factory, sphere, torus, 
     for k in ("rounds", "tests", "proposals", "modifications", "convergences", "evaluated", "energy"):
         assert r0[k] == r1[k], (k, r0[k], r1[k])
     assert g.clean_clustering() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the -m 1 row: IsVertexManifold on the device, one DetectNonManifoldOutputVertices step, the ACVD post-process sums
+
+def _pinched_open_mesh(sphere):
+    """sphere with a few faces removed (boundary edges) and two distant vertices merged (a pinch)"""
+    p, t = sphere
+    t = np.delete(t, [5, 400, 401, 2000], axis=0)
+    a, b = int(t[0, 0]), int(t[-1, 0])
+    t = t.copy()
+    t[t == b] = a
+    return p, t
+
+
+def test_input_manifold_flags_match_oracle(oracle_mod, gpu_ctx_factory, sphere, spindle):
+    for p, t in (sphere, spindle, _pinched_open_mesh(sphere)):
+        o = oracle_mod.Oracle(p, t)
+        g = gpu_ctx_factory()
+        g.set_mesh(p, t)
+        want, got = o.input_vertex_manifold(), g.input_manifold_flags()
+        assert np.array_equal(want, got), int((want != got).sum())
+    assert (want == 0).sum() >= 8
+
+
+@pytest.mark.parametrize("force", [0, 1])
+def test_output_manifold_flags_match_oracle(oracle_mod, gpu_ctx_factory, sphere, force):
+    """vtkSurfaceBase::IsVertexManifold on the dual mesh (with and without the -m edges of vtkDiscreteRemeshing.h:1114-1133):
+    a converged clustering, a fragmented one, and caps + band (no dual face at all)."""
+    p, t = sphere
+    K = 120
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K)
+    cl0 = o.initial_sampling().copy()
+    o.minimize()
+    cases = [o.clustering().copy(), _scrambled_clustering(o, p, K, 9, 600)]
+    n_bad = 0
+    for cl in cases:
+        o.set_clustering(cl)
+        g.set_clustering(cl)
+        want, got = o.output_vertex_manifold(force), g.output_manifold_flags(force)
+        assert np.array_equal(want, got), int((want != got).sum())
+        n_bad += int((want == 0).sum())
+    assert cases[0] is not None and n_bad > 5
+    band = np.where(p[:, 2] > 0.4, 0, np.where(p[:, 2] < -0.4, 2, 1)).astype(np.int32)
+    o3, g3 = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", 3)
+    o3.set_clustering(band)
+    g3.set_clustering(band)
+    assert np.array_equal(o3.output_vertex_manifold(force), g3.output_manifold_flags(force))
+    assert not g3.output_manifold_flags(force).any()
+
+
+def test_detect_non_manifold_step_matches_oracle(oracle_mod, gpu_ctx_factory, sphere):
+    """One DetectNonManifoldOutputVertices step (DiscreteRemeshing/vtkDiscreteRemeshing.h:166-383) from the same
+    clustering: same issues, same grown cluster count, same edited clustering, same frozen flags -- then the -m loop
+    (re-enter MinimizeEnergy with the connexity constraint off, detect again) ends on a manifold dual mesh."""
+    p, t = sphere
+    K = 150
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K)
+    o.initial_sampling()
+    cl = _scrambled_clustering(o, p, K, 21, 500)
+    # include a one-item cluster among the offenders (exercises the "take a ring neighbour" branch)
+    lone = int(np.flatnonzero(np.bincount(cl, minlength=K) > 3)[0])
+    keep = int(np.flatnonzero(cl == lone)[0])
+    rp, col = g.csr()
+    other = cl[col[rp[keep]]]
+    cl[(cl == lone) & (np.arange(p.shape[0]) != keep)] = other if other != lone else (lone + 1) % K
+    o.set_clustering(cl)
+    g.set_clustering(cl)
+    issues_o = o.detect_non_manifold(1)
+    n_g = g.detect_non_manifold(1)
+    assert n_g == issues_o.size and n_g > 3
+    assert g.K == o.K and g.K > K
+    assert np.array_equal(g.clustering(), o.clustering())
+    assert np.array_equal(g.frozen(), o.frozen())
+    # the loop of vtkDiscreteRemeshing.h:937-950 on the device side
+    for _ in range(40):
+        g.minimize(connexity=0)
+        if g.detect_non_manifold(1) == 0:
+            break
+    else:
+        raise AssertionError("-m loop did not end")
+    assert g.output_manifold_flags(1).all()
+    cg = g.clustering()
+    assert cg.min() >= 0 and cg.max() < g.K and np.bincount(cg, minlength=g.K).min() >= 1
+    n_tri = g.dual_triangles().shape[0]
+    assert n_tri == 2 * g.K - 4                     # closed genus-0 manifold output
+
+
+def test_cluster_quadrics_match_item_sums(oracle_mod, gpu_ctx_factory, sphere):
+    """ACVD's quadric post-process (Examples/ACVD.cxx:237-262) sums, per cluster, the quadrics of the faces around every
+    item: that is the sum of the QEM item quadrics (vtkQEMetricForClustering.h:151-167) over the cluster's items."""
+    p, t = sphere
+    K = 90
+    o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, "iso", K)
+    cl = o.initial_sampling().copy()
+    o.fill_holes()
+    cl = o.clustering().copy()
+    g.set_clustering(cl)
+    q = g.cluster_quadrics()
+    oq = oracle_mod.Oracle(p, t)
+    oq.build_metric("qem")
+    items = oq.items()[:, 4:13]
+    want = np.zeros((K, 9))
+    np.add.at(want, cl, items)
+    assert rel_err(q, want) <= REL
+    assert np.array_equal(g.cluster_quadrics(10), q[:10])

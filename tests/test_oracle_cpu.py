@@ -418,3 +418,58 @@ def test_baseline_fixture_c1_matches_live_oracle(oracle_mod):
     assert hashlib.sha256(o.clustering().tobytes()).hexdigest() == fx["C1"]["sha256_clustering"]
     for k in ("C2", "C3"):
         assert fx[k]["convergences"] >= 3 and fx[k]["loops"] > 10 and fx[k]["energy"] < 0
+
+
+# ---------------------------------------------------------------- the -m 1 loop (vtkDiscreteRemeshing.h:166-383)
+def test_vertex_manifold_known_answers(oracle_mod):
+    """vtkSurfaceBase::IsVertexManifold restated literally (Common/vtkSurfaceBase.cxx:259-317): a closed sphere is
+    manifold everywhere; for the reference an edge with a single face is not "manifold" (IsEdgeManifold,
+    vtkSurfaceBase.h:521-528), so the three corners of a removed face are flagged; a pinch (two fans on one vertex) too."""
+    from acvd_b200 import meshgen
+    p, t = meshgen.geodesic_icosphere(4)
+    o = oracle_mod.Oracle(p, t)
+    assert o.input_vertex_manifold().all()
+    t2 = np.delete(t, 7, axis=0)
+    o2 = oracle_mod.Oracle(p, t2)
+    f2 = o2.input_vertex_manifold()
+    assert set(np.flatnonzero(f2 == 0)) == set(t[7])
+    # pinch: vertex b is merged into vertex a (far apart): a keeps two separate closed fans
+    a, b = int(t[0, 0]), int(t[-1, 0])
+    nb_a = set(np.unique(t[(t == a).any(axis=1)]))
+    assert b not in nb_a and not (nb_a & set(np.unique(t[(t == b).any(axis=1)])))
+    t3 = t.copy()
+    t3[t3 == b] = a
+    f3 = oracle_mod.Oracle(p, t3).input_vertex_manifold()
+    assert f3[a] == 0 and f3[b] == 0 and f3.sum() == p.shape[0] - 2     # b has no edge left: fewer than two edges
+
+
+def test_output_manifold_and_detection_step(oracle_mod):
+    from acvd_b200 import meshgen
+    p, t = meshgen.geodesic_icosphere(12)
+    V = p.shape[0]
+    # (1) a converged clustering of a sphere: closed manifold dual mesh (Euler: 2K - 4 triangles), nothing to repair
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric("iso")
+    o.set_num_clusters(40)
+    o.initial_sampling()
+    o.minimize()
+    assert o.dual_triangles().shape[0] == 2 * 40 - 4
+    assert o.output_vertex_manifold(1).all() and o.output_vertex_manifold(0).all()
+    assert o.detect_non_manifold(1).size == 0 and o.K == 40 and o.frozen().all()
+    # (2) two caps and a band: no three clusters meet, the dual mesh has no face: every output vertex is an issue
+    cl = np.where(p[:, 2] > 0.4, 0, np.where(p[:, 2] < -0.4, 2, 1)).astype(np.int32)
+    o = oracle_mod.Oracle(p, t)
+    o.build_metric("iso")
+    o.set_num_clusters(3)
+    o.set_clustering(cl)
+    assert o.dual_triangles().shape[0] == 0
+    assert not o.output_vertex_manifold(1).any()
+    issues = o.detect_non_manifold(1)
+    assert list(issues) == [0, 1, 2] and o.K == 6
+    new = o.clustering()
+    assert not o.frozen().any()
+    # one item moved into each new cluster: the first (lowest index) item of the offending cluster
+    for k in range(3):
+        first = int(np.flatnonzero(cl == k)[0])
+        assert new[first] == 3 + k and (new == 3 + k).sum() == 1
+    assert (new != cl).sum() == 3
