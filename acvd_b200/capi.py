@@ -63,6 +63,7 @@ SYMBOLS = [
     ("acvd_get_csr", C.c_int, [_vp, _vp, _vp]),
     ("acvd_subdivide", C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     ("acvd_get_subdivision", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    ("acvd_split_long_edges", C.c_int, [_vp, _d, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     ("acvd_curvature", C.c_int, [_vp, _i32, _vp, _vp]),
     ("acvd_build_items", C.c_int, [_vp, C.c_int, _d, _vp, _vp]),
     ("acvd_set_items", C.c_int, [_vp, C.c_int, _vp]),
@@ -175,6 +176,19 @@ class Context:
         p2 = np.zeros(nv.value, dtype=np.int32)
         self._ck(self.L.acvd_get_subdivision(self.h, _p(p), _p(t), _p(p1), _p(p2)))
         return p, t, p1, p2
+
+    def split_long_edges(self, ratio, fetch=True):
+        """vtkSurface::SplitLongEdges of the context's mesh: (points, triangles, parent1, parent2, passes), or the sizes."""
+        nv, nf, npass = _i32(), _i32(), _i32()
+        self._ck(self.L.acvd_split_long_edges(self.h, float(ratio), C.byref(nv), C.byref(nf), C.byref(npass)))
+        if not fetch:
+            return nv.value, nf.value, npass.value
+        p = np.zeros((nv.value, 3), dtype=np.float32)
+        t = np.zeros((nf.value, 3), dtype=np.int32)
+        p1 = np.zeros(nv.value, dtype=np.int32)
+        p2 = np.zeros(nv.value, dtype=np.int32)
+        self._ck(self.L.acvd_get_subdivision(self.h, _p(p), _p(t), _p(p1), _p(p2)))
+        return p, t, p1, p2, npass.value
 
     def curvature(self, ring_size=3, principal_directions=True):
         """vtkCurvatureMeasure (polynomial fitting, vertices, n-ring): (indicator[V] float64, info[V, 6] float32 or None)."""

@@ -40,7 +40,7 @@ static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("AC
 
 // ACVD_TRACE=1: wall-clock trace of the host driver's stages on stderr (the reference's ConsoleOutput>1
 // per-loop lines are the analogue, Common/vtkUniformClustering.h:752-760)
-constexpr int64_t kReplicatedTailProposals = 4096;
+constexpr int64_t kReplicatedTailEvaluated = 400000;   // multi-GPU: below this many evaluated vertices per round the phase goes replicated
 constexpr int kRoundSlots = 8;            // exact rounds that may be in flight between two host synchronisations
 constexpr int kTailBatch = 4;             // rounds launched back to back in the long tail of the last phases
 constexpr int kSparseChunkAlloc = 512;    // rounds of one sparse launch (kSparseChunk)
@@ -151,6 +151,8 @@ extern "C" int acvd_destroy(acvd_ctx* c) {
 
 // ---------------------------------------------------------------------------------------------
 // mesh
+static void dist_sliced_upload(acvd_ctx* c, void* d, const void* h, size_t n_items, size_t item_bytes);   // dist.cuh
+
 extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz, const int32_t* tri) {
     ACVD_API_BEGIN(c)
     if (V <= 0 || F <= 0 || !xyz || !tri) throw std::runtime_error("acvd_set_mesh: bad arguments");
@@ -164,8 +166,13 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     c->tri.alloc(3 * (size_t)F);
     {
         TraceScope ts(c, "set_mesh: upload");
-        ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        if (c->world > 1) {   // every rank uploads its vertex / face range over its own PCIe link; NVLink completes the copies
+            dist_sliced_upload(c, c->xyz.p, xyz, (size_t)V, 3 * sizeof(float));
+            dist_sliced_upload(c, c->tri.p, tri, (size_t)F, 3 * sizeof(int));
+        } else {
+            ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        }
         // vertex indices outside [0, V) would index the counting build out of bounds: reject them here
         ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(unsigned long long), c->stream));
         k_check_range<<<grid_for(3 * (int64_t)F), kThreads, 0, c->stream>>>(3 * (int64_t)F, c->tri.p, V, c->scalars.p);
@@ -248,6 +255,7 @@ extern "C" int acvd_get_csr(acvd_ctx* c, int32_t* row_ptr, int32_t* col) {
 
 // ---------------------------------------------------------------------------------------------
 // 1 -> 4 subdivision of the context's mesh (kept on the device until fetched)
+static void exclusive_sum(acvd_ctx* c, const int* in, int* out, int64_t n);
 static void inclusive_sum(acvd_ctx* c, const int* in, int* out, int64_t n) {
     size_t tb = 0;
     ACVD_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, in, out, n, c->stream));
@@ -255,18 +263,23 @@ static void inclusive_sum(acvd_ctx* c, const int* in, int* out, int64_t n) {
     ACVD_CUDA(cub::DeviceScan::InclusiveSum(t, tb, in, out, n, c->stream));
 }
 
-extern "C" int acvd_subdivide(acvd_ctx* c, int32_t* n_vertices, int32_t* n_faces) {
-    ACVD_API_BEGIN(c)
-    if (!c->V || !n_vertices || !n_faces) throw std::runtime_error("acvd_subdivide: set the mesh first");
-    const int V = c->V, F = c->F;
+// The reference's edge ids of a triangle list on the device: edges are numbered in the order AddEdge first sees them
+// over the faces (Common/vtkSurfaceBase.cxx:1166-1221).  Sort of the 3F undirected half-edges (stable: a run starts with
+// the first occurrence of its edge), runs ranked by their first slot.
+struct EdgeTable {
+    int E = 0;
+    DevBuf<int> first_sorted;     // E: half-edge slot 3f + k of the first occurrence of edge e
+    DevBuf<int> edge_of_slot;     // 3F: edge id of every half-edge slot (undefined for inactive faces / self loops)
+};
+static void build_edge_table(acvd_ctx* c, const int* tri, int F, EdgeTable& T) {
     const int64_t n = 3 * (int64_t)F;
-    if (n >= ((int64_t)1 << 31)) throw std::runtime_error("acvd_subdivide: mesh too large");
+    if (n >= ((int64_t)1 << 31)) throw std::runtime_error("edge table: mesh too large");
     DevBuf<unsigned long long> keys, keys_alt;
-    DevBuf<int> slots, slots_alt, head, run_incl, first_slot, run_id, first_sorted, run_sorted, edge_of_run, edge_of_slot, flag, rank_incl;
+    DevBuf<int> slots, slots_alt, head, run_incl, first_slot, run_id, run_sorted, edge_of_run;
     keys.alloc(n); keys_alt.alloc(n); slots.alloc(n); slots_alt.alloc(n); head.alloc(n); run_incl.alloc(n);
-    k_sub_edge_keys<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, keys.p, slots.p);
+    k_sub_edge_keys<<<grid_for(F), kThreads, 0, c->stream>>>(F, tri, keys.p, slots.p);
     ACVD_LAUNCH_CHECK();
-    {   // stable: equal keys keep ascending slot order, so a run starts with the first occurrence of its edge
+    {
         cub::DoubleBuffer<unsigned long long> dk(keys.p, keys_alt.p);
         cub::DoubleBuffer<int> dv(slots.p, slots_alt.p);
         size_t tb = 0;
@@ -282,26 +295,40 @@ extern "C" int acvd_subdivide(acvd_ctx* c, int32_t* n_vertices, int32_t* n_faces
     int E = 0;
     ACVD_CUDA(cudaMemcpyAsync(&E, run_incl.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
-    if ((int64_t)V + E >= ((int64_t)1 << 31)) throw std::runtime_error("acvd_subdivide: too many vertices");
-    first_slot.alloc(std::max(E, 1)); run_id.alloc(std::max(E, 1)); first_sorted.alloc(std::max(E, 1)); run_sorted.alloc(std::max(E, 1));
-    edge_of_run.alloc(std::max(E, 1)); edge_of_slot.alloc(n);
+    T.E = E;
+    first_slot.alloc(std::max(E, 1)); run_id.alloc(std::max(E, 1)); T.first_sorted.alloc(std::max(E, 1)); run_sorted.alloc(std::max(E, 1));
+    edge_of_run.alloc(std::max(E, 1)); T.edge_of_slot.alloc(n);
     k_sub_first_slots<<<grid_for(n), kThreads, 0, c->stream>>>(n, head.p, run_incl.p, slots.p, first_slot.p, run_id.p);
     ACVD_LAUNCH_CHECK();
     if (E > 0) {
         size_t tb = 0;
-        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, first_slot.p, first_sorted.p, run_id.p, run_sorted.p, E, 0, 32, c->stream));
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, first_slot.p, T.first_sorted.p, run_id.p, run_sorted.p, E, 0, 32, c->stream));
         void* t = cub_temp(c, tb);
-        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, first_slot.p, first_sorted.p, run_id.p, run_sorted.p, E, 0, 32, c->stream));
+        ACVD_CUDA(cub::DeviceRadixSort::SortPairs(t, tb, first_slot.p, T.first_sorted.p, run_id.p, run_sorted.p, E, 0, 32, c->stream));
+        k_edge_of_run<<<grid_for(E), kThreads, 0, c->stream>>>(E, run_sorted.p, edge_of_run.p);
+        ACVD_LAUNCH_CHECK();
+        k_sub_slot_edges<<<grid_for(n), kThreads, 0, c->stream>>>(n, keys.p, run_incl.p, slots.p, edge_of_run.p, T.edge_of_slot.p);
+        ACVD_LAUNCH_CHECK();
     }
+}
+
+extern "C" int acvd_subdivide(acvd_ctx* c, int32_t* n_vertices, int32_t* n_faces) {
+    ACVD_API_BEGIN(c)
+    if (!c->V || !n_vertices || !n_faces) throw std::runtime_error("acvd_subdivide: set the mesh first");
+    const int V = c->V, F = c->F;
+    EdgeTable T;
+    build_edge_table(c, c->tri.p, F, T);
+    const int E = T.E;
+    if ((int64_t)V + E >= ((int64_t)1 << 31)) throw std::runtime_error("acvd_subdivide: too many vertices");
+    DevBuf<int> flag, rank_incl, dummy;
     const int Vn = V + E;
     c->sub_xyz.alloc(3 * (size_t)Vn); c->sub_parent1.alloc(Vn); c->sub_parent2.alloc(Vn);
     k_sub_old_points<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->xyz.p, c->sub_xyz.p, c->sub_parent1.p, c->sub_parent2.p);
     ACVD_LAUNCH_CHECK();
     if (E > 0) {
-        k_sub_edges<<<grid_for(E), kThreads, 0, c->stream>>>(E, V, first_sorted.p, run_sorted.p, c->tri.p, c->xyz.p, edge_of_run.p, c->sub_xyz.p,
+        dummy.alloc(E);
+        k_sub_edges<<<grid_for(E), kThreads, 0, c->stream>>>(E, V, T.first_sorted.p, c->tri.p, c->xyz.p, c->sub_xyz.p,
                                                               c->sub_parent1.p, c->sub_parent2.p);
-        ACVD_LAUNCH_CHECK();
-        k_sub_slot_edges<<<grid_for(n), kThreads, 0, c->stream>>>(n, keys.p, run_incl.p, slots.p, edge_of_run.p, edge_of_slot.p);
         ACVD_LAUNCH_CHECK();
     }
     flag.alloc(F); rank_incl.alloc(F);
@@ -313,11 +340,104 @@ extern "C" int acvd_subdivide(acvd_ctx* c, int32_t* n_vertices, int32_t* n_faces
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     if (4 * (int64_t)n_kept >= ((int64_t)1 << 31) / 3) throw std::runtime_error("acvd_subdivide: too many faces");
     c->sub_tri.alloc(12 * (size_t)std::max(n_kept, 1));
-    k_sub_faces<<<grid_for(F), kThreads, 0, c->stream>>>(F, V, c->tri.p, flag.p, rank_incl.p, edge_of_slot.p, c->sub_tri.p);
+    k_sub_faces<<<grid_for(F), kThreads, 0, c->stream>>>(F, V, c->tri.p, flag.p, rank_incl.p, T.edge_of_slot.p, c->sub_tri.p);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     c->sub_V = Vn; c->sub_F = 4 * n_kept;
     *n_vertices = Vn; *n_faces = 4 * n_kept;
+    ACVD_API_END(c)
+}
+
+// vtkSurface::SplitLongEdges (Common/vtkSurface.cxx:444-604): passes of mark / cut on the device (mesh.cuh).  The result
+// stays on the device (fetch with acvd_get_subdivision: parents = the end points of the cut edge, itself for old points).
+extern "C" int acvd_split_long_edges(acvd_ctx* c, double ratio, int32_t* n_vertices, int32_t* n_faces, int32_t* n_passes) {
+    ACVD_API_BEGIN(c)
+    if (!c->V || !n_vertices || !n_faces || !(ratio > 0)) throw std::runtime_error("acvd_split_long_edges: bad arguments");
+    int V = c->V, F = c->F;
+    // working copies that grow pass by pass (points are appended in place; faces ping-pong)
+    DevBuf<float> xyz;
+    DevBuf<int> tri_a, tri_b, par1, par2, mark, rank_excl, n_child, child_excl;
+    DevBuf<double> len, d_sum;
+    size_t cap_v = (size_t)V + (size_t)V / 2 + 1024;
+    xyz.alloc(3 * cap_v); par1.alloc(cap_v); par2.alloc(cap_v); tri_a.alloc(3 * (size_t)F);
+    ACVD_CUDA(cudaMemcpyAsync(xyz.p, c->xyz.p, 3 * (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(tri_a.p, c->tri.p, 3 * (size_t)F * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, par1.p);
+    k_iota<<<grid_for(V), kThreads, 0, c->stream>>>(V, par2.p);
+    ACVD_LAUNCH_CHECK();
+    int* tri = tri_a.p;
+    DevBuf<int>* other = &tri_b;
+    double threshold = 0;
+    int passes = 0;
+    d_sum.alloc(1);
+    for (;; passes++) {
+        if (passes >= 64) throw std::runtime_error("acvd_split_long_edges: more than 64 passes");
+        EdgeTable T;
+        build_edge_table(c, tri, F, T);
+        const int E = T.E;
+        if (E == 0) break;
+        len.alloc(E); mark.alloc(E); rank_excl.alloc((size_t)E + 1);
+        k_split_lengths<<<grid_for(E), kThreads, 0, c->stream>>>(E, T.first_sorted.p, tri, xyz.p, len.p);
+        ACVD_LAUNCH_CHECK();
+        if (passes == 0) {      // the threshold is fixed by the mesh as given (:455-462)
+            size_t tb = 0;
+            ACVD_CUDA(cub::DeviceReduce::Sum(nullptr, tb, len.p, d_sum.p, E, c->stream));
+            void* t = cub_temp(c, tb);
+            ACVD_CUDA(cub::DeviceReduce::Sum(t, tb, len.p, d_sum.p, E, c->stream));
+            double total = 0;
+            ACVD_CUDA(cudaMemcpyAsync(&total, d_sum.p, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+            ACVD_CUDA(cudaStreamSynchronize(c->stream));
+            threshold = ratio * total / (double)E;
+        }
+        k_split_mark<<<grid_for(E), kThreads, 0, c->stream>>>(E, len.p, threshold, mark.p);
+        ACVD_LAUNCH_CHECK();
+        exclusive_sum(c, mark.p, rank_excl.p, E);
+        int last_rank = 0, last_mark = 0;
+        ACVD_CUDA(cudaMemcpyAsync(&last_rank, rank_excl.p + (E - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaMemcpyAsync(&last_mark, mark.p + (E - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        const int n_cut = last_rank + last_mark;
+        if (n_cut == 0) break;
+        if ((int64_t)V + n_cut >= ((int64_t)1 << 31)) throw std::runtime_error("acvd_split_long_edges: too many vertices");
+        if ((size_t)V + n_cut > cap_v) {      // grow the point arrays
+            const size_t cap_new = (size_t)V + n_cut + ((size_t)V + n_cut) / 2;
+            DevBuf<float> x2; DevBuf<int> p1, p2;
+            x2.alloc(3 * cap_new); p1.alloc(cap_new); p2.alloc(cap_new);
+            ACVD_CUDA(cudaMemcpyAsync(x2.p, xyz.p, 3 * (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            ACVD_CUDA(cudaMemcpyAsync(p1.p, par1.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            ACVD_CUDA(cudaMemcpyAsync(p2.p, par2.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            std::swap(xyz.p, x2.p); std::swap(xyz.n, x2.n); std::swap(par1.p, p1.p); std::swap(par1.n, p1.n); std::swap(par2.p, p2.p); std::swap(par2.n, p2.n);
+            cap_v = cap_new;
+        }
+        k_split_points<<<grid_for(E), kThreads, 0, c->stream>>>(E, V, mark.p, rank_excl.p, T.first_sorted.p, tri, xyz.p, par1.p, par2.p);
+        ACVD_LAUNCH_CHECK();
+        n_child.alloc(F); child_excl.alloc((size_t)F + 1);
+        k_split_count<<<grid_for(F), kThreads, 0, c->stream>>>(F, V, tri, T.edge_of_slot.p, mark.p, rank_excl.p, n_child.p);
+        ACVD_LAUNCH_CHECK();
+        exclusive_sum(c, n_child.p, child_excl.p, F);
+        int last_off = 0, last_n = 0;
+        ACVD_CUDA(cudaMemcpyAsync(&last_off, child_excl.p + (F - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaMemcpyAsync(&last_n, n_child.p + (F - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        const int64_t F_new = (int64_t)last_off + last_n;
+        if (3 * F_new >= ((int64_t)1 << 31)) throw std::runtime_error("acvd_split_long_edges: too many faces");
+        other->alloc(3 * (size_t)F_new);
+        k_split_emit<<<grid_for(F), kThreads, 0, c->stream>>>(F, V, tri, T.edge_of_slot.p, mark.p, rank_excl.p, child_excl.p, other->p);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        tri = other->p;
+        other = (other == &tri_b) ? &tri_a : &tri_b;
+        V += n_cut; F = (int)F_new;
+    }
+    c->sub_xyz.alloc(3 * (size_t)V); c->sub_tri.alloc(3 * (size_t)F); c->sub_parent1.alloc(V); c->sub_parent2.alloc(V);
+    ACVD_CUDA(cudaMemcpyAsync(c->sub_xyz.p, xyz.p, 3 * (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->sub_tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->sub_parent1.p, par1.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->sub_parent2.p, par2.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
+    c->sub_V = V; c->sub_F = F;
+    *n_vertices = V; *n_faces = F;
+    if (n_passes) *n_passes = passes;
     ACVD_API_END(c)
 }
 
@@ -483,7 +603,8 @@ static void set_num_clusters_impl(acvd_ctx* c, int32_t K) {
     c->K = K;
     c->cid.alloc((size_t)c->vpad);
     c->csize.alloc(K); c->mod_round.alloc(K); c->anchor.alloc(K); c->frozen.alloc(K);
-    c->csum.alloc((size_t)K * npad); c->cenergy.alloc(K); c->ccentroid.alloc(3 * (size_t)K);
+    const size_t Kp = (size_t)K + 64;   // room for the equal-chunk in-place all-gather of the statistics (world <= 64)
+    c->csum.alloc(Kp * npad); c->cenergy.alloc(Kp); c->ccentroid.alloc(3 * Kp);
     c->isum.alloc(4 * (size_t)K); c->bulk_cen.alloc(4 * (size_t)K); c->bulk_energy.alloc(K); c->bulk_energy_sum.alloc(1); c->leave_cnt.alloc(K); c->join_cnt.alloc(K);
     c->best.alloc(K); c->modbits.alloc((size_t)(K + 31) / 32 + 1); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->plist_b.alloc(V); c->work.alloc(V);
     {
@@ -647,8 +768,10 @@ static void members_build(acvd_ctx* c) {
     c->members_valid = true;
 }
 
-// one pass over the clusters: sort members [+ connected components / cleaning] [+ statistics]
-static void cluster_pass(acvd_ctx* c, bool do_cc, bool do_stats, int constrained, int qlevel, double thr) {
+// one pass over the clusters [k_begin, k_end): sort members [+ connected components / cleaning] [+ statistics]
+static void cluster_pass(acvd_ctx* c, bool do_cc, bool do_stats, int constrained, int qlevel, double thr, int k_begin = 0, int k_end = -1,
+                         bool apply_resets = true) {
+    if (k_end < 0) k_end = c->K;
     ClusterPassArgs P;
     P.V = c->V; P.K = c->K; P.off = c->memb_off.p; P.memb = c->memb.p; P.memb_tmp = c->memb_tmp.p; P.pos = c->memb_pos.p;
     P.cid = c->cid.p; P.csize = c->csize.p; P.row_ptr = c->row_ptr.p; P.col = c->col.p; P.items = c->items.p;
@@ -656,8 +779,9 @@ static void cluster_pass(acvd_ctx* c, bool do_cc, bool do_stats, int constrained
     P.anchor = c->has_anchor ? c->anchor.p : nullptr; P.xyz = c->xyz.p;
     P.cc_par = c->cc_par.p; P.cc_sz = c->cc_sz.p; P.counters = c->scalars.p + 1;
     P.do_sort = 1; P.do_cc = do_cc ? 1 : 0; P.do_stats = do_stats ? 1 : 0;
+    P.apply_resets = apply_resets ? 1 : 0; P.k_begin = k_begin; P.k_end = k_end;
     P.cfg = make_cfg(constrained, qlevel, thr);
-    const int blocks = grid_for((int64_t)c->K * 32);
+    const int blocks = grid_for((int64_t)std::max(1, k_end - k_begin) * 32);
 #define PASS(MM, EE) k_cluster_pass<MM, EE><<<blocks, kThreads, 0, c->stream>>>(P)
     switch (c->metric) {
         case M_ISO: PASS(M_ISO, M_ISO); break;
@@ -673,11 +797,19 @@ static void cluster_pass(acvd_ctx* c, bool do_cc, bool do_stats, int constrained
     if (do_stats) { c->stats_valid = true; c->stats_constrained = constrained; c->stats_qlevel = qlevel; }
 }
 
+// multi-GPU: the cluster range this rank runs the cluster pass on (equal chunks: the results are all-gathered in place)
+static int dist_cluster_chunk(const acvd_ctx* c) { return (c->K + c->world - 1) / c->world; }
+static void dist_allgather_stats(acvd_ctx* c);     // dist.cuh
+
 // ReComputeStatistics (:376-403) + ReComputeClustersSize (:353-373)
 static void recompute_statistics(acvd_ctx* c, int constrained, int qlevel, double thr) {
     TraceScope ts(c, "recompute_statistics");
     members_build(c);
-    cluster_pass(c, false, true, constrained, qlevel, thr);
+    if (c->world > 1) {     // every rank accumulates its share of the clusters; NCCL all-gather of the per-cluster statistics
+        const int chunk = dist_cluster_chunk(c), k0 = std::min(c->K, c->rank * chunk), k1 = std::min(c->K, k0 + chunk);
+        cluster_pass(c, false, true, constrained, qlevel, thr, k0, k1);
+        dist_allgather_stats(c);
+    } else cluster_pass(c, false, true, constrained, qlevel, thr);
 }
 
 extern "C" int acvd_recompute_statistics(acvd_ctx* c, int constrained, int qlevel) {
@@ -690,14 +822,32 @@ extern "C" int acvd_recompute_statistics(acvd_ctx* c, int constrained, int qleve
 
 // CleanClustering (:406-549) inside the cluster pass.  With `with_stats` the same pass also leaves fresh statistics,
 // valid when nothing had to be cleaned (n_reset == 0: the caller checks stats_valid).
+static void dist_allreduce_counters(acvd_ctx* c, unsigned long long* d, int n);   // dist.cuh
 static int clean_clustering(acvd_ctx* c, bool with_stats = false, int constrained = 1, int qlevel = 3, double thr = 0) {
     TraceScope ts(c, "clean_clustering");
     if (!c->members_valid) members_build(c);
     ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
-    cluster_pass(c, true, with_stats, constrained, qlevel, thr);
+    bool sharded = c->world > 1;
+    if (sharded) {
+        // every rank checks (and accumulates) its share of the clusters without touching the clustering; the counts are
+        // summed over the ranks.  Only when some cluster really is disconnected does every rank run the whole pass.
+        const int chunk = dist_cluster_chunk(c), k0 = std::min(c->K, c->rank * chunk), k1 = std::min(c->K, k0 + chunk);
+        cluster_pass(c, true, with_stats, constrained, qlevel, thr, k0, k1, false);
+        dist_allreduce_counters(c, c->scalars.p + 1, 2);
+    } else cluster_pass(c, true, with_stats, constrained, qlevel, thr);
     ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
-    const int disc = (int)c->h_scalars[1], n_reset = (int)c->h_scalars[2];
+    int disc = (int)c->h_scalars[1], n_reset = (int)c->h_scalars[2];
+    if (sharded) {
+        if (n_reset > 0) {
+            ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, 8 * sizeof(unsigned long long), c->stream));
+            cluster_pass(c, true, false, constrained, qlevel, thr);
+            ACVD_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            ACVD_CUDA(cudaStreamSynchronize(c->stream));
+            disc = (int)c->h_scalars[1]; n_reset = (int)c->h_scalars[2];
+            c->stats_valid = false;
+        } else if (with_stats) dist_allgather_stats(c);
+    }
     if (n_reset > 0) { c->stats_valid = false; c->members_valid = false; c->sig_valid = false; }
     if (trace_on()) fprintf(stderr, "[acvd trace]   disconnected %d, reset %d\n", disc, n_reset);
     return disc;
@@ -1403,6 +1553,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         // re-evaluates every boundary vertex, because stored proposals are only known to the rank that owns them.
         RoundResult r;
         memset(&r, 0, sizeof r);
+        int64_t synced_proposals = -1;             // multi-GPU: live proposals installed on every rank at the switch to the replicated tail
         if (force_all) c->replicated_tail = false;
         auto account = [&](const RoundResult& q) {
             loops++;
@@ -1443,8 +1594,13 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
             r = rr[n - 1];
         } else if (c->world > 1 && !c->replicated_tail) {
             r = run_round_dist(c, cfg, connexity, force_all, as_iso);
-            c->modlist_valid = false;
-            if ((int64_t)r.proposals <= kReplicatedTailProposals && r.mods > 0) { c->replicated_tail = true; reeval_all = true; }
+            // Once a round evaluates few enough vertices the exchanges cost more than the work they split: the rest of the
+            // phase runs replicated (sparse rounds, no communication).  Every rank first receives every live proposal.
+            if ((int64_t)r.evaluated <= kReplicatedTailEvaluated && r.mods > 0) {
+                synced_proposals = dist_sync_proposals(c);
+                c->replicated_tail = true;
+                c->sig_valid = false;            // tile signatures were kept for the rank's own range only
+            }
         } else {
             for (int j = 0; j < batch; j++) launch_round(c, cfg, connexity, (j == 0 && (force_all || reeval_all)) ? 1 : 0, as_iso, j);
             if (batch > 1) c->modlist_valid = false;      // the list holds the last round of the batch only if all of them ran to the end
@@ -1455,7 +1611,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
             }
             reeval_all = false;
         }
-        last_proposals = (int64_t)r.proposals;
+        last_proposals = synced_proposals >= 0 ? synced_proposals : (int64_t)r.proposals;
         force_all = 0;
         account(r);
         const int64_t mods = (int64_t)r.mods;

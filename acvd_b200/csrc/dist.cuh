@@ -76,13 +76,86 @@ static int64_t dist_gather_moves(acvd_ctx* c, size_t rec_bytes, RoundResult& r) 
     return total;
 }
 
+// in-place NCCL all-gather of the per-cluster statistics every rank computed for its cluster chunk (sums, energies,
+// representative points): the "allreduce of per-cluster statistics" of the vertex-range design, without changing a bit
+// of what one GPU computes (each cluster is summed by exactly one rank, in item order)
+static void dist_allgather_stats(acvd_ctx* c) {
+    const size_t chunk = (size_t)dist_cluster_chunk(c), npad = (size_t)payload_npad(c->metric);
+    ACVD_NCCL(nccl().GroupStart());
+    ACVD_NCCL(nccl().AllGather(c->csum.p + (size_t)c->rank * chunk * npad, c->csum.p, chunk * npad, ncclDouble, c->comm, c->stream));
+    ACVD_NCCL(nccl().AllGather(c->cenergy.p + (size_t)c->rank * chunk, c->cenergy.p, chunk, ncclDouble, c->comm, c->stream));
+    ACVD_NCCL(nccl().AllGather(c->ccentroid.p + 3 * (size_t)c->rank * chunk, c->ccentroid.p, 3 * chunk, ncclDouble, c->comm, c->stream));
+    ACVD_NCCL(nccl().GroupEnd());
+}
+static void dist_allreduce_counters(acvd_ctx* c, unsigned long long* d, int n) {
+    ACVD_NCCL(nccl().AllReduce(d, d, (size_t)n, ncclUint64, ncclSum, c->comm, c->stream));
+}
+
+// every rank uploads its slice of a host array; grouped broadcasts complete the device copy on all ranks
+static void dist_sliced_upload(acvd_ctx* c, void* d, const void* h, size_t n_items, size_t item_bytes) {
+    const int W = c->world;
+    auto lo = [&](int r) { return n_items * (size_t)r / (size_t)W; };
+    const size_t b0 = lo(c->rank) * item_bytes, b1 = lo(c->rank + 1) * item_bytes;
+    if (b1 > b0) ACVD_CUDA(cudaMemcpyAsync((char*)d + b0, (const char*)h + b0, b1 - b0, cudaMemcpyHostToDevice, c->stream));
+    ACVD_NCCL(nccl().GroupStart());
+    for (int r = 0; r < W; r++) {
+        const size_t r0 = lo(r) * item_bytes, r1 = lo(r + 1) * item_bytes;
+        if (r1 > r0) ACVD_NCCL(nccl().Broadcast((char*)d + r0, (char*)d + r0, r1 - r0, ncclChar, r, c->comm, c->stream));
+    }
+    ACVD_NCCL(nccl().GroupEnd());
+}
+
+// When a phase leaves the exchanged rounds for its replicated tail, every rank needs every live proposal (they are
+// stored by the rank that owns the vertex): pack, all-gather, install.  Returns the number of live proposals.
+struct PropRec { int v, d; unsigned long long key; double ea, eb; };
+__global__ void __launch_bounds__(kThreads) k_pack_proposals(ReassignArgs A, PropRec* out, unsigned long long* n_out) {
+    const int n_props = (int)A.ctr->proposals;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_props; i += gridDim.x * blockDim.x) {
+        const int v = A.plist[i];
+        const int d = A.prop_dst[v];
+        if (d < 0) continue;
+        const double2 e = A.prop_e[v];
+        out[(int)atomicAdd(n_out, 1ull)] = PropRec{v, d, A.prop_key[v], e.x, e.y};
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_install_proposals(ReassignArgs A, const PropRec* __restrict__ in, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const PropRec r = in[i];
+        A.prop_dst[r.v] = r.d; A.prop_key[r.v] = r.key; A.prop_e[r.v] = make_double2(r.ea, r.eb);
+        A.plist[i] = r.v;
+    }
+}
+static int64_t dist_sync_proposals(acvd_ctx* c) {
+    EvalCfg cfg = make_cfg(1, 3, 0);
+    ReassignArgs A = make_args(c, cfg, 0, 0);          // A.plist = the list the last round wrote
+    c->moves_local.alloc(((size_t)c->V / c->world + 4096) * sizeof(PropRec));
+    ACVD_CUDA(cudaMemsetAsync(c->n_moves.p, 0, sizeof(unsigned long long), c->stream));
+    k_pack_proposals<<<kNumSMs * 4, kThreads, 0, c->stream>>>(A, reinterpret_cast<PropRec*>(c->moves_local.p), c->n_moves.p);
+    ACVD_LAUNCH_CHECK();
+    RoundResult dummy;
+    memset(&dummy, 0, sizeof dummy);
+    const int64_t total = dist_gather_moves(c, sizeof(PropRec), dummy);
+    ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
+    if (total > 0) {
+        k_install_proposals<<<kNumSMs * 4, kThreads, 0, c->stream>>>(A, reinterpret_cast<const PropRec*>(c->moves_all.p), (int)total);
+        ACVD_LAUNCH_CHECK();
+    }
+    return total;
+}
+
 // exact round on `world` GPUs
 static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity, int force_all, bool as_iso) {
     if (force_all) ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p + 1, 0, sizeof(unsigned long long), c->stream));
     else ACVD_CUDA(cudaMemcpyAsync(c->round_scalars.p + 1, &c->ctr.p->proposals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
     c->plist_cur ^= 1;
-    c->members_valid = false; c->modlist_valid = false;    // rebuilt when the phase enters its replicated tail
+    c->members_valid = false;                              // rebuilt when the phase enters its replicated tail
     ReassignArgs A = make_args(c, cfg, connexity, force_all);
+    // the clusters this round modifies (every rank applies every move), for the sparse rounds of the replicated tail
+    c->mod_par ^= 1;
+    A.modlist = c->mod_par ? c->modlist1.p : c->modlist0.p;
+    A.n_mod = c->sp_nmod.p;
+    ACVD_CUDA(cudaMemsetAsync(c->sp_nmod.p, 0, sizeof(unsigned long long), c->stream));
+    c->modlist_valid = true;
     ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)c->K * sizeof(unsigned long long), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, sizeof(unsigned long long), c->stream));

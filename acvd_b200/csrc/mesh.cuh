@@ -249,10 +249,12 @@ __global__ void k_sub_first_slots(int64_t n, const int* __restrict__ head, const
         if (head[i]) { first_slot[run_incl[i] - 1] = slots[i]; run_id[run_incl[i] - 1] = run_incl[i] - 1; }
 }
 // after sorting the runs by first slot: edge id of run run_sorted[e] is e; the edge's endpoints in first-seen order
-__global__ void k_sub_edges(int E, int V, const int* __restrict__ first_sorted, const int* __restrict__ run_sorted, const int* __restrict__ tri,
-                            const float* __restrict__ xyz, int* edge_of_run, float* xyz_out, int* parent1, int* parent2) {
+__global__ void k_edge_of_run(int E, const int* __restrict__ run_sorted, int* edge_of_run) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) edge_of_run[run_sorted[e]] = e;
+}
+__global__ void k_sub_edges(int E, int V, const int* __restrict__ first_sorted, const int* __restrict__ tri,
+                            const float* __restrict__ xyz, float* xyz_out, int* parent1, int* parent2) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-        edge_of_run[run_sorted[e]] = e;
         const int s = first_sorted[e], f = s / 3, k = s % 3;
         const int a = tri[3 * (int64_t)f + k], b = tri[3 * (int64_t)f + (k + 1) % 3];
         parent1[V + e] = a; parent2[V + e] = b;
@@ -291,6 +293,89 @@ __global__ void k_sub_faces(int F, int V, const int* __restrict__ tri, const int
         o[3] = v4; o[4] = v2; o[5] = v5;
         o[6] = v5; o[7] = v3; o[8] = v6;
         o[9] = v4; o[10] = v5; o[11] = v6;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// vtkSurface::SplitLongEdges (reference Common/vtkSurface.cxx:444-604, option -l): threshold = ratio x mean edge length
+// of the mesh as given; then passes until nothing is split: every edge longer than the threshold gets a midpoint vertex
+// (added in edge-id order), every triangle is replaced according to which of its edges were cut -- Split2 / Split3
+// (:429-443) or the 1 -> 4 pattern (:569-576).  Each pass works on a snapshot of the mesh, exactly like the reference's
+// loop over the edges and the first NumCells faces, so it is one set of data-parallel kernels per pass.  Edge ids inside a
+// pass are first-seen ids of the current mesh (upstream recycles deleted slots, its numbering is unobservable).
+__global__ void k_split_lengths(int E, const int* __restrict__ first_sorted, const int* __restrict__ tri, const float* __restrict__ xyz, double* len) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int s = first_sorted[e], f = s / 3, k = s % 3;
+        const int a = tri[3 * (int64_t)f + k], b = tri[3 * (int64_t)f + (k + 1) % 3];
+        double d2 = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { const double t = (double)xyz[3 * (int64_t)a + d] - (double)xyz[3 * (int64_t)b + d]; d2 += t * t; }
+        len[e] = sqrt(d2);
+    }
+}
+__global__ void k_split_mark(int E, const double* __restrict__ len, double threshold, int* mark) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) mark[e] = len[e] > threshold ? 1 : 0;
+}
+// midpoints of the marked edges: vertex V + (rank of the edge among the marked ones, in edge-id order)
+__global__ void k_split_points(int E, int V, const int* __restrict__ mark, const int* __restrict__ rank_excl, const int* __restrict__ first_sorted,
+                               const int* __restrict__ tri, float* xyz, int* parent1, int* parent2) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        if (!mark[e]) continue;
+        const int s = first_sorted[e], f = s / 3, k = s % 3;
+        const int a = tri[3 * (int64_t)f + k], b = tri[3 * (int64_t)f + (k + 1) % 3];
+        const int64_t m = (int64_t)V + rank_excl[e];
+        parent1[m] = a; parent2[m] = b;
+#pragma unroll
+        for (int d = 0; d < 3; d++) xyz[3 * m + d] = (float)(0.5 * ((double)xyz[3 * (int64_t)a + d] + (double)xyz[3 * (int64_t)b + d]));
+    }
+}
+// mid-vertex (or -1) of the three sides 12, 23, 31 of face f
+__device__ __forceinline__ void split_mids(int f, int V, const int* __restrict__ tri, const int* __restrict__ edge_of_slot, const int* __restrict__ mark,
+                                           const int* __restrict__ rank_excl, int& m12, int& m23, int& m13) {
+    const bool active = tri[3 * (int64_t)f] != tri[3 * (int64_t)f + 1];
+    int m[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const bool loop = tri[3 * (int64_t)f + k] == tri[3 * (int64_t)f + (k + 1) % 3];
+        const int e = (active && !loop) ? edge_of_slot[3 * (int64_t)f + k] : -1;
+        m[k] = (e >= 0 && mark[e]) ? V + rank_excl[e] : -1;
+    }
+    m12 = m[0]; m23 = m[1]; m13 = m[2];
+}
+__global__ void k_split_count(int F, int V, const int* __restrict__ tri, const int* __restrict__ edge_of_slot, const int* __restrict__ mark,
+                              const int* __restrict__ rank_excl, int* n_child) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        int m12, m23, m13;
+        split_mids(f, V, tri, edge_of_slot, mark, rank_excl, m12, m23, m13);
+        n_child[f] = 1 + (m12 >= 0) + (m23 >= 0) + (m13 >= 0);
+    }
+}
+__global__ void k_split_emit(int F, int V, const int* __restrict__ tri, const int* __restrict__ edge_of_slot, const int* __restrict__ mark,
+                             const int* __restrict__ rank_excl, const int* __restrict__ child_excl, int* tri_out) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        int v12, v23, v13;
+        split_mids(f, V, tri, edge_of_slot, mark, rank_excl, v12, v23, v13);
+        const int v1 = tri[3 * (int64_t)f], v2 = tri[3 * (int64_t)f + 1], v3 = tri[3 * (int64_t)f + 2];
+        int* o = tri_out + 3 * (int64_t)child_excl[f];
+        auto face = [&](int i, int a, int b, int c) { o[3 * i] = a; o[3 * i + 1] = b; o[3 * i + 2] = c; };
+        // Split2(f, a, b, c, ab): (a, ab, c) (ab, b, c);  Split3(f, a, b, c, ab, ac): (a, ab, ac) (ab, b, c) (c, ac, ab)
+        if (v12 < 0) {
+            if (v13 < 0) {
+                if (v23 < 0) face(0, v1, v2, v3);
+                else { face(0, v2, v23, v1); face(1, v23, v3, v1); }                                   // Split2(v2, v3, v1, v23)
+            } else {
+                if (v23 < 0) { face(0, v3, v13, v2); face(1, v13, v1, v2); }                            // Split2(v3, v1, v2, v13)
+                else { face(0, v3, v13, v23); face(1, v13, v1, v2); face(2, v2, v23, v13); }            // Split3(v3, v1, v2, v13, v23)
+            }
+        } else {
+            if (v13 < 0) {
+                if (v23 < 0) { face(0, v1, v12, v3); face(1, v12, v2, v3); }                            // Split2(v1, v2, v3, v12)
+                else { face(0, v2, v23, v12); face(1, v23, v3, v1); face(2, v1, v12, v23); }            // Split3(v2, v3, v1, v23, v12)
+            } else {
+                if (v23 < 0) { face(0, v1, v12, v13); face(1, v12, v2, v3); face(2, v3, v13, v12); }    // Split3(v1, v2, v3, v12, v13)
+                else { face(0, v1, v12, v13); face(1, v12, v2, v23); face(2, v23, v3, v13); face(3, v12, v23, v13); }
+            }
+        }
     }
 }
 

@@ -111,6 +111,8 @@ struct ClusterPassArgs {
     int* cc_sz;
     unsigned long long* counters;   // [0] clusters with more than one recorded component, [1] vertices reset to NULL
     int do_sort, do_cc, do_stats;
+    int apply_resets;         // 0: the connectivity check only counts (multi-GPU: every rank checks its share of the clusters first)
+    int k_begin, k_end;       // clusters handled by this launch
     EvalCfg cfg;
 };
 
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) k_cluster_pass(ClusterPassArgs P) {
     __shared__ int s_b[kThreads / 32][kClusterCap];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
-    for (int c = blockIdx.x * warps_per_block + w; c < P.K; c += gridDim.x * warps_per_block) {
+    for (int c = P.k_begin + blockIdx.x * warps_per_block + w; c < P.k_end; c += gridDim.x * warps_per_block) {
         const int b = P.off[c], n = P.csize[c];
         const bool small = n <= kClusterCap;
         int* mv = small ? s_v[w] : P.memb + b;          // the cluster's members, ascending after the sort
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) k_cluster_pass(ClusterPassArgs P) {
                     unsigned n_reset = 0;
                     for (int i = lane; i < n; i += 32) {
                         const int r = par[i];
-                        if (mv[r] != 0 && r != win) { P.cid[mv[i]] = P.K; n_reset++; }
+                        if (mv[r] != 0 && r != win) { if (P.apply_resets) P.cid[mv[i]] = P.K; n_reset++; }
                     }
                     n_reset = __reduce_add_sync(0xffffffffu, n_reset);
                     if (lane == 0) { atomicAdd(P.counters, 1ull); atomicAdd(P.counters + 1, (unsigned long long)n_reset); }

@@ -66,6 +66,12 @@ int acvd_get_csr(acvd_ctx* ctx, int32_t* row_ptr /*V+1*/, int32_t* col /*2E*/);
  * parent1/parent2[v] are the edge endpoints of a midpoint (v itself for old points), as the reference keeps them for
  * interpolating the curvature indicator (:733-745).  Any pointer of acvd_get_subdivision may be NULL. */
 int acvd_subdivide(acvd_ctx* ctx, int32_t* n_vertices, int32_t* n_faces);
+/* vtkSurface::SplitLongEdges (Common/vtkSurface.cxx:444-604, option -l): threshold = ratio x mean edge length of the
+ * context's mesh; passes of "cut every edge above the threshold at its midpoint, replace the triangles by the Split2 /
+ * Split3 / 1 -> 4 patterns" until no edge is above it.  The result stays on the device like a subdivision (fetch it with
+ * acvd_get_subdivision; parents are the end points of the cut edge).  New points follow the old ones pass by pass, in the
+ * edge-id order of the pass; faces keep their order, children in the pattern's order. */
+int acvd_split_long_edges(acvd_ctx* ctx, double ratio, int32_t* n_vertices, int32_t* n_faces, int32_t* n_passes /*may be NULL*/);
 int acvd_get_subdivision(acvd_ctx* ctx, float* xyz /*3 nv*/, int32_t* tri /*3 nf*/, int32_t* parent1 /*nv*/, int32_t* parent2 /*nv*/);
 
 /* vtkCurvatureMeasure with ComputationMethod 1 (polynomial fitting), ElementsType 1 (vertices) and the n-ring
