@@ -718,14 +718,22 @@ extern "C" int acvd_set_fixed_clusters(acvd_ctx* c, const int64_t* items, int32_
 extern "C" int acvd_initial_sampling(acvd_ctx* c) {
     ACVD_API_BEGIN(c)
     if (!c->K || !c->have_items) throw std::runtime_error("acvd_initial_sampling: need items and a cluster count");
-    std::vector<double> w(c->V);
-    ACVD_CUDA(cudaMemcpy(w.data(), c->weight.p, (size_t)c->V * sizeof(double), cudaMemcpyDeviceToHost));
-    std::vector<int> h_tri(3 * (size_t)c->F);
-    ACVD_CUDA(cudaMemcpy(h_tri.data(), c->tri.p, h_tri.size() * sizeof(int), cudaMemcpyDeviceToHost));
-    HostRings rings;
-    rings.build(c->V, c->F, h_tri.data());
+    // the rings in the reference's order come from the device (k_ring_order: neighbours sorted by the first half-edge
+    // slot of their edge), so the host does not rebuild the edge table; the region growing itself is sequential
+    const int V = c->V;
+    DevBuf<int> ring_col;
+    ring_col.alloc((size_t)std::max<int64_t>(c->nnz, 1));
+    FillMesh M{V, c->K, c->row_ptr.p, c->col.p, c->vf_ptr.p, c->vf_keys.p, c->tri.p};
+    k_ring_order<<<grid_for(V), kThreads, 0, c->stream>>>(M, ring_col.p);
+    ACVD_LAUNCH_CHECK();
+    std::vector<double> w((size_t)V);
+    std::vector<int> h_ptr((size_t)V + 1), h_nbr((size_t)c->nnz);
+    ACVD_CUDA(cudaMemcpyAsync(w.data(), c->weight.p, (size_t)V * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(h_ptr.data(), c->row_ptr.p, ((size_t)V + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(h_nbr.data(), ring_col.p, (size_t)c->nnz * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ACVD_CUDA(cudaStreamSynchronize(c->stream));
     std::vector<int> out;
-    initial_random_sampling(c->V, c->K, rings, w.data(), c->fixed, out);
+    initial_random_sampling(V, c->K, FlatRings{h_ptr.data(), h_nbr.data()}, w.data(), c->fixed, out);
     ACVD_CUDA(cudaMemcpy(c->cid.p, out.data(), (size_t)c->V * sizeof(int), cudaMemcpyHostToDevice));
     ACVD_CUDA(cudaMemset(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int)));
     c->stats_valid = false; c->sig_valid = false; c->members_valid = false; c->modlist_valid = false;

@@ -52,6 +52,34 @@ __device__ __forceinline__ unsigned edge_slot(const FillMesh& M, int a, int b) {
     return best;
 }
 
+// The neighbours of every vertex in the reference's ring order (edge creation order = ascending first half-edge slot),
+// written over the CSR layout: what ComputeInitialRandomSampling's region growing walks (host_sampling.hpp).
+__global__ void __launch_bounds__(kThreads) k_ring_order(FillMesh M, int* ring_col) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < M.V; v += gridDim.x * blockDim.x) {
+        const int beg = M.row_ptr[v], deg = M.row_ptr[v + 1] - beg;
+        if (deg <= 16) {
+            unsigned s[16];
+            int u[16];
+            for (int k = 0; k < deg; k++) {
+                const int w = M.col[beg + k];
+                const unsigned sl = edge_slot(M, v, w);
+                int j = k;
+                while (j > 0 && s[j - 1] > sl) { s[j] = s[j - 1]; u[j] = u[j - 1]; j--; }
+                s[j] = sl; u[j] = w;
+            }
+            for (int k = 0; k < deg; k++) ring_col[beg + k] = u[k];
+        } else {        // long rows: selection sort in place over the output row
+            for (int k = 0; k < deg; k++) ring_col[beg + k] = M.col[beg + k];
+            for (int k = 0; k < deg; k++) {
+                int best = k;
+                unsigned sb = edge_slot(M, v, ring_col[beg + k]);
+                for (int j = k + 1; j < deg; j++) { const unsigned sj = edge_slot(M, v, ring_col[beg + j]); if (sj < sb) { sb = sj; best = j; } }
+                const int t = ring_col[beg + k]; ring_col[beg + k] = ring_col[beg + best]; ring_col[beg + best] = t;
+            }
+        }
+    }
+}
+
 // NULL vertices in ascending order are collected by k_collect_null + a sort (cleanup.cuh); ids below 0 are
 // normalised to K first so that "NULL" is one value everywhere.
 __global__ void k_normalise_null(int V, int K, int* cid) {

@@ -1,6 +1,8 @@
 // VTK-free mesh container for the ACVD front-ends (see vtkSurface.h).
 #include "vtkSurface.h"
 
+#include "../../../include/acvd_b200.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -330,64 +332,24 @@ vtkSurface* vtkSurface::Subdivide(vtkIntArray* parent1, vtkIntArray* parent2) {
     return out;
 }
 
-// Bisects every edge longer than ratio x (mean edge length), longest first, until none is left
-// (behaviour of reference Common/vtkSurface.cxx:444-604; the numbering of the new elements differs,
-// which only matters to the sequential processing order).
+// vtkSurface::SplitLongEdges (reference Common/vtkSurface.cxx:444-604): threshold = ratio x mean edge length of the mesh
+// as given, then passes of "cut every edge above it at its midpoint, replace the triangles by the Split2 / Split3 / 1 -> 4
+// patterns".  Runs on the device through the C ABI (acvd_split_long_edges); new points follow the old ones.
 void vtkSurface::SplitLongEdges(double ratio) {
-    for (int pass = 0; pass < 64; pass++) {
-        BuildTopology();
-        const int ne = (int)edges.size();
-        double mean = 0;
-        std::vector<double> len((size_t)ne);
-        for (int e = 0; e < ne; e++) {
-            double d = 0;
-            for (int k = 0; k < 3; k++) { double t = (double)xyz[3 * (size_t)edges[e][0] + k] - (double)xyz[3 * (size_t)edges[e][1] + k]; d += t * t; }
-            len[(size_t)e] = std::sqrt(d); mean += len[(size_t)e];
-        }
-        if (ne == 0) return;
-        mean /= ne;
-        if (pass > 0) mean = split_reference_length;
-        else split_reference_length = mean;
-        // independent set of long edges: one split per face per pass
-        std::vector<int> order;
-        for (int e = 0; e < ne; e++) if (len[(size_t)e] > ratio * mean) order.push_back(e);
-        if (order.empty()) return;
-        std::sort(order.begin(), order.end(), [&](int a, int b) { return len[(size_t)a] > len[(size_t)b]; });
-        const int nf = (int)GetNumberOfCells();
-        std::vector<char> face_used((size_t)nf, 0);
-        std::vector<int> new_tri;
-        std::vector<char> face_dead((size_t)nf, 0);
-        for (int e : order) {
-            const int a = edges[(size_t)e][0], b = edges[(size_t)e][1];
-            std::vector<int> fs;
-            for (int i = vf_ptr[a]; i < vf_ptr[a + 1]; i++) {
-                const int* t = &tri[3 * (size_t)vf[i]];
-                if (t[0] == b || t[1] == b || t[2] == b) fs.push_back(vf[i]);
-            }
-            bool busy = false;
-            for (int f : fs) busy |= face_used[(size_t)f] != 0;
-            if (busy || fs.empty()) continue;
-            const int m = (int)(xyz.size() / 3);
-            for (int k = 0; k < 3; k++) xyz.push_back((float)(0.5 * ((double)xyz[3 * (size_t)a + k] + (double)xyz[3 * (size_t)b + k])));
-            for (int f : fs) {
-                face_used[(size_t)f] = 1; face_dead[(size_t)f] = 1;
-                int t[3] = {tri[3 * (size_t)f], tri[3 * (size_t)f + 1], tri[3 * (size_t)f + 2]};
-                for (int k = 0; k < 3; k++) {
-                    const int p = t[k], q = t[(k + 1) % 3], r = t[(k + 2) % 3];
-                    if ((p == a && q == b) || (p == b && q == a)) {
-                        const int t1[3] = {p, m, r}, t2[3] = {m, q, r};
-                        new_tri.insert(new_tri.end(), t1, t1 + 3); new_tri.insert(new_tri.end(), t2, t2 + 3);
-                    }
-                }
-            }
-        }
-        std::vector<int> kept;
-        kept.reserve(tri.size() + new_tri.size());
-        for (int f = 0; f < nf; f++) if (!face_dead[(size_t)f]) kept.insert(kept.end(), &tri[3 * (size_t)f], &tri[3 * (size_t)f] + 3);
-        kept.insert(kept.end(), new_tri.begin(), new_tri.end());
-        tri.swap(kept);
-        Invalidate();
+    acvd_ctx* ctx = nullptr;
+    if (acvd_create(&ctx, -1) != ACVD_OK) { std::cout << "ERROR : " << acvd_last_error(nullptr) << std::endl; return; }
+    int32_t nv = 0, nf = 0, passes = 0;
+    if (acvd_set_mesh(ctx, (int32_t)GetNumberOfPoints(), (int32_t)GetNumberOfCells(), Points(), Triangles()) != ACVD_OK ||
+        acvd_split_long_edges(ctx, ratio, &nv, &nf, &passes) != ACVD_OK) {
+        std::cout << "ERROR : " << acvd_last_error(ctx) << std::endl;
+        acvd_destroy(ctx);
+        return;
     }
+    std::vector<float> p(3 * (size_t)nv);
+    std::vector<int> t(3 * (size_t)nf);
+    if (acvd_get_subdivision(ctx, p.data(), t.data(), nullptr, nullptr) == ACVD_OK) { xyz.swap(p); tri.swap(t); Invalidate(); }
+    else std::cout << "ERROR : " << acvd_last_error(ctx) << std::endl;
+    acvd_destroy(ctx);
 }
 
 void vtkSurface::GetMeshProperties(vtkIdType& non_manifold, vtkIdType& boundary, vtkIdType& components) {

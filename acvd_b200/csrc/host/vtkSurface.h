@@ -68,7 +68,7 @@ public:
 
     // ---- processing
     vtkSurface* Subdivide(vtkIntArray* parent1 = nullptr, vtkIntArray* parent2 = nullptr);   // vtkSurface.cxx:605-677
-    void SplitLongEdges(double ratio);                         // vtkSurface.cxx:444-604 (bisects edges longer than ratio x mean)
+    void SplitLongEdges(double ratio);                         // vtkSurface.cxx:444-604, on the device (acvd_split_long_edges)
     void DisplayMeshProperties();                              // vtkSurface.cxx:762-873 (subset)
     void GetMeshProperties(vtkIdType& nonManifoldEdges, vtkIdType& boundaryEdges, vtkIdType& components);
 
@@ -89,7 +89,6 @@ private:
     void BuildTopology();
     void Invalidate() { topo_valid = false; }
     bool topo_valid = false;
-    double split_reference_length = 0;               // mean edge length of the mesh SplitLongEdges started from
     std::vector<int> vf_ptr, vf;                     // vertex -> faces
     std::vector<std::array<int, 2>> edges;           // undirected, (lo, hi)
     std::vector<int> edge_nfaces;                    // faces per edge

@@ -156,6 +156,44 @@ def thin_torus(nu: int = 16000, nv: int = 10000, dtype=np.float32):
     return torus_grid(nu, nv, 1.0, 0.078125, dtype=dtype)
 
 
+def banded_thin_torus(nu: int = 16000, nv: int = 10000, band: float = 0.1, stretch: int = 8, dtype=np.float32):
+    """C5 input: closed thin torus R = 1, r = 0.078125 with 8:1 elongated cells along the major circle, where a
+    band of the major-circle columns (`band` of the circumference) is coarsened `stretch` times: its edges exceed 3 x the
+    mean edge length, so `-l 3` (vtkSurface::SplitLongEdges) really cuts there.  `nu` is the number of major-circle columns
+    the *uniform* torus would have; the band keeps every `stretch`-th of its columns.  Built column block by column block
+    straight into float32 / int32 (the full-size mesh is 146 M vertices, 291 M triangles)."""
+    n_band = int(round(nu * band))
+    cols = np.concatenate([np.arange(0, n_band, stretch), np.arange(n_band, nu)]).astype(np.float64)
+    nc = cols.size
+    R, r = 1.0, 0.078125
+    v = np.arange(nv) * (2 * np.pi / nv)
+    ring_r = (R + r * np.cos(v))                       # distance of the minor-circle points from the axis
+    ring_z = (r * np.sin(v)).astype(dtype)
+    pts = np.empty((nc * nv, 3), dtype=dtype)
+    tris = np.empty((2 * nc * nv, 3), dtype=np.int32)
+    jn = ((np.arange(nv) + 1) % nv).astype(np.int64)
+    j = np.arange(nv, dtype=np.int64)
+    block = 512
+    for c0 in range(0, nc, block):
+        c1 = min(nc, c0 + block)
+        u = cols[c0:c1] * (2 * np.pi / nu)
+        sl = slice(c0 * nv, c1 * nv)
+        pts[sl, 0] = (np.cos(u)[:, None] * ring_r[None, :]).reshape(-1)
+        pts[sl, 1] = (np.sin(u)[:, None] * ring_r[None, :]).reshape(-1)
+        pts[sl, 2] = np.broadcast_to(ring_z[None, :], (c1 - c0, nv)).reshape(-1)
+        i = np.arange(c0, c1, dtype=np.int64)[:, None]
+        i1 = (i + 1) % nc
+        a = (i * nv + j[None, :]).reshape(-1)
+        b = (i1 * nv + j[None, :]).reshape(-1)
+        c = (i1 * nv + jn[None, :]).reshape(-1)
+        d = (i * nv + jn[None, :]).reshape(-1)
+        # faces (a, b, c) of all cells first, then (a, c, d): the order torus_grid uses (fixed diagonal)
+        tris[sl, 0] = a; tris[sl, 1] = b; tris[sl, 2] = c
+        s2 = slice(nc * nv + c0 * nv, nc * nv + c1 * nv)
+        tris[s2, 0] = a; tris[s2, 1] = c; tris[s2, 2] = d
+    return pts, tris
+
+
 def displaced_sphere(n: int = 2000, amp: float = 0.05, seed: int = 2, dtype=np.float32):
     """C4: geodesic icosphere radially displaced by amp * sum_k a_k sin(f_k d_k.p + phi_k)."""
     pts, tris = geodesic_icosphere(n, dtype=np.float64)
@@ -262,6 +300,16 @@ def workload(name: str):
         pd, ind = ellipsoid_principal_directions(p)
         return dict(points=p, triangles=t, K=10000 if name == "C3" else 625, metric="anisoq", gradation=1.5,
                     indicator=ind, pd=pd)
+    if name in ("C5", "C5s"):
+        # ACVD m K 0 -m 1 -l 3 on the banded thin torus: V = vertex count AFTER SplitLongEdges (what the clustering sees);
+        # the split itself is part of the run (acvd_split_long_edges), `split_ratio` tells the caller to apply it
+        if name == "C5":
+            p, t = banded_thin_torus(16000, 10000)
+            K = 1600000
+        else:   # 1/256 scale twin
+            p, t = banded_thin_torus(1000, 625)
+            K = 6250
+        return dict(points=p, triangles=t, K=K, metric="iso", gradation=0.0, indicator=None, split_ratio=3.0, force_manifold=1)
     if name == "C4":
         p, t = displaced_sphere(2000)
         return dict(points=p, triangles=t, K=400000, metric="qem", gradation=0.0, indicator=None)

@@ -36,6 +36,8 @@ WORKLOADS = {
     "C1": "ACVD isotropic on a 163,842-vertex icosphere -> 3000 clusters (configs[0])",
     "C3": "AnisotropicRemeshingQ gradation 1.5 (analytic curvature) on a 998,562-vertex ridged ellipsoid -> 10k clusters (configs[2])",
     "C3s": "1/16-scale C3",
+    "C5": "ACVD -m 1 -l 3 on a 160M-vertex (after SplitLongEdges) banded thin torus, 8:1 elongated cells -> 1.6M clusters (BASELINE configs[4])",
+    "C5s": "1/256-scale C5",
 }
 
 
@@ -44,7 +46,8 @@ def log(*a):
 
 
 def config_dict(name, w, world):
-    """The `config` object of the JSON line: identical in both arms (ours / --impl reference)."""
+    """The `config` object of the JSON line: identical in both arms (ours / --impl reference).  For workloads with a
+    SplitLongEdges pre-pass V and F are those of the mesh after the split (what the clustering sees)."""
     V, F, K = int(w["points"].shape[0]), int(w["triangles"].shape[0]), int(w["K"])
     return {"workload": f"{name}: {WORKLOADS[name]}", "V": V, "F": F, "K": K,
             "metric_kind": w["metric"], "gradation": w["gradation"],
@@ -130,12 +133,21 @@ def profiled_traffic(workload, kernel):
 
 
 # --------------------------------------------------------------------------------------------
+def cpu_mesh(w):
+    """The mesh the clustering sees on the CPU legs: workloads with `-l` go through the restated SplitLongEdges first."""
+    if w.get("split_ratio"):
+        from oracle import oracle
+        p, t, _, _, _ = oracle.split_long_edges(w["points"], w["triangles"], w["split_ratio"])
+        w["points"], w["triangles"], w["split_ratio"] = p, t, None
+    return w["points"], w["triangles"]
+
+
 def cpu_sample(w, threads, loops, steps=1, warmup=0):
     """Bounded sample of the restated reference (oracle) on the same workload: `loops` passes of
     ProcessOneLoop from the initial sampling.  Returns per-step (tests, seconds) and setup info."""
     from oracle import oracle
     t0 = time.time()
-    o = oracle.Oracle(w["points"], w["triangles"])
+    o = oracle.Oracle(*cpu_mesh(w))
     o.build_metric(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
     o.set_num_clusters(w["K"])
     cl0 = o.initial_sampling().copy()
@@ -161,7 +173,7 @@ def cpu_to_convergence(w, threads=1):
     """The restated reference run TO CONVERGENCE on workload dict `w` (timer where the reference's own sits,
     Common/vtkUniformClustering.h:690-706).  Returns seconds, loops, tests, energy (fresh statistics)."""
     from oracle import oracle
-    o = oracle.Oracle(w["points"], w["triangles"])
+    o = oracle.Oracle(*cpu_mesh(w))
     o.build_metric(w["metric"], w["gradation"], w["indicator"], w.get("pd"))
     o.set_num_clusters(w["K"])
     o.initial_sampling()
@@ -171,6 +183,12 @@ def cpu_to_convergence(w, threads=1):
         o.minimize_threaded(threads, 0)
     else:
         o.minimize(0)
+    if w.get("force_manifold"):        # the -m 1 loop (vtkDiscreteRemeshing.h:937-950), sequential engine
+        for _ in range(200):
+            if o.detect_non_manifold(1).size == 0:
+                break
+            o.set_connexity(0)
+            o.minimize(0)
     dt = time.perf_counter() - t0
     r = o.report()
     o.recompute_statistics()
@@ -179,7 +197,7 @@ def cpu_to_convergence(w, threads=1):
 
 
 # workloads whose sequential CPU run to convergence fits the bench's time bound (seconds on one core: C1 0.4, C2 ~40)
-CPU_CONVERGES_LIVE = {"C1", "C2", "C4s", "C2s", "C3s"}
+CPU_CONVERGES_LIVE = {"C1", "C2", "C4s", "C2s", "C3s", "C5s"}
 SCALED_TWIN = {"C4": ("C4s", 100.0), "C3": ("C3s", 16.0), "C5": ("C5s", 256.0)}
 
 
@@ -215,6 +233,7 @@ def run_reference(args):
     if rank != 0:
         return
     w = make_workload(args.workload)
+    cpu_mesh(w)
     threads = os.cpu_count() or 1
     loops = args.ref_loops
     res, setup_s = cpu_sample(w, threads, loops, steps=args.steps, warmup=args.warmup)
@@ -303,25 +322,86 @@ def main():
         uid = [capi.Context.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.dist_init(rank, world, uid[0])
+    split_s = None
+    if w.get("split_ratio"):
+        # -l: vtkSurface::SplitLongEdges on the device; the clustering (and V in the config) sees the mesh after the split
+        t0 = time.time()
+        ctx.set_mesh(h_xyz, h_tri)
+        ratio = w["split_ratio"]
+        nv2, nf2, n_pass = ctx.split_long_edges(ratio, fetch=False)
+        del _k1, _k2, h_xyz, h_tri
+        w["points"] = w["triangles"] = None
+        _k1 = torch.empty((nv2, 3), dtype=torch.float32).pin_memory()
+        _k2 = torch.empty((nf2, 3), dtype=torch.int32).pin_memory()
+        h_xyz, h_tri = _k1.numpy(), _k2.numpy()
+        ctx._ck(ctx.L.acvd_get_subdivision(ctx.h, capi._p(h_xyz), capi._p(h_tri), None, None))
+        w["points"], w["triangles"] = h_xyz, h_tri
+        w["split_ratio"] = None           # done: the CPU baseline legs below get the mesh the clustering sees
+        V, F = nv2, nf2
+        split_s = time.time() - t0
+        log(f"[rank {rank}] SplitLongEdges({ratio}): {n_pass} passes -> V={V} F={F} in {split_s:.2f}s (upload, split, download)")
+    fm = bool(w.get("force_manifold"))
     t0 = time.time()
     ctx.set_mesh(h_xyz, h_tri)
     t1 = time.time()
     ctx.build_items(w["metric"], w["gradation"], h_ind, h_pd)
     ctx.set_num_clusters(K)
     t2 = time.time()
-    ctx.initial_sampling()          # host, sequential; outside the timed region as in the reference (:690)
+    # host, sequential; outside the timed region as in the reference (:690).  Across GPUs rank 0 runs it and broadcasts
+    # ("run once on host or GPU 0 and scatter")
+    if world > 1:
+        cl_t = torch.empty(V, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            ctx.initial_sampling()
+            cl_t.copy_(torch.from_numpy(ctx.clustering()))
+        dist.broadcast(cl_t, src=0)
+        if rank != 0:
+            ctx.set_clustering(cl_t.cpu().numpy())
+        del cl_t
+    else:
+        ctx.initial_sampling()
     t3 = time.time()
     ctx.save_clustering()
     _k4, h_cl0 = pinned(ctx.clustering())
-    setup = {"set_mesh_s": t1 - t0, "build_items_s": t2 - t1, "initial_sampling_s": t3 - t2,
+    setup = {"split_long_edges_s": split_s, "set_mesh_s": t1 - t0, "build_items_s": t2 - t1, "initial_sampling_s": t3 - t2,
              "note": "first calls of the process (memory pool growth included); initial sampling is sequential by definition "
                      "(vtkUniformClustering.h:1178-1316) and outside the reference's own timer (:690)"}
     log(f"[rank {rank}] setup: set_mesh {t1-t0:.2f}s, items {t2-t1:.2f}s, initial sampling {t3-t2:.2f}s")
     mparams = dict(unconstrained_init=w["unconstrained_init"])
 
+    SUM_KEYS = None
+
+    def run_clustering():
+        """MinimizeEnergy, and under -m 1 the loop of vtkDiscreteRemeshing.h:937-950: detect non-manifold output
+        vertices, re-enter MinimizeEnergy with the connexity constraint off, until the dual mesh is manifold."""
+        rep = ctx.minimize(**mparams)
+        if not fm:
+            return rep
+        rep["m_loop_iterations"] = 0
+        rep["ms_detect"] = 0.0
+        for _ in range(200):
+            t0 = time.perf_counter()
+            n_issues = ctx.detect_non_manifold(1)
+            dt = 1e3 * (time.perf_counter() - t0)
+            rep["ms_detect"] += dt
+            rep["ms_device"] += dt          # wall time of the detection step (device kernels + the host list logic)
+            if n_issues == 0:
+                break
+            r2 = ctx.minimize(connexity=0, **mparams)
+            rep["m_loop_iterations"] += 1
+            for k, v in r2.items():
+                if k in ("energy", "disconnected"):
+                    rep[k] = v
+                else:
+                    rep[k] += v
+        rep["output_vertices"] = ctx.K
+        return rep
+
     def step():
+        if fm:
+            ctx.set_num_clusters(K)     # the -m loop of the previous step appended clusters
         ctx.restore_clustering()
-        return ctx.minimize(**mparams)
+        return run_clustering()
 
     for _ in range(args.warmup):
         step()
@@ -367,7 +447,8 @@ def main():
         ctx.build_items(w["metric"], w["gradation"], h_ind, h_pd); tt.append(time.perf_counter())
         ctx.set_num_clusters(K); tt.append(time.perf_counter())
         ctx.set_clustering(h_cl0); tt.append(time.perf_counter())
-        r = ctx.minimize(**mparams); tt.append(time.perf_counter())
+        r = run_clustering(); tt.append(time.perf_counter())
+
         ctx.clustering(h_out); tt.append(time.perf_counter())
         sums, cen, en, sz = ctx.cluster_stats(); tt.append(time.perf_counter())
         e2e_tests += r["tests"]
@@ -434,6 +515,8 @@ def main():
             "time_to_convergence_s": ms_per_step * 1e-3, "wall_s_per_step": t_wall / args.steps,
             "rounds": last["rounds"], "convergences": last["convergences"], "modifications": last["modifications"],
             "energy": last["energy"], "tests_per_step": tests / args.steps, "clustering_sha256_16": final_sha,
+            "m_loop": ({"iterations": last.get("m_loop_iterations"), "output_vertices": last.get("output_vertices"),
+                        "ms_detect": last.get("ms_detect")} if fm else None),
             "vs_cpu_time_ratio": (cpu["time_to_convergence_s"] / (ms_per_step * 1e-3)) if cpu else None, "setup": setup,
             "tail": {"ms_sparse_rounds": sum(r.get("ms_sparse", 0.0) for r in reps) / args.steps,
                      "sparse_rounds": sum(r.get("sparse_rounds", 0) for r in reps) / args.steps,

@@ -1391,4 +1391,88 @@ int64_t orc_cluster_adjacency(void* h, int64_t* out, int64_t cap) {
     for (int64_t i = 0; i < (int64_t)p.size() && i < cap; i++) out[i] = p[i];
     return (int64_t)p.size();
 }
+
+// vtkSurface::SplitLongEdges (Common/vtkSurface.cxx:444-604) with Split2 / Split3 (:429-443): threshold = ratio x mean
+// edge length of the mesh as given, then passes of "midpoint on every edge above the threshold (edge-id order), faces
+// replaced by pattern" until nothing is cut.  Edge ids inside a pass are the first-seen ids of the current face list
+// (upstream recycles deleted face / edge slots, SURVEY A.6: its numbering is unobservable here), faces keep their order
+// with the children in the pattern's order.  Two calls: sizes first (xyz_out == null), then the arrays.
+static std::vector<float> g_split_xyz;
+static std::vector<int> g_split_tri, g_split_p1, g_split_p2;
+int orc_split_long_edges(int V, int F, const float* xyz_in, const int* tri_in, double ratio, int* nv, int* nf,
+                         float* xyz_out, int* tri_out, int* parent1, int* parent2) {
+    if (xyz_out) {
+        std::copy(g_split_xyz.begin(), g_split_xyz.end(), xyz_out);
+        std::copy(g_split_tri.begin(), g_split_tri.end(), tri_out);
+        if (parent1) std::copy(g_split_p1.begin(), g_split_p1.end(), parent1);
+        if (parent2) std::copy(g_split_p2.begin(), g_split_p2.end(), parent2);
+        return 0;
+    }
+    std::vector<float> xyz(xyz_in, xyz_in + 3 * (size_t)V);
+    std::vector<int> tri(tri_in, tri_in + 3 * (size_t)F), p1(V), p2(V);
+    for (int v = 0; v < V; v++) p1[v] = p2[v] = v;
+    double threshold = 0;
+    int passes = 0;
+    for (;; passes++) {
+        const int nf_cur = (int)(tri.size() / 3), nv_cur = (int)(xyz.size() / 3);
+        // edge table, first-seen order (AddEdge, Common/vtkSurfaceBase.cxx:1166-1221)
+        std::vector<std::vector<std::pair<int, int>>> ring(nv_cur);     // (other end, edge id)
+        std::vector<int> ea, eb;
+        std::vector<int> eos(3 * (size_t)nf_cur, -1);
+        auto find = [&](int a, int b) { for (auto& q : ring[a]) if (q.first == b) return q.second; return -1; };
+        for (int f = 0; f < nf_cur; f++) {
+            const int* t = &tri[3 * (size_t)f];
+            if (t[0] == t[1]) continue;
+            for (int k = 0; k < 3; k++) {
+                int a = t[k], b = t[(k + 1) % 3];
+                if (a == b) continue;
+                int e = find(a, b);
+                if (e < 0) { e = (int)ea.size(); ea.push_back(a); eb.push_back(b); ring[a].push_back({b, e}); ring[b].push_back({a, e}); }
+                eos[3 * (size_t)f + k] = e;
+            }
+        }
+        const int E = (int)ea.size();
+        if (E == 0) break;
+        std::vector<double> len(E);
+        for (int e = 0; e < E; e++) {
+            double d2 = 0;
+            for (int d = 0; d < 3; d++) { double t = (double)xyz[3 * (size_t)ea[e] + d] - (double)xyz[3 * (size_t)eb[e] + d]; d2 += t * t; }
+            len[e] = std::sqrt(d2);
+        }
+        if (passes == 0) { double total = 0; for (int e = 0; e < E; e++) total += len[e]; threshold = ratio * total / (double)E; }
+        std::vector<int> mid(E, -1);
+        int n_cut = 0;
+        for (int e = 0; e < E; e++) if (len[e] > threshold) {
+            mid[e] = nv_cur + n_cut++;
+            for (int d = 0; d < 3; d++) xyz.push_back((float)(0.5 * ((double)xyz[3 * (size_t)ea[e] + d] + (double)xyz[3 * (size_t)eb[e] + d])));
+            p1.push_back(ea[e]); p2.push_back(eb[e]);
+        }
+        if (n_cut == 0) break;
+        std::vector<int> out;
+        out.reserve(tri.size() * 2);
+        auto face = [&](int a, int b, int c) { out.push_back(a); out.push_back(b); out.push_back(c); };
+        auto split2 = [&](int a, int b, int c, int ab) { face(a, ab, c); face(ab, b, c); };
+        auto split3 = [&](int a, int b, int c, int ab, int ac) { face(a, ab, ac); face(ab, b, c); face(c, ac, ab); };
+        for (int f = 0; f < nf_cur; f++) {
+            const int v1 = tri[3 * (size_t)f], v2 = tri[3 * (size_t)f + 1], v3 = tri[3 * (size_t)f + 2];
+            auto m = [&](int k) { int e = eos[3 * (size_t)f + k]; return e >= 0 ? mid[e] : -1; };
+            const int v12 = m(0), v23 = m(1), v13 = m(2);
+            if (v12 < 0) {
+                if (v13 < 0) { if (v23 < 0) face(v1, v2, v3); else split2(v2, v3, v1, v23); }
+                else { if (v23 < 0) split2(v3, v1, v2, v13); else split3(v3, v1, v2, v13, v23); }
+            } else {
+                if (v13 < 0) { if (v23 < 0) split2(v1, v2, v3, v12); else split3(v2, v3, v1, v23, v12); }
+                else {
+                    if (v23 < 0) split3(v1, v2, v3, v12, v13);
+                    else { face(v1, v12, v13); face(v12, v2, v23); face(v23, v3, v13); face(v12, v23, v13); }
+                }
+            }
+        }
+        tri.swap(out);
+        if (passes > 64) break;
+    }
+    g_split_xyz.swap(xyz); g_split_tri.swap(tri); g_split_p1.swap(p1); g_split_p2.swap(p2);
+    *nv = (int)(g_split_xyz.size() / 3); *nf = (int)(g_split_tri.size() / 3);
+    return passes;
+}
 }

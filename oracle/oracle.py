@@ -54,6 +54,7 @@ def lib():
             ("orc_dual_triangles", [vp, vp, i], i), ("orc_boundary_flags", [vp, vp], None),
             ("orc_cluster_adjacency", [vp, vp, C.c_int64], C.c_int64),
             ("orc_curvature", [vp, i, vp, vp], None),
+            ("orc_split_long_edges", [i, i, vp, vp, d, vp, vp, vp, vp, vp, vp], i),
             ("orc_output_vertex_manifold", [vp, i, vp], None), ("orc_input_vertex_manifold", [vp, vp], None),
             ("orc_detect_non_manifold", [vp, i, vp, i], i), ("orc_num_clusters", [vp], i), ("orc_get_frozen", [vp, vp], None),
         ]:
@@ -86,6 +87,20 @@ def mt19937_first(n=3):
     out = np.zeros(n, dtype=np.uint32)
     lib().orc_mt19937_first(_p(out), n)
     return out
+
+
+def split_long_edges(points, triangles, ratio):
+    """vtkSurface::SplitLongEdges restated (Common/vtkSurface.cxx:444-604): (points, triangles, parent1, parent2, passes)."""
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    t = np.ascontiguousarray(triangles, dtype=np.int32)
+    nv, nf = C.c_int(), C.c_int()
+    passes = lib().orc_split_long_edges(p.shape[0], t.shape[0], _p(p), _p(t), float(ratio), C.byref(nv), C.byref(nf), None, None, None, None)
+    po = np.zeros((nv.value, 3), dtype=np.float32)
+    to = np.zeros((nf.value, 3), dtype=np.int32)
+    p1 = np.zeros(nv.value, dtype=np.int32)
+    p2 = np.zeros(nv.value, dtype=np.int32)
+    lib().orc_split_long_edges(0, 0, None, None, 0.0, C.byref(nv), C.byref(nf), _p(po), _p(to), _p(p1), _p(p2))
+    return po, to, p1, p2, passes
 
 
 class Oracle:
