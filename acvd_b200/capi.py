@@ -98,6 +98,7 @@ SYMBOLS = [
     ("acvd_bench_kernel", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("acvd_dist_unique_id", C.c_int, [_vp]),
     ("acvd_dist_init", C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    ("acvd_dist_partition", C.c_int, [_i64, _i64, _i32, _i32, _i32, _vp]),
 ]
 
 _LIB = None
@@ -120,6 +121,17 @@ def load_library():
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def dist_partition(V, F, K, rank, world):
+    """acvd_dist_partition: the ranges rank works on -- dict(tiles, clusters, points, faces), each (begin, end).  Host
+    arithmetic inside the library: needs no CUDA device."""
+    out = np.zeros(8, dtype=np.int64)
+    rc = load_library().acvd_dist_partition(int(V), int(F), int(K), int(rank), int(world), _p(out))
+    if rc != 0:
+        raise AcvdError(rc, "acvd_dist_partition: bad arguments")
+    o = [int(x) for x in out]
+    return dict(tiles=(o[0], o[1]), clusters=(o[2], o[3]), points=(o[4], o[5]), faces=(o[6], o[7]))
 
 
 class Context:

@@ -806,7 +806,7 @@ static void cluster_pass(acvd_ctx* c, bool do_cc, bool do_stats, int constrained
 }
 
 // multi-GPU: the cluster range this rank runs the cluster pass on (equal chunks: the results are all-gathered in place)
-static int dist_cluster_chunk(const acvd_ctx* c) { return (c->K + c->world - 1) / c->world; }
+static int dist_cluster_chunk(const acvd_ctx* c) { return (c->K + c->world - 1) / c->world; }   // = acvd_dist_partition out[2..3]
 static void dist_allgather_stats(acvd_ctx* c);     // dist.cuh
 
 // ReComputeStatistics (:376-403) + ReComputeClustersSize (:353-373)

@@ -38,11 +38,28 @@ extern "C" int acvd_dist_init(acvd_ctx* c, int rank, int world, const void* id_b
     return ACVD_OK;
 }
 
+// The partition of the work across ranks, as pure host arithmetic (no device needed: the CPU tests call it through the
+// C ABI): rank r scans and evaluates the vertices of the 32-vertex tiles [out[0], out[1]) -- a contiguous vertex range --
+// uploads the points / faces [out[4], out[5]) / [out[6], out[7]) of the mesh, and runs the cluster pass (statistics,
+// connectivity) on the clusters [out[2], out[3]) (equal chunks: the results are all-gathered in place).
+extern "C" int acvd_dist_partition(int64_t V, int64_t F, int32_t K, int32_t rank, int32_t world, int64_t* out) {
+    if (!out || world < 1 || rank < 0 || rank >= world || V < 0 || F < 0 || K < 0) return ACVD_EINVAL;
+    const int64_t n_tiles = (V + 31) / 32;
+    out[0] = n_tiles * rank / world;
+    out[1] = n_tiles * (rank + 1) / world;
+    const int64_t chunk = ((int64_t)K + world - 1) / world;
+    out[2] = std::min<int64_t>(K, chunk * rank);
+    out[3] = std::min<int64_t>(K, out[2] + chunk);
+    out[4] = V * rank / world; out[5] = V * (rank + 1) / world;
+    out[6] = F * rank / world; out[7] = F * (rank + 1) / world;
+    return ACVD_OK;
+}
+
 // tile range owned by this rank
 static void dist_tile_range(const acvd_ctx* c, int& t0, int& t1) {
-    const int64_t n_tiles = ((int64_t)c->V + 31) / 32;
-    t0 = (int)(n_tiles * c->rank / c->world);
-    t1 = (int)(n_tiles * (c->rank + 1) / c->world);
+    int64_t r[8];
+    acvd_dist_partition(c->V, c->F, c->K, c->rank, c->world, r);
+    t0 = (int)r[0]; t1 = (int)r[1];
 }
 
 // All-gather of variable-length records: the 64-byte headers first (they carry the local count and the
@@ -94,7 +111,7 @@ static void dist_allreduce_counters(acvd_ctx* c, unsigned long long* d, int n) {
 // every rank uploads its slice of a host array; grouped broadcasts complete the device copy on all ranks
 static void dist_sliced_upload(acvd_ctx* c, void* d, const void* h, size_t n_items, size_t item_bytes) {
     const int W = c->world;
-    auto lo = [&](int r) { return n_items * (size_t)r / (size_t)W; };
+    auto lo = [&](int r) { return n_items * (size_t)r / (size_t)W; };      // the ranges of acvd_dist_partition
     const size_t b0 = lo(c->rank) * item_bytes, b1 = lo(c->rank + 1) * item_bytes;
     if (b1 > b0) ACVD_CUDA(cudaMemcpyAsync((char*)d + b0, (const char*)h + b0, b1 - b0, cudaMemcpyHostToDevice, c->stream));
     ACVD_NCCL(nccl().GroupStart());

@@ -229,6 +229,10 @@ int acvd_bench_kernel(acvd_ctx* ctx, int kernel, int variant, int stage, int rep
 #define ACVD_NCCL_ID_BYTES 128
 int acvd_dist_unique_id(void* id_out /*ACVD_NCCL_ID_BYTES*/);
 int acvd_dist_init(acvd_ctx* ctx, int rank, int world, const void* id /*ACVD_NCCL_ID_BYTES*/);
+/* The partition the library uses across ranks (pure host arithmetic, callable without a device): out[0..1] = the
+ * 32-vertex tiles (a contiguous vertex range) rank scans and evaluates, out[2..3] = the clusters it runs the cluster
+ * pass (statistics, connectivity) on, out[4..5] / out[6..7] = the points / faces of the mesh it uploads. */
+int acvd_dist_partition(int64_t V, int64_t F, int32_t K, int32_t rank, int32_t world, int64_t* out /*8*/);
 
 #ifdef __cplusplus
 }
