@@ -43,7 +43,7 @@ class Report(C.Structure):
         ("kernel_launches", C.c_int64), ("bulk_rounds", C.c_int64),
         ("dense_scan_launches", C.c_int64), ("ms_dense_scan", C.c_double), ("dense_scan_bytes", C.c_int64),
         ("dense_scan_vertices", C.c_int64), ("bulk_rollbacks", C.c_int64), ("sparse_rounds", C.c_int64),
-        ("ms_sparse", C.c_double),
+        ("ms_sparse", C.c_double), ("sparse_cluster_rounds", C.c_int64),
     ]
 
     def asdict(self):

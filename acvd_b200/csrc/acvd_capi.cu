@@ -605,7 +605,7 @@ static void set_num_clusters_impl(acvd_ctx* c, int32_t K) {
     c->csize.alloc(K); c->mod_round.alloc(K); c->anchor.alloc(K); c->frozen.alloc(K);
     const size_t Kp = (size_t)K + 64;   // room for the equal-chunk in-place all-gather of the statistics (world <= 64)
     c->csum.alloc(Kp * npad); c->cenergy.alloc(Kp); c->ccentroid.alloc(3 * Kp);
-    c->isum.alloc(4 * (size_t)K); c->bulk_cen.alloc(4 * (size_t)K); c->bulk_energy.alloc(K); c->bulk_energy_sum.alloc(1); c->leave_cnt.alloc(K); c->join_cnt.alloc(K);
+    c->isum.alloc(4 * (size_t)K); c->bulk_cen.alloc(4 * (size_t)K + 4); c->cmeta.alloc((size_t)K + 1); c->bulk_energy.alloc(K); c->bulk_energy_sum.alloc(1); c->leave_cnt.alloc(K); c->join_cnt.alloc(K);
     c->best.alloc(K); c->modbits.alloc((size_t)(K + 31) / 32 + 1); c->prop_key.alloc(V); c->prop_dst.alloc(V); c->plist.alloc(V); c->plist_b.alloc(V); c->work.alloc(V);
     {
         const size_t n_tiles = ((size_t)V + 31) / 32;
@@ -766,8 +766,8 @@ static void members_build(acvd_ctx* c) {
     ACVD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, c->memb_cap.p, c->memb_off.p, K + 1, c->stream));
     void* t = cub_temp(c, tb);
     ACVD_CUDA(cub::DeviceScan::ExclusiveSum(t, tb, c->memb_cap.p, c->memb_off.p, K + 1, c->stream));
-    // total slots <= V + K * 16 + V / 2: allocate the bound, no host round trip
-    const size_t slots = (size_t)V + (size_t)V / 2 + 16 * (size_t)K + 64;
+    // total slots <= 2 V + 16 K: allocate the bound, no host round trip
+    const size_t slots = 2 * (size_t)V + 16 * (size_t)K + 64;
     c->memb.alloc(slots); c->memb_tmp.alloc(slots); c->cc_par.alloc(slots); c->cc_sz.alloc(slots);
     ACVD_CUDA(cudaMemsetAsync(c->csize.p, 0, (size_t)K * sizeof(int), c->stream));
     k_members_scatter<<<grid_for(V), kThreads, 0, c->stream>>>(V, K, c->cid.p, c->memb_off.p, c->csize.p, c->memb.p, c->memb_pos.p);
@@ -971,7 +971,7 @@ static ReassignArgs make_args(acvd_ctx* c, const EvalCfg& cfg, int connexity, in
     A.row_ptr = c->row_ptr.p; A.col = c->col.p; A.ell = c->ell.p; A.ringadj = c->ringadj.p; A.vpad = c->vpad; A.cid = c->cid.p;
     A.items = c->items.p; A.csum = c->csum.p; A.cenergy = c->cenergy.p; A.csize = c->csize.p;
     A.mod_round = c->mod_round.p;
-    A.modbits = c->modbits.p;
+    A.modbits = c->modbits.p; A.cmeta = c->cmeta.p; A.blist = c->blist.p; A.blist_cnt = c->blist_cnt.p;
     A.frozen = c->has_frozen ? c->frozen.p : nullptr;
     A.anchor = c->has_anchor ? c->anchor.p : nullptr;
     A.xyz = c->xyz.p;
@@ -1016,6 +1016,36 @@ static void launch_scan_bulk_dense2(acvd_ctx* c, const ReassignArgs& A) {
     const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
     k_scan_bulk_dense2<W, S, MINB><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
 }
+template <int W, int S, int MINB, bool STATIC, int PF, int DBG = 0>
+static void launch_scan_bulk_dense3(acvd_ctx* c, const ReassignArgs& A) {
+    static bool configured[64] = {};
+    if (c->device >= 64 || !configured[c->device]) {
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense3<W, S, MINB, false, STATIC, PF, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W, S)));
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense3<W, S, MINB, true, STATIC, PF, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W, S)));
+        if (c->device < 64) configured[c->device] = true;
+    }
+    const int n_tiles = A.tile_end - A.tile_begin;
+    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
+    if (A.bulk_stage == 1) k_scan_bulk_dense3<W, S, MINB, true, STATIC, PF, DBG><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
+    else k_scan_bulk_dense3<W, S, MINB, false, STATIC, PF, DBG><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
+}
+// split dense scan: k_scan_classify (frontier scan -> candidate list) + k_bulk_decide (decision over the list)
+template <int W, int S, int MINB>
+static void launch_scan_split(acvd_ctx* c, const ReassignArgs& A, int decide_bps) {
+    static bool configured[64] = {};
+    if (c->device >= 64 || !configured[c->device]) {
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_classify<W, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, classify_smem_bytes(W, S)));
+        if (c->device < 64) configured[c->device] = true;
+    }
+    const int n_tiles = A.tile_end - A.tile_begin;
+    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
+    k_scan_classify<W, S, MINB><<<grid, kDenseThreads, classify_smem_bytes(W, S), c->stream>>>(A);
+    ACVD_LAUNCH_CHECK();
+    const int gd = std::min(grid, kNumSMs * decide_bps);
+    if (A.bulk_stage == 1) k_bulk_decide<true><<<gd, 256, 0, c->stream>>>(A, grid);
+    else k_bulk_decide<false><<<gd, 256, 0, c->stream>>>(A, grid);
+    c->launches += 1;
+}
 // (stages, blocks per SM) variants kept for the kernel micro-benchmark (acvd_bench_kernel); variants >= 10 are the
 // second generation of the kernel (static tile assignment, two tiles in flight per warp)
 constexpr int kDenseDefaultVariant = 0;
@@ -1035,6 +1065,24 @@ static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, i
         case 13: launch_scan_bulk_dense2<W, 4, 3>(c, A); break;
         case 14: launch_scan_bulk_dense2<W, 2, 5>(c, A); break;
         case 15: launch_scan_bulk_dense2<W, 4, 4>(c, A); break;
+        case 20: launch_scan_bulk_dense3<W, 3, 4, false, 0>(c, A); break;
+        case 21: launch_scan_bulk_dense3<W, 3, 4, false, 1>(c, A); break;
+        case 22: launch_scan_bulk_dense3<W, 3, 4, false, 2>(c, A); break;
+        case 23: launch_scan_bulk_dense3<W, 2, 4, false, 2>(c, A); break;
+        case 24: launch_scan_bulk_dense3<W, 4, 4, false, 2>(c, A); break;
+        case 25: launch_scan_bulk_dense3<W, 3, 4, true, 2>(c, A); break;
+        case 26: launch_scan_bulk_dense3<W, 3, 3, false, 2>(c, A); break;
+        case 40: launch_scan_split<W, 3, 6>(c, A, 8); break;
+        case 41: launch_scan_split<W, 2, 8>(c, A, 8); break;
+        case 42: launch_scan_split<W, 3, 8>(c, A, 8); break;
+        case 43: launch_scan_split<W, 3, 4>(c, A, 8); break;
+        case 44: launch_scan_split<W, 4, 6>(c, A, 8); break;
+        case 45: launch_scan_split<W, 2, 6>(c, A, 8); break;
+        case 46: launch_scan_split<W, 3, 6>(c, A, 4); break;
+        case 30: launch_scan_bulk_dense3<W, 3, 4, false, 0, 1>(c, A); break;
+        case 31: launch_scan_bulk_dense3<W, 3, 4, false, 0, 2>(c, A); break;
+        case 32: launch_scan_bulk_dense3<W, 3, 6, false, 0, 2>(c, A); break;
+        case 33: launch_scan_bulk_dense3<W, 3, 6, false, 0, 1>(c, A); break;
         default: launch_scan_bulk_dense<W, 3, 4>(c, A); break;
     }
 }
@@ -1187,6 +1235,7 @@ static BulkArgs make_bulk_args(acvd_ctx* c) {
 }
 
 static void bulk_init(acvd_ctx* c) {
+    c->blist.alloc((size_t)c->vpad); c->blist_cnt.alloc(4096);          // candidate list of the split dense scan (one record per vertex at most)
     k_bulk_init<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, payload_npad(c->metric), c->csum.p, make_bulk_args(c));
     ACVD_LAUNCH_CHECK();
 }
@@ -1213,7 +1262,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     if (stage == 1) A.moved_mask = c->moved_mask.p;      // stage 1 can be undone (energy guard)
     BulkArgs B = make_bulk_args(c);
     k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, c->ctr.p,
-                                                          c->round_scalars.p, 2);
+                                                          c->round_scalars.p, 2, c->csize.p, c->cmeta.p);
     ACVD_LAUNCH_CHECK();
     const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS), ge = kNumSMs * 2;
     const int n_tiles = (c->V + 31) / 32;
@@ -1243,13 +1292,10 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
 
 // the stage-1 energy guard tripped: the last bulk round is undone (cluster ids only; the statistics are recomputed
 // from the clustering when the bulk rounds end)
+static void dist_bulk_rollback(acvd_ctx* c);   // dist.cuh
 static void bulk_rollback(acvd_ctx* c) {
     if (c->world > 1) {
-        if (c->last_bulk_total > 0) {
-            k_bulk_rollback_moves<<<kNumSMs * 4, kThreads, 0, c->stream>>>(c->cid.p, c->prop_dst.p, reinterpret_cast<const int2*>(c->moves_all.p),
-                                                                         (int)c->last_bulk_total);
-            ACVD_LAUNCH_CHECK();
-        }
+        if (c->last_bulk_total > 0) dist_bulk_rollback(c);
     } else {
         EvalCfg cfg = make_cfg(0, 0, 0);
         ReassignArgs A = make_args(c, cfg, 0, 0);
@@ -1280,23 +1326,41 @@ static RoundResult finish_round(acvd_ctx* c, int slot = 0, bool last_of_batch = 
 constexpr int kSparseChunk = 512;
 static bool sparse_enabled() { static int v = getenv("ACVD_NO_SPARSE") ? 0 : 1; return v == 1; }
 
+// Shape of a sparse launch: the whole device (cooperative grid) while a round has real work, ONE thread-block cluster once
+// a round evaluates a few thousand vertices or fewer (its cost is then the barriers between its steps).
+constexpr int kSparseClusterBlocks = 8;             // portable cluster size: 8 x 256 threads
+constexpr int64_t kSparseClusterBelow = 3000;       // evaluated vertices per round at or below which the cluster form takes over
+constexpr int64_t kSparseClusterAbove = 12000;      // ... and above which the grid form takes over again
+static bool sparse_cluster_enabled() { return getenv("ACVD_NO_SPARSE_CLUSTER") == nullptr; }   // read per launch (tests switch it)
+
 template <int EM, int STRIDE, int UM>
-static void launch_sparse(acvd_ctx* c, ReassignArgs& A, SparseCtl& S) {
+static void launch_sparse(acvd_ctx* c, ReassignArgs& A, SparseCtl& S, bool cluster) {
+    if (cluster) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(kSparseClusterBlocks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kSparseClusterBlocks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ACVD_CUDA(cudaLaunchKernelEx(&cfg, k_sparse_rounds<EM, STRIDE, UM, true>, A, S));
+        return;
+    }
     static int blocks_per_sm[64] = {};
     int& bps = blocks_per_sm[c->device < 64 ? c->device : 0];
     if (bps == 0) {
-        ACVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sparse_rounds<EM, STRIDE, UM>, kThreads, 0));
+        ACVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sparse_rounds<EM, STRIDE, UM, false>, kThreads, 0));
         if (bps < 1) throw std::runtime_error("k_sparse_rounds does not fit an SM");
         if (bps > 4) bps = 4;
     }
     int n_sm = kNumSMs;
     ACVD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
     void* args[] = {&A, &S};
-    ACVD_CUDA(cudaLaunchCooperativeKernel((void*)k_sparse_rounds<EM, STRIDE, UM>, dim3(n_sm * bps), dim3(kThreads), args, 0, c->stream));
+    ACVD_CUDA(cudaLaunchCooperativeKernel((void*)k_sparse_rounds<EM, STRIDE, UM, false>, dim3(n_sm * bps), dim3(kThreads), args, 0, c->stream));
 }
 
 static int run_sparse_rounds(acvd_ctx* c, const EvalCfg& cfg, int connexity, bool as_iso, int max_rounds, long long stop_props,
-                             int64_t n_prev_props, std::vector<RoundResult>& out) {
+                             int64_t n_prev_props, int64_t last_evaluated, std::vector<RoundResult>& out) {
     const int K = c->K;
     max_rounds = std::max(1, std::min(max_rounds, kSparseChunk));
     c->sp_rc.alloc(kSparseChunk); c->sp_resub.alloc((size_t)kSparseChunk * kMaxPasses); c->sp_ts.alloc((size_t)kSparseChunk * 4);
@@ -1320,19 +1384,27 @@ static int run_sparse_rounds(acvd_ctx* c, const EvalCfg& cfg, int connexity, boo
     S.has_long_rows = c->max_deg > kRingW ? 1 : 0;
     S.stop_props = stop_props;
     S.done = c->sp_done.p;
+    // launch shape from the work of the previous round; the launch ends when the other shape fits better
+    const bool cluster = sparse_cluster_enabled() && S.passes <= 2 && max_rounds > 1 && last_evaluated <= kSparseClusterBelow;
+    S.leave_below = (!cluster && sparse_cluster_enabled() && S.passes <= 2 && max_rounds > 1) ? kSparseClusterBelow : -1;
+    S.leave_above = cluster ? kSparseClusterAbove : -1;
+    if (cluster) {      // the cluster form resets only the key-table entries a round touched: it starts from clean tables
+        ACVD_CUDA(cudaMemsetAsync(c->best.p, 0xff, (size_t)K * sizeof(unsigned long long), c->stream));
+        ACVD_CUDA(cudaMemsetAsync(c->best2.p, 0xff, (size_t)K * sizeof(unsigned long long), c->stream));
+    }
     ACVD_CUDA(cudaMemsetAsync(c->sp_rc.p, 0, (size_t)max_rounds * sizeof(RoundCounters), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->sp_nmod.p + 1, 0, (size_t)max_rounds * sizeof(unsigned long long), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->sp_resub.p, 0, (size_t)max_rounds * kMaxPasses * sizeof(unsigned long long), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->sp_done.p, 0, 4 * sizeof(int), c->stream));
     ACVD_CUDA(cudaEventRecord(c->ev[0], c->stream));
     switch (c->metric) {
-        case M_ISO: launch_sparse<M_ISO, 4, M_ISO>(c, A, S); break;
+        case M_ISO: launch_sparse<M_ISO, 4, M_ISO>(c, A, S, cluster); break;
         case M_QEM:
-            if (as_iso) launch_sparse<M_ISO, 14, M_QEM>(c, A, S);
-            else launch_sparse<M_QEM, 14, M_QEM>(c, A, S);
+            if (as_iso) launch_sparse<M_ISO, 14, M_QEM>(c, A, S, cluster);
+            else launch_sparse<M_QEM, 14, M_QEM>(c, A, S, cluster);
             break;
-        case M_ANISO: launch_sparse<M_ANISO, 14, M_ANISO>(c, A, S); break;
-        default: launch_sparse<M_ANISOQ, 22, M_ANISOQ>(c, A, S); break;
+        case M_ANISO: launch_sparse<M_ANISO, 14, M_ANISO>(c, A, S, cluster); break;
+        default: launch_sparse<M_ANISOQ, 22, M_ANISOQ>(c, A, S, cluster); break;
     }
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -1376,6 +1448,7 @@ static int run_sparse_rounds(acvd_ctx* c, const EvalCfg& cfg, int connexity, boo
     if (out.back().overflow) c->members_valid = false;
     c->last_all_tiles = 0; c->last_bulk = 0; c->last_dense_kernel = false; c->dense_next = false;
     c->launches += 1;
+    c->last_sparse_cluster = cluster;
     return n_done;
 }
 
@@ -1478,6 +1551,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     timed_clean([&] { fill_holes(c, connexity); recompute_statistics(c, constrained, qlevel, thr); });
     int force_all = 1;
     int64_t last_proposals = -1;
+    unsigned long long last_evaluated = 1ull << 62;   // dirty vertices of the previous round (picks the shape of a sparse launch)
     bool reeval_all = false;   // first replicated round of a multi-GPU tail
     int nconv = 0;
     // earlyStopItems = items of non-frozen clusters (:733-736)
@@ -1561,6 +1635,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         // re-evaluates every boundary vertex, because stored proposals are only known to the rank that owns them.
         RoundResult r;
         memset(&r, 0, sizeof r);
+        const unsigned long long r_prev_evaluated = last_evaluated;
         int64_t synced_proposals = -1;             // multi-GPU: live proposals installed on every rank at the switch to the replicated tail
         if (force_all) c->replicated_tail = false;
         auto account = [&](const RoundResult& q) {
@@ -1570,6 +1645,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
             R.round_launches++; R.evaluate_bytes += eval_bytes(c, q, as_iso); R.evaluated += (int64_t)q.evaluated;
             if (q.sparse) {
                 R.sparse_rounds++; R.ms_sparse += q.ms_scan + q.ms_eval + q.ms_commit;
+                if (c->last_sparse_cluster) R.sparse_cluster_rounds++;
                 R.scan_bytes += sparse_scan_bytes(c, q);
             } else R.scan_bytes += scan_bytes(c, q);
             if (p.log_energy) c->energy_log.push_back(global_energy(c));
@@ -1597,7 +1673,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
             const long long stop_props = nconv <= 1 ? (long long)(early_items / p.early_stop_div) : -1;
             std::vector<RoundResult> rr;
             const int n = run_sparse_rounds(c, cfg, connexity, as_iso, per_round ? 1 : (int)std::min<int64_t>(budget, kSparseChunk),
-                                            stop_props, last_proposals, rr);
+                                            stop_props, last_proposals, (int64_t)r_prev_evaluated, rr);
             for (int j = 0; j + 1 < n; j++) account(rr[j]);
             r = rr[n - 1];
         } else if (c->world > 1 && !c->replicated_tail) {
@@ -1620,6 +1696,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
             reeval_all = false;
         }
         last_proposals = synced_proposals >= 0 ? synced_proposals : (int64_t)r.proposals;
+        last_evaluated = r.evaluated;
         force_all = 0;
         account(r);
         const int64_t mods = (int64_t)r.mods;
@@ -1759,7 +1836,8 @@ extern "C" int acvd_bench_kernel(acvd_ctx* c, int kernel, int variant, int stage
     ReassignArgs A = make_args(c, cfg, 0, 0);
     A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 1;
     A.all_tiles = 1; A.sig_mode = 1; A.tile_begin = 0; A.tile_end = (c->V + 31) / 32;
-    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, 0, c->modbits.p);
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, 0, c->modbits.p, nullptr, nullptr, 0,
+                                                          c->csize.p, c->cmeta.p);
     ACVD_LAUNCH_CHECK();
     const int gs = grid_for((int64_t)c->V, kThreads, ACVD_SCAN_BPS);
     EventPair evp;

@@ -55,6 +55,8 @@ struct acvd_ctx {
     DevBuf<int> prop_dst, plist, plist_b, work, tile_sig, active_tiles;
     DevBuf<unsigned char> tile_active, tile_stale;
     DevBuf<unsigned> moved_mask;                // stage-1 bulk rounds: vertices the last commit moved (rollback)
+    bool last_bulk_seg = false;                 // ... laid out as fixed-size segments (one-collective exchange)
+    long long last_seg_bytes = 0, last_seg_cap = 0, bulk_cap_next = 0;   // segment geometry; capacity of the next round's segments
     int64_t last_bulk_total = 0;                // multi-GPU: move records of the last bulk round (in moves_all)
     DevBuf<unsigned> prop_mask;                 // bulk rounds: proposing vertices, one bit per vertex
     DevBuf<unsigned long long> round_scalars;   // [0] active tiles, [1] proposals of the previous round
@@ -68,6 +70,7 @@ struct acvd_ctx {
     DevBuf<unsigned long long> best2, sp_nmod, sp_resub, sp_ts;
     DevBuf<RoundCounters> sp_rc;
     bool members_valid = false;
+    bool last_sparse_cluster = false;  // the last sparse launch was the one-cluster form
     int mod_par = 0;                  // which modlist the last round wrote (0 / 1)
     bool modlist_valid = false;       // ... and whether it describes the last round completely
     RoundCounters* h_sp_rc = nullptr; // pinned mirrors of the per-round records of one sparse launch
@@ -79,6 +82,9 @@ struct acvd_ctx {
     double fx_scale = 0.0;
     DevBuf<double2> prop_e;
     DevBuf<unsigned> modbits;
+    DevBuf<int4> blist;           // split dense bulk scan: candidate list (vpad entries), segment counts
+    DevBuf<int> blist_cnt;
+    DevBuf<int> cmeta;            // K + 1: size | modified << 31, for the dense bulk scan
     DevBuf<RoundCounters> ctr;
     int commit_passes = 4;            // select+commit passes per round (ACVD_COMMIT_PASSES)
     RoundCounters* h_ctr = nullptr;   // pinned, kRoundSlots entries (rounds launched back to back report into separate slots)

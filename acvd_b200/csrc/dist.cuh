@@ -246,6 +246,111 @@ static RoundResult run_round_dist(acvd_ctx* c, const EvalCfg& cfg, int connexity
     return r;
 }
 
+// ---- one-collective exchange of the bulk rounds.  Every rank sends ONE fixed-size segment -- a 64-byte header (its move
+// count and the round's counters) followed by room for `cap` (vertex, destination) records -- in a single ncclAllGather;
+// the kernels that apply the moves read the counts from the gathered headers on the device, so the round needs no host
+// round trip between packing and applying (the two-step form -- headers, host sync, one broadcast per rank -- costs more
+// than the scan of a rank's share of the mesh).  `cap` follows the previous round's largest count with a margin; a rank
+// that would overflow it says so in its header, every rank then skips the round's apply (same headers, same decision)
+// and the host repeats the exchange in the two-step form.
+struct SegMoves { const unsigned char* base; long long seg_bytes; long long cap; int world; };
+__device__ __forceinline__ long long seg_count(const SegMoves& S, int r) {
+    return (long long)*reinterpret_cast<const unsigned long long*>(S.base + (size_t)r * S.seg_bytes);
+}
+__device__ __forceinline__ const int2* seg_records(const SegMoves& S, int r) {
+    return reinterpret_cast<const int2*>(S.base + (size_t)r * S.seg_bytes + 64);
+}
+__device__ __forceinline__ bool seg_overflowed(const SegMoves& S) {
+    bool o = false;
+    for (int r = 0; r < S.world; r++) o |= seg_count(S, r) > S.cap;
+    return o;
+}
+
+// k_pack_bulk_moves with a bound: records beyond `cap` are dropped (the count still says how many there were) and the
+// proposal masks are left alone, so that an overflowing round can be packed again
+__global__ void __launch_bounds__(kThreads) k_pack_bulk_moves_cap(ReassignArgs A, int2* moves, unsigned long long* n_moves, long long cap) {
+    const int n_tiles = A.tile_end - A.tile_begin;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 32; base < n_tiles; base += n_warps * 32) {
+        const int t = A.tile_begin + base + lane;
+        const unsigned m = (base + lane < n_tiles) ? A.prop_mask[t] : 0u;
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        long long slot0 = 0;
+        if (lane == 0) slot0 = (long long)atomicAdd(n_moves, (unsigned long long)total);
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        const long long my_off = slot0 + incl - cnt;
+        unsigned nz = __ballot_sync(0xffffffffu, m != 0);
+        while (nz) {
+            const int src = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned mm = __shfl_sync(0xffffffffu, m, src);
+            const long long off = __shfl_sync(0xffffffffu, my_off, src);
+            if ((mm >> lane) & 1u) {
+                const int v = (A.tile_begin + base + src) * 32 + lane;
+                const long long q = off + __popc(mm & ((1u << lane) - 1u));
+                if (q < cap) moves[q] = make_int2(v, A.prop_dst[v]);
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_bulk_count_seg(int K, const int* __restrict__ cid, SegMoves S, int* leave_cnt) {
+    if (seg_overflowed(S)) return;
+    for (int r = 0; r < S.world; r++) {
+        const int n = (int)seg_count(S, r);
+        const int2* moves = seg_records(S, r);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int a = cid[moves[i].x];
+            if (a < K) atomicAdd(&leave_cnt[a], 1);
+        }
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_bulk_apply_seg(ReassignArgs A, BulkArgs B, int stride, SegMoves S) {
+    if (seg_overflowed(S)) return;
+    const int K = A.K;
+    unsigned n_mods = 0;
+    for (int r = 0; r < S.world; r++) {
+        const int n = (int)seg_count(S, r);
+        const int2* moves = seg_records(S, r);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int v = moves[i].x, d = moves[i].y;
+            const int a = A.cid[v];
+            if (a < K && B.leave_cnt[a] >= A.csize[a]) continue;
+            const double* it = A.items + (int64_t)v * stride;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                long long f = __double2ll_rn(__ldg(it + k) * B.scale);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)d + k]), (unsigned long long)f);
+                if (a < K) atomicAdd(reinterpret_cast<unsigned long long*>(&B.isum[4 * (int64_t)a + k]), (unsigned long long)(-f));
+            }
+            atomicAdd(&B.join_cnt[d], 1);
+            A.mod_round[d] = A.round;
+            if (a < K) A.mod_round[a] = A.round;
+            A.cid[v] = d;
+            A.prop_dst[v] = a;          // what the rollback restores
+            mark_tiles_stale(A, v);
+            n_mods++;
+        }
+    }
+    warp_count_add(&A.ctr->mods, n_mods);
+}
+__global__ void __launch_bounds__(kThreads) k_bulk_rollback_seg(int* cid, const int* __restrict__ prev, SegMoves S) {
+    for (int r = 0; r < S.world; r++) {
+        const int n = (int)seg_count(S, r);
+        const int2* moves = seg_records(S, r);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int v = moves[i].x;
+            if (cid[v] == moves[i].y) cid[v] = prev[v];
+        }
+    }
+}
+static bool dist_one_collective() { return getenv("ACVD_DIST_TWO_STEP") == nullptr; }    // A/B knob (read per round)
+
 // bulk (Lloyd-criterion) round on `world` GPUs: local scan + evaluate, all-gather of the (vertex, destination)
 // pairs, then every rank counts leavers and applies all moves (integer sums: order-independent)
 static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
@@ -257,7 +362,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     BulkArgs B = make_bulk_args(c);
     ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p);
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, nullptr, nullptr, 0, c->csize.p, c->cmeta.p);
     ACVD_LAUNCH_CHECK();
     int t0, t1;
     dist_tile_range(c, t0, t1);
@@ -276,14 +381,69 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     k_bulk_evaluate<<<ge, kThreads, 0, c->stream>>>(A, B, 0, stage, payload_npad(c->metric));
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    RoundResult r;
+    memset(&r, 0, sizeof r);
+    const int W = c->world;
+    c->last_bulk_seg = false;
+    bool exchanged = false;
+    if (!force_all && c->bulk_cap_next > 0 && dist_one_collective()) {
+        // ---- one collective: fixed-size segments, counts read on the device
+        const long long cap = c->bulk_cap_next;
+        const size_t seg = 64 + (size_t)cap * sizeof(int2);
+        c->moves_local.alloc(seg); c->moves_all.alloc(seg * (size_t)W);
+        ACVD_CUDA(cudaMemsetAsync(c->n_moves.p, 0, sizeof(unsigned long long), c->stream));
+        k_pack_bulk_moves_cap<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<int2*>(c->moves_local.p + 64), c->n_moves.p, cap);
+        ACVD_LAUNCH_CHECK();
+        k_pack_header<<<1, 32, 0, c->stream>>>(c->ctr.p, c->round_scalars.p, c->n_moves.p, reinterpret_cast<unsigned long long*>(c->moves_local.p));
+        ACVD_LAUNCH_CHECK();
+        ACVD_NCCL(nccl().AllGather(c->moves_local.p, c->moves_all.p, seg, ncclChar, c->comm, c->stream));
+        SegMoves S{reinterpret_cast<const unsigned char*>(c->moves_all.p), (long long)seg, cap, W};
+        k_bulk_count_seg<<<gc, kThreads, 0, c->stream>>>(c->K, c->cid.p, S, c->leave_cnt.p);
+        ACVD_LAUNCH_CHECK();
+        k_bulk_apply_seg<<<gc, kThreads, 0, c->stream>>>(A, B, payload_npad(c->metric), S);
+        ACVD_LAUNCH_CHECK();
+        k_bulk_refresh<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->csize.p, B);
+        ACVD_LAUNCH_CHECK();
+        ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        ACVD_CUDA(cudaMemcpy2DAsync(c->h_hdr, 64, c->moves_all.p, seg, 64, (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
+        ACVD_CUDA(cudaStreamSynchronize(c->stream));
+        long long mx = 0, total = 0;
+        for (int i = 0; i < W; i++) {
+            const unsigned long long* h = c->h_hdr + 8 * i;
+            mx = std::max<long long>(mx, (long long)h[0]); total += (long long)h[0];
+            r.proposals += h[1]; r.tests += h[2]; r.evaluated += h[3]; r.boundary += h[4]; r.active_tiles += h[5];
+        }
+        c->bulk_cap_next = std::max<long long>(4096, mx + mx / 2 + 1024);
+        if (mx <= cap) {
+            exchanged = true;
+            c->last_bulk_seg = true; c->last_bulk_total = total; c->last_seg_bytes = (long long)seg; c->last_seg_cap = cap;
+            // the proposal masks of the rank's range were left in place for a possible second packing
+            ACVD_CUDA(cudaMemsetAsync(c->prop_mask.p + t0, 0, (size_t)own_tiles * sizeof(unsigned), c->stream));
+            r.mods = c->h_ctr->mods;
+            ACVD_CUDA(cudaEventElapsedTime(&r.ms_scan, c->ev[0], c->ev[3]));
+            ACVD_CUDA(cudaEventElapsedTime(&r.ms_eval, c->ev[3], c->ev[1]));
+            ACVD_CUDA(cudaEventElapsedTime(&r.ms_commit, c->ev[1], c->ev[2]));
+            c->round++;
+            c->stats_valid = false;
+            update_density(c, r);
+            return r;
+        }
+        // some rank had more moves than the segment holds: nothing was applied anywhere; repeat in the two-step form
+        memset(&r, 0, sizeof r);
+    }
+    (void)exchanged;
     c->moves_local.alloc(((size_t)(own_tiles) * 32 + 64) * sizeof(int2));
     ACVD_CUDA(cudaMemsetAsync(c->n_moves.p, 0, sizeof(unsigned long long), c->stream));
     k_pack_bulk_moves<<<gc, kThreads, 0, c->stream>>>(A, reinterpret_cast<int2*>(c->moves_local.p), c->n_moves.p);
     ACVD_LAUNCH_CHECK();
-    RoundResult r;
-    memset(&r, 0, sizeof r);
     const int64_t total = dist_gather_moves(c, sizeof(int2), r);
     c->last_bulk_total = total;
+    {   // the next round's segment capacity from this round's largest per-rank count
+        long long mx = 0;
+        for (int i = 0; i < W; i++) mx = std::max<long long>(mx, (long long)c->h_hdr[8 * i]);
+        c->bulk_cap_next = std::max<long long>(4096, mx + mx / 2 + 1024);
+    }
     if (total > 0) {
         const int2* mv = reinterpret_cast<const int2*>(c->moves_all.p);
         k_bulk_count<<<gc, kThreads, 0, c->stream>>>(c->K, c->cid.p, mv, (int)total, c->leave_cnt.p);
@@ -304,4 +464,16 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     c->stats_valid = false;
     update_density(c, r);
     return r;
+}
+
+// undo of the last bulk round's moves (stage-1 energy guard), whichever way they were exchanged
+static void dist_bulk_rollback(acvd_ctx* c) {
+    if (c->last_bulk_seg) {
+        SegMoves S{reinterpret_cast<const unsigned char*>(c->moves_all.p), c->last_seg_bytes, c->last_seg_cap, c->world};
+        k_bulk_rollback_seg<<<kNumSMs * 4, kThreads, 0, c->stream>>>(c->cid.p, c->prop_dst.p, S);
+    } else {
+        k_bulk_rollback_moves<<<kNumSMs * 4, kThreads, 0, c->stream>>>(c->cid.p, c->prop_dst.p, reinterpret_cast<const int2*>(c->moves_all.p),
+                                                                     (int)c->last_bulk_total);
+    }
+    ACVD_LAUNCH_CHECK();
 }

@@ -89,7 +89,8 @@ static __device__ __noinline__ bool connexity_problem(int v, int a, const int* _
 // active-tile count and the round counters are zeroed.
 __global__ void __launch_bounds__(kThreads) k_modbits(int K, const int* __restrict__ mod_round, int rm1, int force_all,
                                                       unsigned* __restrict__ bits, RoundCounters* ctr = nullptr,
-                                                      unsigned long long* round_scalars = nullptr, int prev_mode = 0) {
+                                                      unsigned long long* round_scalars = nullptr, int prev_mode = 0,
+                                                      const int* __restrict__ csize = nullptr, int* __restrict__ cmeta = nullptr) {
     if (ctr && blockIdx.x == 0 && threadIdx.x == 0) {
         if (prev_mode == 1) round_scalars[1] = ctr->proposals;
         else if (prev_mode == 2) round_scalars[1] = 0;
@@ -102,6 +103,8 @@ __global__ void __launch_bounds__(kThreads) k_modbits(int K, const int* __restri
         bool m = c < K && (force_all || mod_round[c] >= rm1);
         unsigned w = __ballot_sync(0xffffffffu, m);
         if ((threadIdx.x & 31) == 0) bits[c >> 5] = w;
+        // size and modified flag in one word: one load per cluster in the dense bulk scan (entry K = the NULL cluster)
+        if (cmeta && c <= K) cmeta[c] = c < K ? (csize[c] | (m ? (int)0x80000000 : 0)) : 0;
     }
 }
 

@@ -36,6 +36,7 @@ struct ReassignArgs {
     int* csize;                         // K
     int* mod_round;                     // K: last round a cluster was modified
     unsigned* modbits;                  // ceil(K/32) words: cluster modified in the previous round
+    const int* cmeta;                   // K + 1: cluster size, bit 31 = modified in the previous round (bulk rounds; written by k_modbits)
     const unsigned char* __restrict__ frozen;   // K or null
     const int* __restrict__ anchor;     // K or null (QEM fixed clusters)
     const float* __restrict__ xyz;      // V x 3 (anchor coordinates)
@@ -66,6 +67,8 @@ struct ReassignArgs {
     int bulk_stage;                     // 0: Lloyd criterion, 1: delta-E criterion against the round-start sums
     int bulk_count_leave;               // count leavers per cluster here (single GPU) or after the all-gather
     const double* bulk_cen;             // K x 4 centroid + weight
+    int4* blist;                        // split dense bulk scan: (vertex, up to three candidate clusters in slot order) per dirty boundary vertex,
+    int* blist_cnt;                     //   one segment per scanning block (segment b starts at its first tile x 32), and the segment lengths
     int* bulk_leave;                    // K
     int item_stride;                    // doubles per item row
     int all_tiles;                      // dense round: scan tiles [tile_begin, tile_end) directly, no filter / list

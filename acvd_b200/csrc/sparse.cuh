@@ -42,10 +42,11 @@ __global__ void __launch_bounds__(kThreads) k_members_count(int V, int K, const 
         if (c < K && lane == __ffs(peers) - 1) atomicAdd(cnt + c, __popc(peers));
     }
 }
-// capacity = size + slack: clusters drift by a few vertices during the exact rounds of a phase
+// capacity = twice the size (at least size + 16): a cluster whose array fills up ends the sparse launch and has the arrays
+// rebuilt; with half the size as slack the anisotropic configurations (C3) relaunched every ~17 rounds
 __global__ void k_members_cap(int K, const int* cnt, int* cap) {   // in place
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= K; c += gridDim.x * blockDim.x)
-        cap[c] = c < K ? cnt[c] + max(16, cnt[c] >> 1) : 0;
+        cap[c] = c < K ? cnt[c] + max(16, cnt[c]) : 0;
 }
 // fills the arrays (order inside a cluster depends on the atomics: k_cluster_pass sorts it) and leaves the sizes in csize
 __global__ void __launch_bounds__(kThreads) k_members_scatter(int V, int K, const int* __restrict__ cid, const int* __restrict__ off,
@@ -434,12 +435,29 @@ struct SparseCtl {
     int max_rounds, passes, has_long_rows;
     long long stop_props;              // convergence event on "live proposals <= stop_props" (first two phases), -1 = off
     int* done;                         // [0] rounds executed
+    long long leave_below, leave_above;   // the launch ends after a round that evaluated <= / > this many vertices (-1: off): the
+                                          // host continues with the launch shape that fits the work (grid <-> one cluster)
 };
 
-// EM / STRIDE / UM as in k_evaluate / k_commit.  Cooperative launch, one resident wave of blocks.
-template <int EM, int STRIDE, int UM>
+// Barrier between the steps of a round.  CL = false: cooperative launch over the whole device (grid barrier).
+// CL = true: the launch is ONE thread-block cluster -- the long tail of a phase moves a few hundred vertices per round,
+// and what a round costs there is its five or six device-wide barriers, not its work; the hardware cluster barrier
+// costs a fraction of a grid barrier.
+template <bool CL>
+__device__ __forceinline__ void rounds_barrier() {
+    if constexpr (CL) {
+        __threadfence();                              // the steps exchange data through global memory
+        cg::this_cluster().sync();
+    } else cg::this_grid().sync();
+}
+
+// EM / STRIDE / UM as in k_evaluate / k_commit.  CL = false: cooperative launch, one resident wave of blocks;
+// CL = true: one cluster of blocks.  The key tables (best0 / best1: minimum priority key per cluster) must read
+// "no key" where a round looks: the grid form clears them wholesale while it enumerates (K entries spread over ~75 k
+// threads); the cluster form resets exactly the entries the previous round touched -- the clusters of its proposals
+// and the clusters its commits modified -- and expects clean tables at launch (host memset).
+template <int EM, int STRIDE, int UM, bool CL>
 __global__ void __launch_bounds__(kThreads, 2) k_sparse_rounds(const __grid_constant__ ReassignArgs A0, const __grid_constant__ SparseCtl S) {
-    cg::grid_group grid = cg::this_grid();
     __shared__ int s_buf[(kThreads / 32) * kPushBuf];
     __shared__ ReassignArgs sA[2];      // the round's arguments (per-round fields patched in), double-buffered by round parity
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
@@ -463,38 +481,54 @@ __global__ void __launch_bounds__(kThreads, 2) k_sparse_rounds(const __grid_cons
         const int n_modin = (int)S.n_mod[it];
         const int n_prev = it == 0 ? (int)S.n_prev_props : (int)S.rc[it - 1].proposals;
         // ---- enumerate the dirty set (and clear the key table of the first pass)
-        for (int i = tid; i < K; i += n_threads) S.best0[i] = ~0ull;
+        if constexpr (CL) {
+            if (it > 0) {       // the entries the previous round touched: its surviving proposals' clusters + the clusters it modified
+                const ReassignArgs& P = sA[(it - 1) & 1];
+                for (int i = tid; i < n_prev; i += n_threads) {
+                    const int v = P.plist[i];
+                    const int d = P.prop_dst[v];
+                    if (d < 0) continue;
+                    const int a = P.cid[v];
+                    if (a < K) { S.best0[a] = ~0ull; S.best1[a] = ~0ull; }
+                    S.best0[d] = ~0ull; S.best1[d] = ~0ull;
+                }
+                for (int i = tid; i < n_modin; i += n_threads) { const int c = modin[i]; S.best0[c] = ~0ull; S.best1[c] = ~0ull; }
+            }
+        } else {
+            for (int i = tid; i < K; i += n_threads) S.best0[i] = ~0ull;
+        }
         enumerate_modified(A, modin, n_modin, s_buf);
-        grid.sync();
+        rounds_barrier<CL>();
         if (tid == 0) S.ts[4 * it] = global_timer_ns();
         // ---- evaluate it; untouched live proposals compete again
         const int n_work = (int)A.ctr->evaluated;
         carry_sparse(A, n_prev);
         evaluate_list<EM, STRIDE>(A, n_work);
         if (S.has_long_rows) evaluate_long_list<EM, STRIDE>(A, n_work);
-        grid.sync();
+        rounds_barrier<CL>();
         if (tid == 0) S.ts[4 * it + 1] = global_timer_ns();
         // ---- select + commit passes: a pass is skipped (and the round ends) when nothing could be resubmitted to it
         const int n_props = (int)A.ctr->proposals;
         for (int pass = 0; pass < S.passes; pass++) {
-            if (threadIdx.x == 0) A.best = (pass & 1) ? S.best1 : S.best0;      // (the previous use of A ended at a grid barrier)
+            if (threadIdx.x == 0) A.best = (pass & 1) ? S.best1 : S.best0;      // (the previous use of A ended at a barrier)
             __syncthreads();
             if (pass > 0) {
                 resubmit_list(A, n_props, S.resub + it * kMaxPasses + pass);
-                grid.sync();
+                rounds_barrier<CL>();
                 if (S.resub[it * kMaxPasses + pass] == 0) break;
             }
-            if (pass + 1 < S.passes) {                       // the next pass's key table is idle during this commit
+            if (!CL && pass + 1 < S.passes) {                // the next pass's key table is idle during this commit
                 unsigned long long* other = (pass & 1) ? S.best0 : S.best1;
                 for (int i = tid; i < K; i += n_threads) other[i] = ~0ull;
             }
             commit_list<EM, UM>(A, n_props);
-            grid.sync();
+            rounds_barrier<CL>();
         }
         if (tid == 0) S.ts[4 * it + 2] = global_timer_ns();
         const unsigned long long mods = A.ctr->mods;
         it++;
         if (mods == 0 || (S.stop_props >= 0 && (long long)n_props <= S.stop_props) || (A.mem.overflow && *A.mem.overflow)) break;
+        if ((S.leave_below >= 0 && n_work <= S.leave_below) || (S.leave_above >= 0 && n_work > S.leave_above)) break;
     }
     if (tid == 0) S.done[0] = it;
 }

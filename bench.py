@@ -480,8 +480,16 @@ def main():
     roof_dense = kernel_roof("k_scan_bulk_dense", "k_scan_bulk_dense (TMA-staged frontier scan + bulk decision of the reassignment loop, all tiles)",
                              S("dense_scan_bytes"), S("ms_dense_scan"), S("dense_scan_launches"))
     if S("dense_scan_launches"):
-        roof_dense["scan_only_GBps"] = S("dense_scan_vertices") / world * 56.0 / (S("ms_dense_scan") * 1e-3) / 1e9
-        roof_dense["scan_only_note"] = "frontier-scan bytes alone (8 + 8 deg = 56 B per vertex, SURVEY 8d), without the tests' operands"
+        # roofline.achieved / frac count the HBM-compulsory bytes only: SURVEY 8d's frontier-scan figure, 8 + 8 deg = 56 B per
+        # vertex (row_ptr / own cluster id / neighbour ids / neighbour cluster ids), times the vertices one launch scans.
+        # The operands of the tests (centroids, sizes: gathers the kernel serves from L1/L2) are reported beside it.
+        with_ops = dict(GBps=roof_dense["achieved"], frac=roof_dense["frac"], bytes_per_launch=roof_dense["bytes_per_launch"],
+                        note="scan bytes + the tests' operands (per decided vertex 48 B, per test 32 B, per proposal 8 B): L1/L2-resident gathers, not HBM traffic")
+        scan_b = S("dense_scan_vertices") / world * 56.0
+        ach = scan_b / (S("ms_dense_scan") * 1e-3) / 1e9
+        roof_dense.update(achieved=ach, frac=ach / peak, bytes_per_launch=scan_b / S("dense_scan_launches"),
+                          bytes_model=f"56 B per vertex (SURVEY 8d frontier scan: 8 + 8 deg, deg = 6) x {int(S('dense_scan_vertices') / world / S('dense_scan_launches'))} vertices per launch",
+                          with_test_operands=with_ops)
     roof_scan = kernel_roof("k_scan_avg", "k_scan (all frontier-scan launches of the loop, dense + list-based)", S("scan_bytes"), S("ms_scan"), n_l)
     # (the ncu DRAM figures of these two are per full-activity launch and do not pair with per-launch averages over a
     # whole run, so no `traffic` is attached to them; profiles/README.md has the full-launch captures)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ACVD_B200_ABI_VERSION 3
+#define ACVD_B200_ABI_VERSION 4
 
 typedef struct acvd_ctx acvd_ctx;
 
@@ -159,6 +159,7 @@ typedef struct acvd_report {
     int64_t bulk_rollbacks;      /* stage-1 bulk rounds undone by the energy guard (0 or 1 per phase) */
     int64_t sparse_rounds;       /* exact rounds run inside the persistent sparse-round kernel (k_sparse_rounds) */
     double ms_sparse;            /* device time of those rounds (enumerate + evaluate + commit, %globaltimer inside the kernel) */
+    int64_t sparse_cluster_rounds; /* of those, rounds run by the one-cluster form of the kernel (a few thousand dirty vertices or fewer) */
 } acvd_report;
 
 /* MinimizeEnergy (Common/vtkUniformClustering.h:725-830) with ProcessOneLoop (:833-995) replaced by

@@ -320,7 +320,7 @@ def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle,
     else:
         (p, t), ind, K, grad = spindle, None, 150, 0.0
     res = []
-    for no_dense, variant in (("", "0"), ("1", "0"), ("", "10"), ("", "11")):   # 10, 11: second-generation kernel (two tiles in flight)
+    for no_dense, variant in (("", "0"), ("1", "0"), ("", "10"), ("", "11"), ("", "20"), ("", "22"), ("", "25"), ("", "40"), ("", "41")):   # 40, 41: split form (classify + decide)   # 10, 11: second generation (two tiles in flight); 20, 21: third (min/max candidates)
         monkeypatch.setenv("ACVD_DENSE_VARIANT", variant)
         if no_dense:
             monkeypatch.setenv("ACVD_NO_DENSE_SCAN", "1")
@@ -745,7 +745,7 @@ def test_baseline_size_energy_vs_oracle(oracle_mod, gpu_ctx_factory, name):
 
 
 @pytest.mark.parametrize("case", ["torus-qem", "sphere-iso", "spindle-qem", "ellipsoid-anisoq", "sphere-qem-passes4"])
-def test_sparse_rounds_equal_tile_filter_rounds(gpu_ctx_factory, sphere, torus, spindle, case):
+def test_sparse_rounds_equal_tile_filter_rounds(gpu_ctx_factory, sphere, torus, spindle, case, monkeypatch):
     """The persistent sparse-round kernel (dirty set enumerated from the member arrays of the modified clusters,
     convergence decided on the device) takes the decisions of the tile-filter path round for round: same clustering,
     same number of rounds, vertex tests, proposals and moves, same energy -- the "recently modified" rule of
@@ -775,15 +775,23 @@ def test_sparse_rounds_equal_tile_filter_rounds(gpu_ctx_factory, sphere, torus, 
     g.initial_sampling()
     g.save_clustering()
     out = {}
-    for sparse in (0, -1):
+    # 0: sparse rounds, launch shape chosen by the work (grid / one cluster); "grid": cluster form off; -1: tile-filter path
+    for sparse in (0, "grid", -1):
+        if sparse == "grid":
+            monkeypatch.setenv("ACVD_NO_SPARSE_CLUSTER", "1")
+        else:
+            monkeypatch.delenv("ACVD_NO_SPARSE_CLUSTER", raising=False)
         g.restore_clustering()
-        rep = g.minimize(unconstrained_init=uncon, sparse_rounds=sparse, **kw)
+        rep = g.minimize(unconstrained_init=uncon, sparse_rounds=-1 if sparse == -1 else 0, **kw)
         out[sparse] = (g.clustering().copy(), rep)
-    (c0, r0), (c1, r1) = out[0], out[-1]
-    assert r0["sparse_rounds"] > 0 and r1["sparse_rounds"] == 0
-    assert np.array_equal(c0, c1)
+    (c0, r0), (cg, rg), (c1, r1) = out[0], out["grid"], out[-1]
+    assert r0["sparse_rounds"] > 0 and rg["sparse_rounds"] > 0 and r1["sparse_rounds"] == 0
+    assert rg["sparse_cluster_rounds"] == 0
+    if case in ("torus-qem", "spindle-qem"):
+        assert r0["sparse_cluster_rounds"] > 0      # these meshes are small: the tail runs in the one-cluster form
+    assert np.array_equal(c0, c1) and np.array_equal(cg, c1)
     for k in ("rounds", "tests", "proposals", "modifications", "convergences", "evaluated", "energy"):
-        assert r0[k] == r1[k], (k, r0[k], r1[k])
+        assert r0[k] == r1[k] == rg[k], (k, r0[k], rg[k], r1[k])
     assert g.clean_clustering() == 0
 
 

@@ -268,7 +268,7 @@ def test_capi_exports_every_declared_symbol(capi_mod):
     assert not missing, missing
     bound = {name for name, _, _ in capi_mod.SYMBOLS}
     assert declared == bound, declared ^ bound
-    assert lib.acvd_abi_version() == int(re.search(r"#define ACVD_B200_ABI_VERSION (\d+)", hdr).group(1)) == 3
+    assert lib.acvd_abi_version() == int(re.search(r"#define ACVD_B200_ABI_VERSION (\d+)", hdr).group(1)) == 4
     assert [lib.acvd_payload_size(m) for m in range(4)] == [4, 13, 13, 22]
 
 
