@@ -301,12 +301,19 @@ class Context:
         self._ck(self.L.acvd_reassign_round(self.h, constrained, quadrics_level, connexity, C.byref(a), C.byref(b), C.byref(c)))
         return dict(proposals=a.value, modifications=b.value, tests=c.value)
 
-    def cluster_stats(self):
+    def cluster_stats(self, out=None):
+        """acvd_get_cluster_stats.  `out` = (sums, centroids, energies, sizes) buffers of the caller (e.g. pinned, reused
+        across calls: fresh pageable arrays cost more in page faults than the copy itself); default: new arrays."""
         np_ = self.L.acvd_payload_size(self.metric)
-        sums = np.zeros((self.K, np_))
-        cen = np.zeros((self.K, 3))
-        en = np.zeros(self.K)
-        sz = np.zeros(self.K, dtype=np.int32)
+        if out is not None:
+            sums, cen, en, sz = out
+            assert sums.shape == (self.K, np_) and cen.shape == (self.K, 3) and en.shape == (self.K,) and sz.shape == (self.K,)
+            assert sums.dtype == np.float64 and cen.dtype == np.float64 and en.dtype == np.float64 and sz.dtype == np.int32
+        else:
+            sums = np.zeros((self.K, np_))
+            cen = np.zeros((self.K, 3))
+            en = np.zeros(self.K)
+            sz = np.zeros(self.K, dtype=np.int32)
         self._ck(self.L.acvd_get_cluster_stats(self.h, _p(sums), _p(cen), _p(en), _p(sz)))
         return sums, cen, en, sz
 

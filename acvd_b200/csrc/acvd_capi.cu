@@ -115,6 +115,8 @@ extern "C" int acvd_create(acvd_ctx** out, int device) {
         c->device = device;
         ACVD_CUDA(cudaSetDevice(device));
         ACVD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        ACVD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : c->copy_ev) ACVD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         {   // keep freed blocks in the pool (the default threshold 0 returns them to the driver at every synchronisation)
             cudaMemPool_t pool;
             ACVD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -139,6 +141,8 @@ extern "C" int acvd_create(acvd_ctx** out, int device) {
 extern "C" int acvd_destroy(acvd_ctx* c) {
     if (!c) return ACVD_OK;
     cudaSetDevice(c->device);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -164,14 +168,24 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     c->vpad = (((int64_t)V + 31) / 32) * 32;      // per-vertex streams are padded to whole 32-vertex tiles (TMA copies whole tiles)
     c->xyz.alloc(3 * (size_t)c->vpad);
     c->tri.alloc(3 * (size_t)F);
+    struct CopyGuard {          // the caller's point array is not read after this call returns, whichever way it returns
+        cudaStream_t s; bool armed = false;
+        ~CopyGuard() { if (armed) cudaStreamSynchronize(s); }
+    } xyz_guard{c->copy_stream};
     {
         TraceScope ts(c, "set_mesh: upload");
         if (c->world > 1) {   // every rank uploads its vertex / face range over its own PCIe link; NVLink completes the copies
             dist_sliced_upload(c, c->xyz.p, xyz, (size_t)V, 3 * sizeof(float));
             dist_sliced_upload(c, c->tri.p, tri, (size_t)F, 3 * sizeof(int));
         } else {
-            ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            // the faces first (everything below is built from them); the points follow on the copy stream and travel
+            // while the adjacency is built (nothing in this call reads them)
             ACVD_CUDA(cudaMemcpyAsync(c->tri.p, tri, 3 * (size_t)F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            ACVD_CUDA(cudaEventRecord(c->copy_ev[0], c->stream));
+            ACVD_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[0], 0));
+            xyz_guard.armed = true;
+            ACVD_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, 3 * (size_t)V * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+            ACVD_CUDA(cudaEventRecord(c->copy_ev[1], c->copy_stream));
         }
         // vertex indices outside [0, V) would index the counting build out of bounds: reject them here
         ACVD_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(unsigned long long), c->stream));
@@ -235,6 +249,7 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
     c->ringadj.alloc((size_t)V);
     k_build_ringadj<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->row_ptr.p, c->col.p, c->ringadj.p);
     ACVD_LAUNCH_CHECK();
+    if (xyz_guard.armed) ACVD_CUDA(cudaStreamWaitEvent(c->stream, c->copy_ev[1], 0));      // later work on the stream sees the points
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     ACVD_API_END(c)
 }
@@ -630,7 +645,7 @@ static void set_num_clusters_impl(acvd_ctx* c, int32_t K) {
     ACVD_CUDA(cudaStreamSynchronize(c->stream));
     c->has_frozen = c->has_anchor = false;
     c->fixed.clear();
-    c->round = 1;
+    c->round = 1; c->cc_since = 0;
     c->stats_valid = false;
 }
 
@@ -642,6 +657,7 @@ extern "C" int acvd_set_num_clusters(acvd_ctx* c, int32_t K) {
 
 extern "C" int acvd_set_clustering(acvd_ctx* c, const int32_t* cl) {
     ACVD_API_BEGIN(c)
+    c->cc_since = 0;      // the clustering changes outside the rounds: the next CleanClustering checks every cluster
     if (!c->K || !cl) throw std::runtime_error("acvd_set_clustering: set the number of clusters first");
     ACVD_CUDA(cudaMemcpyAsync(c->cid.p, cl, (size_t)c->V * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     // ids outside [0, K) are "not assigned" for the reference (:560-561): one NULL value, K, inside the library
@@ -672,6 +688,7 @@ extern "C" int acvd_save_clustering(acvd_ctx* c) {
 
 extern "C" int acvd_restore_clustering(acvd_ctx* c) {
     ACVD_API_BEGIN(c)
+    c->cc_since = 0;      // the clustering changes outside the rounds: the next CleanClustering checks every cluster
     if (!c->K || !c->cid_saved.p) throw std::runtime_error("acvd_restore_clustering: nothing saved");
     ACVD_CUDA(cudaMemcpyAsync(c->cid.p, c->cid_saved.p, (size_t)c->V * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     ACVD_CUDA(cudaMemsetAsync(c->prop_dst.p, 0xff, (size_t)c->V * sizeof(int), c->stream));
@@ -717,6 +734,7 @@ extern "C" int acvd_set_fixed_clusters(acvd_ctx* c, const int64_t* items, int32_
 
 extern "C" int acvd_initial_sampling(acvd_ctx* c) {
     ACVD_API_BEGIN(c)
+    c->cc_since = 0;      // the clustering changes outside the rounds: the next CleanClustering checks every cluster
     if (!c->K || !c->have_items) throw std::runtime_error("acvd_initial_sampling: need items and a cluster count");
     // the rings in the reference's order come from the device (k_ring_order: neighbours sorted by the first half-edge
     // slot of their edge), so the host does not rebuild the edge table; the region growing itself is sequential
@@ -788,6 +806,7 @@ static void cluster_pass(acvd_ctx* c, bool do_cc, bool do_stats, int constrained
     P.cc_par = c->cc_par.p; P.cc_sz = c->cc_sz.p; P.counters = c->scalars.p + 1;
     P.do_sort = 1; P.do_cc = do_cc ? 1 : 0; P.do_stats = do_stats ? 1 : 0;
     P.apply_resets = apply_resets ? 1 : 0; P.k_begin = k_begin; P.k_end = k_end;
+    P.mod_round = c->mod_round.p; P.cc_since = getenv("ACVD_CC_ALL") ? 0 : c->cc_since;
     P.cfg = make_cfg(constrained, qlevel, thr);
     const int blocks = grid_for((int64_t)std::max(1, k_end - k_begin) * 32);
 #define PASS(MM, EE) k_cluster_pass<MM, EE><<<blocks, kThreads, 0, c->stream>>>(P)
@@ -858,6 +877,7 @@ static int clean_clustering(acvd_ctx* c, bool with_stats = false, int constraine
     }
     if (n_reset > 0) { c->stats_valid = false; c->members_valid = false; c->sig_valid = false; }
     if (trace_on()) fprintf(stderr, "[acvd trace]   disconnected %d, reset %d\n", disc, n_reset);
+    c->cc_since = c->round;      // every cluster is connected now: the next check looks at the clusters modified from here on
     return disc;
 }
 
@@ -1030,25 +1050,26 @@ static void launch_scan_bulk_dense3(acvd_ctx* c, const ReassignArgs& A) {
     else k_scan_bulk_dense3<W, S, MINB, false, STATIC, PF, DBG><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
 }
 // split dense scan: k_scan_classify (frontier scan -> candidate list) + k_bulk_decide (decision over the list)
-template <int W, int S, int MINB>
+template <int W, int S, int MINB, int VPL>
 static void launch_scan_split(acvd_ctx* c, const ReassignArgs& A, int decide_bps) {
     static bool configured[64] = {};
     if (c->device >= 64 || !configured[c->device]) {
-        ACVD_CUDA(cudaFuncSetAttribute(k_scan_classify<W, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, classify_smem_bytes(W, S)));
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_classify<W, S, MINB, VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, classify_smem_bytes(W, S, VPL)));
         if (c->device < 64) configured[c->device] = true;
     }
     const int n_tiles = A.tile_end - A.tile_begin;
-    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
-    k_scan_classify<W, S, MINB><<<grid, kDenseThreads, classify_smem_bytes(W, S), c->stream>>>(A);
+    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps * VPL - 1) / (kDenseWarps * VPL)));
+    k_scan_classify<W, S, MINB, VPL><<<grid, kDenseThreads, classify_smem_bytes(W, S, VPL), c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
     const int gd = std::min(grid, kNumSMs * decide_bps);
-    if (A.bulk_stage == 1) k_bulk_decide<true><<<gd, 256, 0, c->stream>>>(A, grid);
-    else k_bulk_decide<false><<<gd, 256, 0, c->stream>>>(A, grid);
+    const int chunk = classify_chunk(n_tiles, grid, VPL);
+    if (A.bulk_stage == 1) k_bulk_decide<true><<<gd, 256, 0, c->stream>>>(A, grid, chunk);
+    else k_bulk_decide<false><<<gd, 256, 0, c->stream>>>(A, grid, chunk);
     c->launches += 1;
 }
 // (stages, blocks per SM) variants kept for the kernel micro-benchmark (acvd_bench_kernel); variants >= 10 are the
 // second generation of the kernel (static tile assignment, two tiles in flight per warp)
-constexpr int kDenseDefaultVariant = 0;
+constexpr int kDenseDefaultVariant = 42;   // split form, 2 tiles per ticket, 2 stages, 4 blocks per SM (C4: 558 us per launch over a run vs 746 us for the fused kernel)
 static int dense_variant() { const char* e = getenv("ACVD_DENSE_VARIANT"); return e ? atoi(e) : kDenseDefaultVariant; }   // read per launch (tests switch it)
 template <int W>
 static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, int variant) {
@@ -1072,13 +1093,14 @@ static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, i
         case 24: launch_scan_bulk_dense3<W, 4, 4, false, 2>(c, A); break;
         case 25: launch_scan_bulk_dense3<W, 3, 4, true, 2>(c, A); break;
         case 26: launch_scan_bulk_dense3<W, 3, 3, false, 2>(c, A); break;
-        case 40: launch_scan_split<W, 3, 6>(c, A, 8); break;
-        case 41: launch_scan_split<W, 2, 8>(c, A, 8); break;
-        case 42: launch_scan_split<W, 3, 8>(c, A, 8); break;
-        case 43: launch_scan_split<W, 3, 4>(c, A, 8); break;
-        case 44: launch_scan_split<W, 4, 6>(c, A, 8); break;
-        case 45: launch_scan_split<W, 2, 6>(c, A, 8); break;
-        case 46: launch_scan_split<W, 3, 6>(c, A, 4); break;
+        case 40: launch_scan_split<W, 3, 6, 1>(c, A, 8); break;
+        case 41: launch_scan_split<W, 2, 8, 1>(c, A, 8); break;
+        case 42: launch_scan_split<W, 2, 4, 2>(c, A, 8); break;
+        case 43: launch_scan_split<W, 3, 4, 2>(c, A, 8); break;
+        case 44: launch_scan_split<W, 2, 5, 2>(c, A, 8); break;
+        case 45: launch_scan_split<W, 2, 3, 4>(c, A, 8); break;
+        case 46: launch_scan_split<W, 2, 4, 4>(c, A, 8); break;
+        case 47: launch_scan_split<W, 3, 3, 2>(c, A, 8); break;
         case 30: launch_scan_bulk_dense3<W, 3, 4, false, 0, 1>(c, A); break;
         case 31: launch_scan_bulk_dense3<W, 3, 4, false, 0, 2>(c, A); break;
         case 32: launch_scan_bulk_dense3<W, 3, 6, false, 0, 2>(c, A); break;
@@ -2090,6 +2112,7 @@ static std::vector<T> download(acvd_ctx* c, const T* d, size_t n) {
 // and the cluster tables are those of the grown cluster count.
 extern "C" int acvd_detect_non_manifold(acvd_ctx* c, int32_t force_manifold_edges, int32_t* n_issues, int32_t* new_num_clusters) {
     ACVD_API_BEGIN(c)
+    c->cc_since = 0;      // the clustering changes outside the rounds: the next CleanClustering checks every cluster
     if (!c->K || !n_issues || !new_num_clusters) throw std::runtime_error("acvd_detect_non_manifold: bad arguments");
     const int V = c->V, K0 = c->K;
     OutputMesh O;

@@ -23,6 +23,8 @@ struct NcclError { ncclResult_t code; const char* what; };
 struct acvd_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;       // uploads that overlap the mesh build (acvd_set_mesh)
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     std::string err;
     // mesh
     int V = 0, F = 0;
@@ -89,6 +91,7 @@ struct acvd_ctx {
     int commit_passes = 4;            // select+commit passes per round (ACVD_COMMIT_PASSES)
     RoundCounters* h_ctr = nullptr;   // pinned, kRoundSlots entries (rounds launched back to back report into separate slots)
     int round = 1;
+    int cc_since = 0;             // CleanClustering: clusters not modified since this round were connected at the last check
     cudaEvent_t ev[4 * 8] = {};       // 4 events per round slot
     // generic scratch
     DevBuf<char> cub_temp;

@@ -923,27 +923,36 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense3(const 
 // and neither a leaner decision nor prefetching moves the total.  So the two halves get the shape each one wants:
 //
 //   k_scan_classify  the frontier scan proper: streams cluster ids + ELL columns (28 B per vertex, TMA-staged as above),
-//                    gathers the neighbours' cluster ids, finds the boundary vertices and their (at most three) distinct
+//                    gathers the neighbours' cluster ids, finds the boundary vertices and their (one or two) distinct
 //                    foreign clusters in slot order, applies the "recently modified" rule (:909-920) through the 50 KB
-//                    bitmap (L1-resident) and appends one 16-byte record per DIRTY boundary vertex to the block's segment
-//                    of a list.  Few registers, no fp64: twice the warps per SM.
+//                    bitmap (L1-resident) and appends one 16-byte record (vertex, own cluster, one or two candidates) per
+//                    DIRTY boundary vertex to the block's segment of a list.  Few registers, no fp64.
 //   k_bulk_decide    the bulk decision over the list: every lane is a vertex that needs one, positions / centroids are
 //                    requested together, candidates compared in slot order -- no divergence on "is this a boundary
 //                    vertex", and the work shrinks with the dirty set (15.8 M -> 3 M vertices over the C4 bulk rounds).
 //
-// Vertices with more than three foreign clusters, a row longer than W or the NULL cluster as own cluster (all rare) go to
-// the work list of k_bulk_evaluate, as rows longer than W do in the fused kernels.  Decisions, counters and proposal
+// Vertices with more than two foreign clusters, the NULL cluster in their ring, a row longer than W or the NULL cluster as
+// own cluster (all rare) go to the work list of k_bulk_evaluate, as rows longer than W do in the fused kernels.  Decisions, counters and proposal
 // masks are those of the fused kernels and of k_scan<W, true>.
-__host__ __device__ constexpr int classify_stage_bytes(int W) { return kDenseGroupV * (4 + 4 * W); }
-__host__ __device__ constexpr int classify_smem_bytes(int W, int S) { return 128 + S * classify_stage_bytes(W); }
+__host__ __device__ constexpr int classify_stage_bytes(int W, int VPL) { return kDenseGroupV * VPL * (4 + 4 * W); }
+__host__ __device__ constexpr int classify_smem_bytes(int W, int S, int VPL) { return 128 + S * classify_stage_bytes(W, VPL); }
+// tiles per scanning block (a multiple of the 8 VPL tiles of a staged group): shared by the two kernels
+__host__ __device__ inline int classify_chunk(int n_tiles, int grid, int vpl) {
+    int chunk = (n_tiles + grid - 1) / grid;
+    const int q = kDenseWarps * vpl;
+    return (chunk + q - 1) / q * q;
+}
 
 __device__ __forceinline__ unsigned mod_bit(const unsigned* __restrict__ modbits, int c) { return (__ldg(modbits + (c >> 5)) >> (c & 31)) & 1u; }
 
-template <int W, int S, int MINB>
+// VPL = 32-vertex tiles per warp and ticket: the gathers of all of them are in flight together (the kernel is bound by
+// the latency chain of a tile, so memory-level parallelism per warp is what counts), and the per-ticket overhead is shared.
+template <int W, int S, int MINB, int VPL>
 __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __grid_constant__ ReassignArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int GV = kDenseGroupV;
-    constexpr int STAGE = classify_stage_bytes(W);
+    constexpr int GV = kDenseGroupV * VPL;                    // vertices per staged group
+    constexpr int GT = kDenseWarps * VPL;                     // tiles per staged group
+    constexpr int STAGE = classify_stage_bytes(W, VPL);
     constexpr int OFF_ELL = 4 * GV;
     // control words: full[s] mbarriers at +8 s, per-stage done counters at +64 + 4 s, ticket at +112, list cursor at +116
     const uint32_t bar0 = smem_addr(smem_raw);
@@ -952,11 +961,10 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
     int* cursor = reinterpret_cast<int*>(smem_raw + 116);
     const int lane = threadIdx.x & 31;
     const int n_tiles = A.tile_end - A.tile_begin;
-    int chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
-    chunk = (chunk + kDenseWarps - 1) / kDenseWarps * kDenseWarps;
+    const int chunk = classify_chunk(n_tiles, gridDim.x, VPL);
     const int t0 = min(A.tile_end, A.tile_begin + (int)blockIdx.x * chunk);
     const int t1 = min(A.tile_end, t0 + chunk);
-    const int n_groups = (t1 - t0 + kDenseWarps - 1) / kDenseWarps;
+    const int n_groups = (t1 - t0 + GT - 1) / GT;
     int4* seg = A.blist + (int64_t)(t0 - A.tile_begin) * 32;
 
     auto issue_group = [&](int g) {
@@ -964,8 +972,8 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
         const int s = g % S;
-        const int tile = t0 + g * kDenseWarps;
-        const uint32_t nv = 32u * (uint32_t)min(kDenseWarps, t1 - tile);
+        const int tile = t0 + g * GT;
+        const uint32_t nv = 32u * (uint32_t)min(GT, t1 - tile);
         const int64_t v0 = (int64_t)tile * 32;
         const uint32_t full = bar0 + 8 * s;
         const uint32_t dst = bar0 + 128 + s * STAGE;
@@ -998,25 +1006,50 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
         const int g = n / kDenseWarps, slot = n % kDenseWarps;
         const int s = g % S;
         mbar_wait(bar0 + 8 * s, (g / S) & 1);
-        const int tile = t0 + n;
-        if (tile < t1) {
-            const unsigned char* st = smem_raw + 128 + s * STAGE;
-            const int idx = slot * 32 + lane;
+        const unsigned char* st = smem_raw + 128 + s * STAGE;
+        // all the tiles of the ticket: ids from the staged group, then every gather in flight before the first is used
+        int av[VPL], nbv[VPL][W];
+#pragma unroll
+        for (int j = 0; j < VPL; j++) {
+            const int idx = (slot * VPL + j) * 32 + lane;
+            av[j] = reinterpret_cast<const int*>(st)[idx];
+#pragma unroll
+            for (int k = 0; k < W; k++) nbv[j][k] = reinterpret_cast<const int*>(st + OFF_ELL)[k * GV + idx];
+        }
+        bool longv[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; j++) {
+            const bool in_range = t0 + n * VPL + j < t1;    // (the last group of the block may be partly filled: stale indices)
+            longv[j] = nbv[j][W - 1] < 0;                   // -2 marks a row longer than W
+            nbv[j][W - 1] = max(nbv[j][W - 1], 0);
+#pragma unroll
+            for (int k = 0; k < W; k++) nbv[j][k] = in_range ? __ldg(A.cid + nbv[j][k]) : 0;     // short rows are padded with the vertex itself
+        }
+        // own cluster's modified bit: asked for now, it travels with the gathers
+        unsigned amod[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; j++) amod[j] = all_dirty ? 1u : mod_bit(modbits, min(max(av[j], 0), K - 1));
+#pragma unroll
+        for (int j = 0; j < VPL; j++) {
+            const int tile = t0 + n * VPL + j;
+            if (tile >= t1) break;
             const int v = tile * 32 + lane;
             const bool valid = v < V;
-            const int a = reinterpret_cast<const int*>(st)[idx];
+            const int a = av[j];
             int nb[W];
 #pragma unroll
-            for (int k = 0; k < W; k++) nb[k] = reinterpret_cast<const int*>(st + OFF_ELL)[k * GV + idx];
-            const bool long_row = valid && nb[W - 1] < 0;           // -2 marks a row longer than W
-            nb[W - 1] = max(nb[W - 1], 0);
+            for (int k = 0; k < W; k++) nb[k] = nbv[j][k];
+            const bool long_row = valid && longv[j];
+            // extremes of the FOREIGN neighbour clusters: one foreign cluster -> equal, two -> nothing strictly between them
+            int mf = 0x7fffffff, Mf = -1;
 #pragma unroll
-            for (int k = 0; k < W; k++) nb[k] = __ldg(A.cid + nb[k]);     // short rows are padded with the vertex itself
-            int m1 = nb[0], M1 = nb[0];
-#pragma unroll
-            for (int k = 1; k < W; k++) { m1 = min(m1, nb[k]); M1 = max(M1, nb[k]); }
-            bool bnd = valid && ((m1 != a) || (M1 != a));
-            int c1 = -1, c2 = -1, c3 = -1;
+            for (int k = 0; k < W; k++) {
+                const bool f = nb[k] != a;
+                mf = min(mf, f ? nb[k] : 0x7fffffff);
+                Mf = max(Mf, f ? nb[k] : -1);
+            }
+            bool bnd = valid && Mf >= 0;
+            int c1 = -1, c2 = -1;
             bool listed = false, to_work = false;
             if (long_row || (valid && a >= K)) {
                 // own cluster NULL or a row longer than W: boundary / dirty over the whole CSR row, decided by k_bulk_evaluate
@@ -1030,36 +1063,29 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
                 if (a < K) dirty |= mod_bit(modbits, a);
                 to_work = bnd && dirty != 0;
             } else if (bnd) {
-                // a neighbour cluster strictly between the extremes that is not the own one, or the NULL cluster around: walk
-                const unsigned span = (unsigned)(M1 - m1 - 1);
-                bool odd = M1 >= K;
+                // a foreign cluster strictly between the two extremes, or the NULL cluster around: more than two candidates
+                // or none -- rare, left to k_bulk_evaluate (dirty over all the distinct foreign clusters)
+                const unsigned span = (unsigned)(Mf - mf - 1);
+                bool odd = Mf >= K;
 #pragma unroll
-                for (int k = 0; k < W; k++) odd |= ((unsigned)(nb[k] - m1 - 1) < span) && (nb[k] != a);
-                unsigned dirty = all_dirty ? 1u : mod_bit(modbits, a);
+                for (int k = 0; k < W; k++) odd |= ((unsigned)(nb[k] - mf - 1) < span) && (nb[k] != a);
+                unsigned dirty = amod[j];
                 if (!odd) {
-                    // one or two foreign clusters: the extremes (one of them may be the own cluster), first occurrence first
+                    // one or two foreign clusters, first occurrence first
                     int first = nb[W - 1];
 #pragma unroll
                     for (int k = W - 2; k >= 0; k--) first = (nb[k] != a) ? nb[k] : first;
                     c1 = first;
-                    const bool two = (m1 != a) && (M1 != a) && (m1 != M1);
-                    if (two) c2 = (first == m1) ? M1 : m1;
+                    const bool two = mf != Mf;
+                    if (two) c2 = (first == mf) ? Mf : mf;
                     if (!all_dirty) { dirty |= mod_bit(modbits, c1); if (two) dirty |= mod_bit(modbits, c2); }
                     listed = dirty != 0;
                 } else {
-                    unsigned rem = 0;
+                    if (!all_dirty) {
 #pragma unroll
-                    for (int k = 0; k < W; k++) rem |= ((nb[k] != a && nb[k] < K) ? 1u : 0u) << k;
-                    int nc = 0;
-                    while (rem) {
-                        const int b = pick_slot<W>(nb, __ffs(rem) - 1);
-#pragma unroll
-                        for (int k = 0; k < W; k++) rem &= ~((nb[k] == b ? 1u : 0u) << k);
-                        if (!all_dirty) dirty |= mod_bit(modbits, b);
-                        if (nc == 0) c1 = b; else if (nc == 1) c2 = b; else if (nc == 2) c3 = b;
-                        nc++;
+                        for (int k = 0; k < W; k++) if (nb[k] != a && nb[k] < K) dirty |= mod_bit(modbits, nb[k]);
                     }
-                    if (nc > 3) to_work = dirty != 0; else listed = dirty != 0;     // (no assigned foreign cluster: listed, no candidate)
+                    to_work = dirty != 0;
                 }
             }
             n_bnd += bnd ? 1u : 0u;
@@ -1068,7 +1094,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
                 int base = 0;
                 if (lane == 0) base = atomicAdd(cursor, __popc(ml));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (listed) seg[base + __popc(ml & lane_lt)] = make_int4(v, c1, c2, c3);
+                if (listed) seg[base + __popc(ml & lane_lt)] = make_int4(v, a, c1, c2);
                 n_listed += listed ? 1u : 0u;
             }
             const unsigned mw = __ballot_sync(0xffffffffu, to_work);
@@ -1079,7 +1105,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
                 if (to_work) A.work[basew + __popc(mw & lane_lt)] = v;
             }
         }
-        // the warp that finishes the last tile of the group refills the stage with the group S ahead
+        // the warp that finishes the last ticket of the group refills the stage with the group S ahead
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
@@ -1098,12 +1124,9 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
     if (threadIdx.x == 0) A.blist_cnt[blockIdx.x] = *cursor;
 }
 
-// The bulk decision over the list k_scan_classify wrote with `grid_a` blocks (one segment each).
+// The bulk decision over the list k_scan_classify wrote with `grid_a` blocks (one segment of `chunk` tiles each).
 template <bool STAGE1>
-__global__ void __launch_bounds__(256) k_bulk_decide(const __grid_constant__ ReassignArgs A, int grid_a) {
-    const int n_tiles = A.tile_end - A.tile_begin;
-    int chunk = (n_tiles + grid_a - 1) / grid_a;
-    chunk = (chunk + kDenseWarps - 1) / kDenseWarps * kDenseWarps;
+__global__ void __launch_bounds__(256) k_bulk_decide(const __grid_constant__ ReassignArgs A, int grid_a, int chunk) {
     const int* __restrict__ cmeta = A.cmeta;
     unsigned n_tests = 0, n_props = 0;
     for (int sg = blockIdx.x; sg < grid_a; sg += gridDim.x) {
@@ -1111,39 +1134,31 @@ __global__ void __launch_bounds__(256) k_bulk_decide(const __grid_constant__ Rea
         const int4* seg = A.blist + (int64_t)(t0 - A.tile_begin) * 32;
         const int n = A.blist_cnt[sg];
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int4 e = seg[i];
-            const int v = e.x;
-            const int a = A.cid[v];
-            const bool two = e.z >= 0, three = e.w >= 0;
-            n_tests += (e.y >= 0 ? 1u : 0u) + (two ? 1u : 0u) + (three ? 1u : 0u);
+            const int4 e = seg[i];                                              // (vertex, own cluster, first candidate, second or -1)
+            const int v = e.x, a = e.y;
+            const bool two = e.w >= 0;
+            n_tests += two ? 2u : 1u;
             int best_b = -1;
-            if (e.y >= 0 && (__ldg(cmeta + a) & 0x7fffffff) != 1) {             // a cluster is never emptied
-                const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)a);
-                const double4 cb1 = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)e.y);
-                const double px = A.xyz[3 * (int64_t)v], py = A.xyz[3 * (int64_t)v + 1], pz = A.xyz[3 * (int64_t)v + 2];
+            // everything the decision reads depends on the record only: one level of latency
+            const int meta_a = __ldg(cmeta + a);
+            const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)a);
+            const double4 cb1 = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)e.z);
+            const double4 cb2 = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)(two ? e.w : e.z));
+            const double px = A.xyz[3 * (int64_t)v], py = A.xyz[3 * (int64_t)v + 1], pz = A.xyz[3 * (int64_t)v + 2];
+            double w = 0;
+            if (STAGE1) w = __ldg(A.weight + v);
+            if ((meta_a & 0x7fffffff) != 1) {                                   // a cluster is never emptied
                 double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
                 double best = dx * dx + dy * dy + dz * dz;
-                double w = 0;
-                if (STAGE1) {
-                    w = __ldg(A.weight + v);
-                    best = ca.w / (ca.w - w) * best;
-                }
+                if (STAGE1) best = ca.w / (ca.w - w) * best;
                 dx = px - cb1.x; dy = py - cb1.y; dz = pz - cb1.z;
                 double d = dx * dx + dy * dy + dz * dz;
                 if (STAGE1) d = cb1.w / (cb1.w + w) * d;
-                if (d < best) { best = d; best_b = e.y; }
+                if (d < best) { best = d; best_b = e.z; }
                 if (two) {
-                    const double4 cb = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)e.z);
-                    dx = px - cb.x; dy = py - cb.y; dz = pz - cb.z;
+                    dx = px - cb2.x; dy = py - cb2.y; dz = pz - cb2.z;
                     d = dx * dx + dy * dy + dz * dz;
-                    if (STAGE1) d = cb.w / (cb.w + w) * d;
-                    if (d < best) { best = d; best_b = e.z; }
-                }
-                if (three) {
-                    const double4 cb = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)e.w);
-                    dx = px - cb.x; dy = py - cb.y; dz = pz - cb.z;
-                    d = dx * dx + dy * dy + dz * dz;
-                    if (STAGE1) d = cb.w / (cb.w + w) * d;
+                    if (STAGE1) d = cb2.w / (cb2.w + w) * d;
                     if (d < best) { best = d; best_b = e.w; }
                 }
             }

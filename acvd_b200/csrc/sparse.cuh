@@ -114,6 +114,9 @@ struct ClusterPassArgs {
     int do_sort, do_cc, do_stats;
     int apply_resets;         // 0: the connectivity check only counts (multi-GPU: every rank checks its share of the clusters first)
     int k_begin, k_end;       // clusters handled by this launch
+    const int* __restrict__ mod_round;   // last round every cluster was modified in
+    int cc_since;             // connectivity is checked for clusters modified in round >= cc_since (the others were
+                              // connected at the last check and have not changed since)
     EvalCfg cfg;
 };
 
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) k_cluster_pass(ClusterPassArgs P) {
         }
         // ---- 2. connected components of the cluster (root = smallest member = the vertex at which the reference's
         //         index-ordered BFS discovers the component, :428-437)
-        if (P.do_cc && n > 1) {
+        if (P.do_cc && n > 1 && P.mod_round[c] >= P.cc_since) {
             int* par = small ? s_a[w] : P.cc_par + b;
             int* sz = small ? s_b[w] : P.cc_sz + b;
             // (a) initial forest without atomics: every member points at its smallest same-cluster neighbour with a

@@ -432,6 +432,12 @@ def main():
     # ---- end to end through the C ABI from pinned host buffers (fresh context state every step)
     e2e_tests = 0
     _k5, h_out = pinned(np.zeros(V, dtype=np.int32))
+    # result buffers of the caller, pinned and reused (as a C++ caller's would be); under -m 1 the loop may append clusters
+    np_pay_out = {"iso": 4, "qem": 13, "aniso": 13, "anisoq": 22}[w["metric"]]
+    stats_out = None
+    if not fm:
+        _k7 = [pinned(np.zeros((K, np_pay_out))), pinned(np.zeros((K, 3))), pinned(np.zeros(K)), pinned(np.zeros(K, dtype=np.int32))]
+        stats_out = tuple(a for _, a in _k7)
     # one untimed pass first (when e2e is measured at all): the first pass after the device-resident steps re-grows
     # the memory pool for the mesh-build scratch, a one-off of the process, not of the path
     e2e_passes = args.e2e_steps + (1 if args.e2e_steps else 0)
@@ -450,7 +456,7 @@ def main():
         r = run_clustering(); tt.append(time.perf_counter())
 
         ctx.clustering(h_out); tt.append(time.perf_counter())
-        sums, cen, en, sz = ctx.cluster_stats(); tt.append(time.perf_counter())
+        sums, cen, en, sz = ctx.cluster_stats(stats_out); tt.append(time.perf_counter())
         e2e_tests += r["tests"]
         log(f"[rank {rank}] e2e step: " + ", ".join(f"{n} {1e3 * (b - a):.1f} ms" for n, a, b in zip(
             ("set_mesh", "build_items", "set_num_clusters", "set_clustering", "minimize", "get_clustering", "get_cluster_stats"), tt, tt[1:])))
@@ -477,7 +483,7 @@ def main():
                 "bytes_per_launch": by / max(1, launches), "us_per_launch": 1e3 * ms / max(1, launches),
                 "launches_per_step": launches / args.steps, "share_of_step": ms / ms_dev}
     S = lambda k: sum(r[k] for r in reps)
-    roof_dense = kernel_roof("k_scan_bulk_dense", "k_scan_bulk_dense (TMA-staged frontier scan + bulk decision of the reassignment loop, all tiles)",
+    roof_dense = kernel_roof("k_scan_bulk_dense", "dense bulk scan = k_scan_classify + k_bulk_decide (TMA-staged frontier scan over all tiles -> candidate list -> bulk decision)",
                              S("dense_scan_bytes"), S("ms_dense_scan"), S("dense_scan_launches"))
     if S("dense_scan_launches"):
         # roofline.achieved / frac count the HBM-compulsory bytes only: SURVEY 8d's frontier-scan figure, 8 + 8 deg = 56 B per

@@ -312,15 +312,18 @@ def test_initial_sampling_matches_oracle(oracle_mod, gpu_ctx_factory, sphere):
 
 @pytest.mark.parametrize("mesh", ["torus", "spindle"])
 def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle, mesh, monkeypatch):
-    """The TMA-staged dense bulk scan (k_scan_bulk_dense) and the list-based k_scan<W, true> take the same decisions:
-    identical clustering, tests, proposals and rounds on the same start."""
+    """The TMA-staged dense bulk scan (every generation: fused k_scan_bulk_dense*, split k_scan_classify + k_bulk_decide) and
+    the list-based k_scan<W, true> take the same decisions: identical clustering, tests, proposals and rounds on the same start."""
     if mesh == "torus":
         p, t, ind = torus
         K, grad = 400, 1.5
     else:
         (p, t), ind, K, grad = spindle, None, 150, 0.0
     res = []
-    for no_dense, variant in (("", "0"), ("1", "0"), ("", "10"), ("", "11"), ("", "20"), ("", "22"), ("", "25"), ("", "40"), ("", "41")):   # 40, 41: split form (classify + decide)   # 10, 11: second generation (two tiles in flight); 20, 21: third (min/max candidates)
+    # variants: 0 = fused first generation; "1"/"0" = the list-based scan; 10, 11 = second generation (two tiles in flight);
+    # 20, 22, 25 = third (min/max candidates, prefetch, static assignment); 40+ = split form (classify + decide) with
+    # 1 / 2 / 4 tiles per ticket -- 42 is the shipped default
+    for no_dense, variant in (("", "0"), ("1", "0"), ("", "10"), ("", "11"), ("", "20"), ("", "22"), ("", "25"), ("", "40"), ("", "42"), ("", "46")):
         monkeypatch.setenv("ACVD_DENSE_VARIANT", variant)
         if no_dense:
             monkeypatch.setenv("ACVD_NO_DENSE_SCAN", "1")
