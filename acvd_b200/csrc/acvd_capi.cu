@@ -1061,11 +1061,25 @@ static void launch_scan_split(acvd_ctx* c, const ReassignArgs& A, int decide_bps
     const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps * VPL - 1) / (kDenseWarps * VPL)));
     k_scan_classify<W, S, MINB, VPL><<<grid, kDenseThreads, classify_smem_bytes(W, S, VPL), c->stream>>>(A);
     ACVD_LAUNCH_CHECK();
-    const int gd = std::min(grid, kNumSMs * decide_bps);
     const int chunk = classify_chunk(n_tiles, grid, VPL);
-    if (A.bulk_stage == 1) k_bulk_decide<true><<<gd, 256, 0, c->stream>>>(A, grid, chunk);
-    else k_bulk_decide<false><<<gd, 256, 0, c->stream>>>(A, grid, chunk);
+    const int split = std::max(1, (kNumSMs * decide_bps + grid - 1) / grid);       // blocks per segment: decide_bps resident blocks per SM
+    const int gd = grid * split;
+    if (A.bulk_stage == 1) k_bulk_decide<true><<<gd, 256, 0, c->stream>>>(A, grid, chunk, split);
+    else k_bulk_decide<false><<<gd, 256, 0, c->stream>>>(A, grid, chunk, split);
     c->launches += 1;
+}
+// opening round of an exact phase: the streaming scan builds k_evaluate's work list (every boundary vertex)
+template <int W>
+static void launch_scan_opening(acvd_ctx* c, const ReassignArgs& A) {
+    constexpr int S = 2, MINB = 4, VPL = 2;
+    static bool configured[64] = {};
+    if (c->device >= 64 || !configured[c->device]) {
+        ACVD_CUDA(cudaFuncSetAttribute(k_scan_classify<W, S, MINB, VPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, classify_smem_bytes(W, S, VPL)));
+        if (c->device < 64) configured[c->device] = true;
+    }
+    const int n_tiles = A.tile_end - A.tile_begin;
+    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps * VPL - 1) / (kDenseWarps * VPL)));
+    k_scan_classify<W, S, MINB, VPL, true><<<grid, kDenseThreads, classify_smem_bytes(W, S, VPL), c->stream>>>(A);
 }
 // (stages, blocks per SM) variants kept for the kernel micro-benchmark (acvd_bench_kernel); variants >= 10 are the
 // second generation of the kernel (static tile assignment, two tiles in flight per warp)
@@ -1118,6 +1132,8 @@ static void launch_scan(acvd_ctx* c, const ReassignArgs& A, int grid) {
     }
     if (A.bulk) {
         if (c->ell_w == 6) k_scan<6, true><<<grid, kThreads, 0, c->stream>>>(A); else k_scan<8, true><<<grid, kThreads, 0, c->stream>>>(A);
+    } else if (A.all_tiles && A.sig_mode == 1 && A.force_all && !getenv("ACVD_NO_DENSE_SCAN")) {
+        if (c->ell_w == 6) launch_scan_opening<6>(c, A); else launch_scan_opening<8>(c, A);
     } else {
         if (c->ell_w == 6) k_scan<6, false><<<grid, kThreads, 0, c->stream>>>(A); else k_scan<8, false><<<grid, kThreads, 0, c->stream>>>(A);
     }
@@ -1262,6 +1278,24 @@ static void bulk_init(acvd_ctx* c) {
     ACVD_LAUNCH_CHECK();
 }
 
+// the same sum, enqueued behind a stage-1 round: its value arrives with the round's counters (one host synchronisation per
+// round instead of two); bulk_energy_fetch() after the synchronisation
+static void bulk_energy_enqueue(acvd_ctx* c) {
+    size_t tb = 0;
+    ACVD_CUDA(cub::DeviceReduce::Sum(nullptr, tb, c->bulk_energy.p, c->bulk_energy_sum.p, c->K, c->stream));
+    void* t = cub_temp(c, tb);
+    ACVD_CUDA(cub::DeviceReduce::Sum(t, tb, c->bulk_energy.p, c->bulk_energy_sum.p, c->K, c->stream));
+    ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 7, c->bulk_energy_sum.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->bulk_energy_pending = true;
+}
+static double bulk_energy(acvd_ctx* c);
+static double bulk_energy_fetch(acvd_ctx* c) {       // after the round's synchronisation
+    if (!c->bulk_energy_pending) return bulk_energy(c);
+    c->bulk_energy_pending = false;
+    double e;
+    memcpy(&e, c->h_scalars + 7, sizeof e);
+    return e;
+}
 // deterministic sum of the per-cluster centroid energies kept by the bulk rounds
 static double bulk_energy(acvd_ctx* c) {
     size_t tb = 0;
@@ -1306,6 +1340,7 @@ static void launch_bulk_round(acvd_ctx* c, int force_all, int stage) {
     k_bulk_refresh<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->csize.p, B);
     ACVD_LAUNCH_CHECK();
     ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if (stage == 1) bulk_energy_enqueue(c);          // the energy guard's sum travels with the counters
     ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
     ACVD_CUDA(cudaMemcpyAsync(c->h_scalars + 8, c->round_scalars.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     c->round++;
@@ -1634,7 +1669,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                     } else {
                         // stage 1 applies its moves simultaneously against round-start sums: no monotonicity guarantee,
                         // hence the guard -- a round that raised the energy is undone, and the exact rounds take over
-                        const double e = bulk_energy(c);
+                        const double e = bulk_energy_fetch(c);
                         if (e > e_prev) {
                             bulk_rollback(c);
                             R.modifications -= (int64_t)r.mods; R.bulk_rollbacks++;

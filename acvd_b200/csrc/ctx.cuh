@@ -72,6 +72,7 @@ struct acvd_ctx {
     DevBuf<unsigned long long> best2, sp_nmod, sp_resub, sp_ts;
     DevBuf<RoundCounters> sp_rc;
     bool members_valid = false;
+    bool bulk_energy_pending = false;  // the energy sum of the last stage-1 round was enqueued with its counters (h_scalars[7])
     bool last_sparse_cluster = false;  // the last sparse launch was the one-cluster form
     int mod_par = 0;                  // which modlist the last round wrote (0 / 1)
     bool modlist_valid = false;       // ... and whether it describes the last round completely

@@ -943,11 +943,15 @@ __host__ __device__ inline int classify_chunk(int n_tiles, int grid, int vpl) {
     return (chunk + q - 1) / q * q;
 }
 
+constexpr int kClassifyPush = 256;       // per-warp staging of work-list entries (work-list form of k_scan_classify)
+
 __device__ __forceinline__ unsigned mod_bit(const unsigned* __restrict__ modbits, int c) { return (__ldg(modbits + (c >> 5)) >> (c & 31)) & 1u; }
 
 // VPL = 32-vertex tiles per warp and ticket: the gathers of all of them are in flight together (the kernel is bound by
 // the latency chain of a tile, so memory-level parallelism per warp is what counts), and the per-ticket overhead is shared.
-template <int W, int S, int MINB, int VPL>
+// WORKLIST = true: the opening round of an exact phase (everything is dirty, no stored proposal survives): the same scan, but
+// every boundary vertex goes to the work list of k_evaluate instead of the candidate list (replaces k_scan<W, false> there).
+template <int W, int S, int MINB, int VPL, bool WORKLIST = false>
 __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __grid_constant__ ReassignArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GV = kDenseGroupV * VPL;                    // vertices per staged group
@@ -998,6 +1002,21 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
     const bool all_dirty = A.force_all != 0;
     unsigned n_bnd = 0, n_listed = 0;
     const int n_tickets = n_groups * kDenseWarps;
+    // work-list form: a third of the vertices go to the list; a global atomic per tile (1.25 M on one address at C4) would
+    // bound the kernel, so every warp stages its entries in shared memory and reserves space once per ~200 entries
+    __shared__ int s_push[WORKLIST ? kDenseWarps * kClassifyPush : 1];
+    int* wbuf = s_push + (WORKLIST ? (threadIdx.x >> 5) * kClassifyPush : 0);
+    int wcnt = 0;                                   // warp-uniform
+    auto flush_work = [&]() {
+        if (wcnt == 0) return;
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)wcnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int i = lane; i < wcnt; i += 32) A.work[base + i] = wbuf[i];
+        __syncwarp();
+        wcnt = 0;
+    };
     while (true) {
         int n = 0;
         if (lane == 0) n = atomicAdd(ticket, 1);
@@ -1089,7 +1108,8 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
                 }
             }
             n_bnd += bnd ? 1u : 0u;
-            const unsigned ml = __ballot_sync(0xffffffffu, listed);
+            if (WORKLIST) { to_work = to_work || listed; listed = false; }
+            const unsigned ml = WORKLIST ? 0u : __ballot_sync(0xffffffffu, listed);
             if (ml) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(cursor, __popc(ml));
@@ -1099,10 +1119,16 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
             }
             const unsigned mw = __ballot_sync(0xffffffffu, to_work);
             if (mw) {
-                int basew = 0;
-                if (lane == 0) basew = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)__popc(mw));
-                basew = __shfl_sync(0xffffffffu, basew, 0);
-                if (to_work) A.work[basew + __popc(mw & lane_lt)] = v;
+                if (WORKLIST) {
+                    if (to_work) wbuf[wcnt + __popc(mw & lane_lt)] = v;
+                    wcnt += __popc(mw);
+                    if (wcnt > kClassifyPush - 32) flush_work();
+                } else {
+                    int basew = 0;
+                    if (lane == 0) basew = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)__popc(mw));
+                    basew = __shfl_sync(0xffffffffu, basew, 0);
+                    if (to_work) A.work[basew + __popc(mw & lane_lt)] = v;
+                }
             }
         }
         // the warp that finishes the last ticket of the group refills the stage with the group S ahead
@@ -1118,22 +1144,27 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_classify(const __g
             }
         }
     }
+    if (WORKLIST) flush_work();
     warp_count_add(&A.ctr->boundary, n_bnd);
-    warp_count_add(&A.ctr->pad[0], n_listed);
-    __syncthreads();
-    if (threadIdx.x == 0) A.blist_cnt[blockIdx.x] = *cursor;
+    if (!WORKLIST) {
+        warp_count_add(&A.ctr->pad[0], n_listed);
+        __syncthreads();
+        if (threadIdx.x == 0) A.blist_cnt[blockIdx.x] = *cursor;
+    }
 }
 
 // The bulk decision over the list k_scan_classify wrote with `grid_a` blocks (one segment of `chunk` tiles each).
+// `split` blocks share a segment (the kernel is bound by the latency of its gathers: it wants every warp slot of the SM).
 template <bool STAGE1>
-__global__ void __launch_bounds__(256) k_bulk_decide(const __grid_constant__ ReassignArgs A, int grid_a, int chunk) {
+__global__ void __launch_bounds__(256) k_bulk_decide(const __grid_constant__ ReassignArgs A, int grid_a, int chunk, int split) {
     const int* __restrict__ cmeta = A.cmeta;
     unsigned n_tests = 0, n_props = 0;
-    for (int sg = blockIdx.x; sg < grid_a; sg += gridDim.x) {
+    for (int job = blockIdx.x; job < grid_a * split; job += gridDim.x) {
+        const int sg = job / split, part = job - sg * split;
         const int t0 = min(A.tile_end, A.tile_begin + sg * chunk);
         const int4* seg = A.blist + (int64_t)(t0 - A.tile_begin) * 32;
         const int n = A.blist_cnt[sg];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        for (int i = part * blockDim.x + threadIdx.x; i < n; i += split * blockDim.x) {
             const int4 e = seg[i];                                              // (vertex, own cluster, first candidate, second or -1)
             const int v = e.x, a = e.y;
             const bool two = e.w >= 0;

@@ -4,7 +4,7 @@
 TAG=${1:?tag}; OUT=${2:-r02}
 cd "$(dirname "$0")/.."
 [ -f gpurun_out/launches_C4_${TAG}.csv ] && python scripts/ncu_summary.py launches gpurun_out/launches_C4_${TAG}.csv "Launch list of one bench.py step, C4 (${TAG}; includes the mesh set-up and the initial fill)" > profiles/${OUT}_launches_C4.md
-for k in bulkdense split rest; do
+for k in bulkdense split splitlate rest; do
   [ -f gpurun_out/prof_${k}_C4_${TAG}.ncu-rep ] && python scripts/ncu_summary.py raw gpurun_out/prof_${k}_C4_${TAG}.ncu-rep "ncu --set full: ${k} kernels, C4 (${TAG})" > profiles/${OUT}_full_${k}_C4.md
 done
 # SASS evidence: the TMA bulk-copy engine and its mbarrier in the streaming kernels
