@@ -798,6 +798,51 @@ def test_sparse_rounds_equal_tile_filter_rounds(gpu_ctx_factory, sphere, torus, 
     assert g.clean_clustering() == 0
 
 
+def test_connectivity_check_of_modified_clusters_only(gpu_ctx_factory, sphere, torus, monkeypatch):
+    """CleanClustering inside acvd_minimize checks the connectivity of the clusters modified since the previous check only
+    (the others were connected then and have not changed).  Same clustering, events and counts as checking every cluster at
+    every event (ACVD_CC_ALL=1), from a start with disconnected clusters (a random labelling) and from the usual sampling."""
+    p, t, ind = torus
+    rng = np.random.default_rng(5)
+    for (pp, tt), K, start in (((p, t), 400, "sampling"), (sphere, 60, "random")):
+        res = []
+        for cc_all in ("", "1"):
+            if cc_all:
+                monkeypatch.setenv("ACVD_CC_ALL", "1")
+            else:
+                monkeypatch.delenv("ACVD_CC_ALL", raising=False)
+            g = gpu_ctx_factory()
+            g.set_mesh(pp, tt)
+            g.build_items("qem")
+            g.set_num_clusters(K)
+            if start == "sampling":
+                g.initial_sampling()
+            else:
+                g.set_clustering(np.random.default_rng(5).integers(0, K, pp.shape[0]).astype(np.int32))
+            rep = g.minimize(unconstrained_init=1)
+            res.append((g.clustering().copy(), rep, g.clean_clustering()))
+        (c0, r0, d0), (c1, r1, d1) = res
+        assert np.array_equal(c0, c1) and d0 == d1 == 0
+        for k in ("rounds", "convergences", "tests", "modifications", "disconnected", "energy"):
+            assert r0[k] == r1[k], (start, k, r0[k], r1[k])
+
+
+def test_cluster_stats_into_caller_buffers(gpu_ctx_factory, sphere):
+    p, t = sphere
+    g = gpu_ctx_factory()
+    g.set_mesh(p, t)
+    g.build_items("qem")
+    g.set_num_clusters(50)
+    g.initial_sampling()
+    g.minimize(unconstrained_init=1, max_loops=5)
+    a = g.cluster_stats()
+    out = (np.full((50, 13), -1.0), np.full((50, 3), -1.0), np.full(50, -1.0), np.full(50, -1, dtype=np.int32))
+    b = g.cluster_stats(out)
+    assert all(x is y for x, y in zip(b, out))
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the -m 1 row: IsVertexManifold on the device, one DetectNonManifoldOutputVertices step, the ACVD post-process sums
 
