@@ -42,6 +42,7 @@ static int scan_bps() { static int v = getenv("ACVD_SCAN_BPS") ? atoi(getenv("AC
 // per-loop lines are the analogue, Common/vtkUniformClustering.h:752-760)
 constexpr int64_t kReplicatedTailEvaluated = 400000;   // multi-GPU: below this many evaluated vertices per round the phase goes replicated
 constexpr int kRoundSlots = 8;            // exact rounds that may be in flight between two host synchronisations
+constexpr int kBulkMinVertices = 500000;    // acvd_params.bulk_rounds == 0 (automatic): bulk rounds on from this mesh size
 constexpr int kTailBatch = 4;             // rounds launched back to back in the long tail of the last phases
 constexpr int kSparseChunkAlloc = 512;    // rounds of one sparse launch (kSparseChunk)
 
@@ -1025,17 +1026,6 @@ static void launch_scan_bulk_dense(acvd_ctx* c, const ReassignArgs& A) {
     const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
     k_scan_bulk_dense<W, S, MINB><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
 }
-template <int W, int S, int MINB>
-static void launch_scan_bulk_dense2(acvd_ctx* c, const ReassignArgs& A) {
-    static bool configured[64] = {};
-    if (c->device >= 64 || !configured[c->device]) {
-        ACVD_CUDA(cudaFuncSetAttribute(k_scan_bulk_dense2<W, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(W, S)));
-        if (c->device < 64) configured[c->device] = true;
-    }
-    const int n_tiles = A.tile_end - A.tile_begin;
-    const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps - 1) / kDenseWarps));
-    k_scan_bulk_dense2<W, S, MINB><<<grid, kDenseThreads, dense_smem_bytes(W, S), c->stream>>>(A);
-}
 template <int W, int S, int MINB, bool STATIC, int PF, int DBG = 0>
 static void launch_scan_bulk_dense3(acvd_ctx* c, const ReassignArgs& A) {
     static bool configured[64] = {};
@@ -1081,44 +1071,24 @@ static void launch_scan_opening(acvd_ctx* c, const ReassignArgs& A) {
     const int grid = std::max(1, std::min(kNumSMs * MINB, (n_tiles + kDenseWarps * VPL - 1) / (kDenseWarps * VPL)));
     k_scan_classify<W, S, MINB, VPL, true><<<grid, kDenseThreads, classify_smem_bytes(W, S, VPL), c->stream>>>(A);
 }
-// (stages, blocks per SM) variants kept for the kernel micro-benchmark (acvd_bench_kernel); variants >= 10 are the
-// second generation of the kernel (static tile assignment, two tiles in flight per warp)
+// variants kept for the kernel micro-benchmark (acvd_bench_kernel) and the A/B tests: 0 / 1 the fused first generation
+// (3 / 2 stages), 20 / 22 / 25 the third (min/max candidates; + prefetch; + static assignment), 30 / 31 diagnostic (no
+// decision / no gathers either), 40-46 the split form (classify + decide; 1, 2, 2, 4 tiles per ticket)
 constexpr int kDenseDefaultVariant = 42;   // split form, 2 tiles per ticket, 2 stages, 4 blocks per SM (C4: 558 us per launch over a run vs 746 us for the fused kernel)
 static int dense_variant() { const char* e = getenv("ACVD_DENSE_VARIANT"); return e ? atoi(e) : kDenseDefaultVariant; }   // read per launch (tests switch it)
 template <int W>
 static void launch_scan_bulk_dense_variant(acvd_ctx* c, const ReassignArgs& A, int variant) {
     switch (variant) {
         case 1: launch_scan_bulk_dense<W, 2, 4>(c, A); break;
-        case 2: launch_scan_bulk_dense<W, 4, 4>(c, A); break;
-        case 3: launch_scan_bulk_dense<W, 2, 5>(c, A); break;
-        case 4: launch_scan_bulk_dense<W, 3, 5>(c, A); break;
-        case 5: launch_scan_bulk_dense<W, 2, 6>(c, A); break;
-        case 6: launch_scan_bulk_dense<W, 3, 3>(c, A); break;
-        case 10: launch_scan_bulk_dense2<W, 3, 4>(c, A); break;
-        case 11: launch_scan_bulk_dense2<W, 3, 3>(c, A); break;
-        case 12: launch_scan_bulk_dense2<W, 2, 4>(c, A); break;
-        case 13: launch_scan_bulk_dense2<W, 4, 3>(c, A); break;
-        case 14: launch_scan_bulk_dense2<W, 2, 5>(c, A); break;
-        case 15: launch_scan_bulk_dense2<W, 4, 4>(c, A); break;
         case 20: launch_scan_bulk_dense3<W, 3, 4, false, 0>(c, A); break;
-        case 21: launch_scan_bulk_dense3<W, 3, 4, false, 1>(c, A); break;
         case 22: launch_scan_bulk_dense3<W, 3, 4, false, 2>(c, A); break;
-        case 23: launch_scan_bulk_dense3<W, 2, 4, false, 2>(c, A); break;
-        case 24: launch_scan_bulk_dense3<W, 4, 4, false, 2>(c, A); break;
         case 25: launch_scan_bulk_dense3<W, 3, 4, true, 2>(c, A); break;
-        case 26: launch_scan_bulk_dense3<W, 3, 3, false, 2>(c, A); break;
-        case 40: launch_scan_split<W, 3, 6, 1>(c, A, 8); break;
-        case 41: launch_scan_split<W, 2, 8, 1>(c, A, 8); break;
-        case 42: launch_scan_split<W, 2, 4, 2>(c, A, 8); break;
-        case 43: launch_scan_split<W, 3, 4, 2>(c, A, 8); break;
-        case 44: launch_scan_split<W, 2, 5, 2>(c, A, 8); break;
-        case 45: launch_scan_split<W, 2, 3, 4>(c, A, 8); break;
-        case 46: launch_scan_split<W, 2, 4, 4>(c, A, 8); break;
-        case 47: launch_scan_split<W, 3, 3, 2>(c, A, 8); break;
         case 30: launch_scan_bulk_dense3<W, 3, 4, false, 0, 1>(c, A); break;
         case 31: launch_scan_bulk_dense3<W, 3, 4, false, 0, 2>(c, A); break;
-        case 32: launch_scan_bulk_dense3<W, 3, 6, false, 0, 2>(c, A); break;
-        case 33: launch_scan_bulk_dense3<W, 3, 6, false, 0, 1>(c, A); break;
+        case 40: launch_scan_split<W, 3, 6, 1>(c, A, 8); break;
+        case 42: launch_scan_split<W, 2, 4, 2>(c, A, 8); break;
+        case 44: launch_scan_split<W, 2, 5, 2>(c, A, 8); break;
+        case 46: launch_scan_split<W, 2, 4, 4>(c, A, 8); break;
         default: launch_scan_bulk_dense<W, 3, 4>(c, A); break;
     }
 }
@@ -1622,7 +1592,10 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
         for (int i = 0; i < c->K; i++) if (!fr[i]) early_items += sz[i];
     }
     int64_t loops = 0;
-    const int bulk_cap = p.bulk_rounds < 0 ? 0 : (p.bulk_rounds == 0 ? 1000 : p.bulk_rounds);
+    // Bulk rounds pay when a scan of the mesh costs more than the fixed cost of a round driven from the host (five launches and
+    // a poll, ~0.1 ms): below kBulkMinVertices the persistent sparse-round kernel takes the phase from its opening round
+    // (C1, 164 k vertices: 104 bulk rounds of ~95 us for ~15 us of work each).  bulk_rounds > 0 forces them on.
+    const int bulk_cap = p.bulk_rounds < 0 ? 0 : (p.bulk_rounds == 0 ? (c->V >= kBulkMinVertices ? 1000 : 0) : p.bulk_rounds);
     const int env_passes = getenv("ACVD_COMMIT_PASSES") ? std::max(1, atoi(getenv("ACVD_COMMIT_PASSES"))) : 0;
     c->commit_passes = std::min(kMaxPasses, p.commit_passes > 0 ? p.commit_passes : (env_passes ? env_passes : 2));   // one default for every world size: N GPUs give the 1-GPU clustering
     while (true) {

@@ -275,252 +275,8 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense(Reassig
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Second generation of the dense bulk scan: same staging, same decisions, but
-//   * static tile assignment -- warp w owns slot w of every staged group -- instead of the block-wide ticket counter
-//     (the shared-memory atomicAdd compiles to a ~30-instruction warp-aggregation sequence per tile);
-//   * stage hand-back through an "empty" mbarrier (8 arrivals, one per warp): warp (g mod 8) waits for it and issues
-//     the refill of group g + S, no done-counter atomics;
-//   * two tiles in flight per warp: the neighbour-cluster-id gathers of the NEXT tile (the L2 round trip that bounds
-//     the kernel at 32 warps per SM) are issued before the current tile is decided, and the own-cluster operands and
-//     candidate centroids are prefetched into L1 as soon as their indices are known.
-template <int W>
-struct DenseTile {          // what phase A leaves in registers for phase B
-    int a;                  // own cluster id (-1: vertex beyond V)
-    int nb[W];              // neighbour cluster ids
-    int tile;               // -1: no tile (beyond the block's range)
-    unsigned flags;         // bit 0: row longer than W, bit 1: some row of the tile is
-};
-
-template <int W, int S, int MINB>
-__global__ void __launch_bounds__(kDenseThreads, MINB) k_scan_bulk_dense2(ReassignArgs A) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int GV = kDenseGroupV;
-    constexpr int STAGE = dense_stage_bytes(W);
-    constexpr int OFF_ELL = 4 * GV, OFF_XYZ = OFF_ELL + 4 * W * GV, OFF_WGT = OFF_XYZ + 12 * GV;
-    // control words: full[s] mbarriers at +8 s, empty[s] mbarriers at +64 + 8 s
-    const uint32_t bar0 = smem_addr(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_tiles = A.tile_end - A.tile_begin;
-    int chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
-    chunk = (chunk + kDenseWarps - 1) / kDenseWarps * kDenseWarps;
-    const int t0 = min(A.tile_end, A.tile_begin + (int)blockIdx.x * chunk);
-    const int t1 = min(A.tile_end, t0 + chunk);
-    const int n_groups = (t1 - t0 + kDenseWarps - 1) / kDenseWarps;
-    const bool stage1 = A.bulk_stage == 1;
-
-    auto issue_group = [&](int g) {
-        uint64_t pol_stream, pol_keep;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-        const int s = g % S;
-        const int tile = t0 + g * kDenseWarps;
-        const uint32_t nv = 32u * (uint32_t)min(kDenseWarps, t1 - tile);
-        const int64_t v0 = (int64_t)tile * 32;
-        const uint32_t full = bar0 + 8 * s;
-        const uint32_t dst = bar0 + 128 + s * STAGE;
-        mbar_expect_tx(full, nv * (4u + 4u * W + 12u + (stage1 ? 8u : 0u)));
-        bulk_g2s(dst, A.cid + v0, 4 * nv, full, pol_keep);
-#pragma unroll
-        for (int k = 0; k < W; k++) bulk_g2s(dst + OFF_ELL + 4 * GV * k, A.ell + (int64_t)k * A.vpad + v0, 4 * nv, full, pol_stream);
-        bulk_g2s(dst + OFF_XYZ, A.xyz + 3 * v0, 12 * nv, full, pol_stream);
-        if (stage1) bulk_g2s(dst + OFF_WGT, A.weight + v0, 8 * nv, full, pol_stream);
-    };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 64 + 8 * s, kDenseWarps); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int g = 0; g < S && g < n_groups; g++) issue_group(g);
-    }
-    __syncthreads();
-
-    const int K = A.K, V = A.V;
-    const unsigned* __restrict__ modbits = A.modbits;
-    const unsigned lane_lt = (1u << lane) - 1u;
-    const bool all_dirty = A.force_all != 0;
-    unsigned n_bnd = 0, n_fused = 0, n_tests = 0, n_props = 0;
-
-    // phase A: own id and neighbour ids from the staged group, neighbour cluster ids requested (not yet consumed)
-    auto phase_a = [&](int g, DenseTile<W>& T) {
-        const int s = g % S;
-        mbar_wait(bar0 + 8 * s, (g / S) & 1);
-        const int tile = t0 + g * kDenseWarps + warp;
-        T.tile = tile < t1 ? tile : -1;
-        T.flags = 0;
-        if (T.tile < 0) return;
-        const unsigned char* st = smem_raw + 128 + s * STAGE;
-        const int idx = warp * 32 + lane;
-        const int v = tile * 32 + lane;
-        const bool valid = v < V;
-        T.a = valid ? reinterpret_cast<const int*>(st)[idx] : -1;
-        const int ac = (unsigned)T.a < (unsigned)K ? T.a : 0;
-        // own cluster's centroid / size / modified word: in L1 by the time phase B asks for them
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.bulk_cen + 4 * (int64_t)ac));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.csize + ac));
-        int nb[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) nb[k] = reinterpret_cast<const int*>(st + OFF_ELL)[k * GV + idx];
-        const bool overflow_row = valid && nb[W - 1] == -2;
-        const bool any_overflow = __any_sync(0xffffffffu, nb[W - 1] == -2);
-        if (any_overflow) {
-            if (overflow_row) nb[W - 1] = A.col[A.row_ptr[v] + W - 1];
-            else if (nb[W - 1] == -2) nb[W - 1] = 0;
-        }
-        T.flags = (overflow_row ? 1u : 0u) | (any_overflow ? 2u : 0u);
-#pragma unroll
-        for (int k = 0; k < W; k++) T.nb[k] = __ldg(A.cid + nb[k]);       // short rows are padded with the vertex itself
-    };
-
-    // phase B: the decision (identical to k_scan<W, true>)
-    auto phase_b = [&](int g, const DenseTile<W>& T) {
-        if (T.tile < 0) return;
-        const int s = g % S;
-        const unsigned char* st = smem_raw + 128 + s * STAGE;
-        const int tile = T.tile;
-        const int idx = warp * 32 + lane;
-        const int v = tile * 32 + lane;
-        const bool valid = v < V;
-        const int a = T.a;
-        const bool overflow_row = T.flags & 1u, any_overflow = T.flags & 2u;
-        int nb[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) nb[k] = T.nb[k];
-        unsigned rem = 0;
-        bool bnd = false;
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-            const bool isb = nb[k] != a;
-            bnd |= isb;
-            rem |= ((isb && (unsigned)nb[k] < (unsigned)K) ? 1u : 0u) << k;
-        }
-        if (!valid) { rem = 0; bnd = false; }
-        unsigned dirty = all_dirty ? 1u : 0u;
-        if (any_overflow) {        // finish long rows from the CSR, warp-uniformly (their decision is k_bulk_evaluate's)
-            const int e0 = overflow_row ? A.row_ptr[v] + W : 0, e1 = overflow_row ? A.row_ptr[v + 1] : 0;
-            const int steps = __reduce_max_sync(0xffffffffu, e1 - e0);
-            for (int q = 0; q < steps; q++) {
-                const int bb = (e0 + q < e1) ? A.cid[A.col[e0 + q]] : a;
-                const bool isb = bb != a;
-                bnd |= isb;
-                if (isb && bb < K) dirty |= (modbits[bb >> 5] >> (bb & 31)) & 1u;
-            }
-        }
-        bnd = bnd && valid;
-        n_bnd += bnd ? 1u : 0u;
-        const bool cand = bnd && !overflow_row;      // decided here if dirty
-        int best_b = -1;
-        if (__any_sync(0xffffffffu, bnd)) {
-            // candidate centroids on their way to L1 before the walk asks for the first one
-            if (cand && a < K) {
-#pragma unroll
-                for (int k = 0; k < W; k++)
-                    if ((rem >> k) & 1u) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.bulk_cen + 4 * (int64_t)nb[k]));
-            }
-            const int ac = (unsigned)a < (unsigned)K ? a : 0;
-            double px = 0, py = 0, pz = 0, best = 0, w = 0;
-            bool blocked = true;
-            unsigned ntest = 0;
-            if (bnd && a < K) dirty |= all_dirty ? 1u : (modbits[ac >> 5] >> (ac & 31)) & 1u;
-            if (!cand) {
-                if (overflow_row && !all_dirty) {    // long row: only the dirty flag of the first W slots is still missing
-                    while (rem) {
-                        const int b = pick_slot<W>(nb, __ffs(rem) - 1);
-                        rem &= rem - 1;
-                        dirty |= (modbits[b >> 5] >> (b & 31)) & 1u;
-                    }
-                }
-                rem = 0;
-            } else if (a >= K) {   // NULL cluster: adopt the first assigned neighbour cluster; dirty if any neighbour cluster is
-                if (rem) best_b = pick_slot<W>(nb, __ffs(rem) - 1);
-                if (!all_dirty) {
-                    while (rem) {
-                        const int b = pick_slot<W>(nb, __ffs(rem) - 1);
-                        rem &= rem - 1;
-                        dirty |= (modbits[b >> 5] >> (b & 31)) & 1u;
-                    }
-                }
-                rem = 0;
-            } else {
-                const float* xs = reinterpret_cast<const float*>(st + OFF_XYZ) + 3 * idx;
-                px = xs[0]; py = xs[1]; pz = xs[2];
-                blocked = __ldg(A.csize + ac) == 1;
-                const double4 ca = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)ac);
-                const double dx = px - ca.x, dy = py - ca.y, dz = pz - ca.z;
-                best = dx * dx + dy * dy + dz * dz;
-                if (stage1) {
-                    w = reinterpret_cast<const double*>(st + OFF_WGT)[idx];
-                    best = ca.w / (ca.w - w) * best;
-                }
-            }
-            // candidates in slot order (first occurrence of every distinct cluster)
-            while (__any_sync(0xffffffffu, rem != 0)) {
-                if (rem) {
-                    const int b = pick_slot<W>(nb, __ffs(rem) - 1);
-#pragma unroll
-                    for (int k = 0; k < W; k++) rem &= ~((nb[k] == b ? 1u : 0u) << k);
-                    ntest++;
-                    dirty |= (modbits[b >> 5] >> (b & 31)) & 1u;
-                    if (!blocked) {
-                        const double4 cb = *reinterpret_cast<const double4*>(A.bulk_cen + 4 * (int64_t)b);
-                        const double dx = px - cb.x, dy = py - cb.y, dz = pz - cb.z;
-                        double d = dx * dx + dy * dy + dz * dz;
-                        if (stage1) d = cb.w / (cb.w + w) * d;
-                        if (d < best) { best = d; best_b = b; }
-                    }
-                }
-            }
-            // a vertex none of whose clusters changed keeps its earlier outcome: it is neither counted nor proposed
-            if (!(cand && dirty)) best_b = -1;
-            else { n_fused++; n_tests += ntest; }
-            if (best_b >= 0) {
-                A.prop_dst[v] = best_b;
-                if (a < K && A.bulk_count_leave) asm volatile("red.global.add.s32 [%0], 1;" ::"l"(A.bulk_leave + a) : "memory");
-            }
-            const unsigned mp = __ballot_sync(0xffffffffu, best_b >= 0);
-            if (lane == 0) { A.prop_mask[tile] = mp; n_props += __popc(mp); }
-            // rows longer than W (rare) are decided by k_bulk_evaluate from the work list
-            if (any_overflow) {
-                const bool ow = bnd && overflow_row && dirty != 0;
-                const unsigned mw = __ballot_sync(0xffffffffu, ow);
-                if (mw) {
-                    int basew = 0;
-                    if (lane == 0) basew = (int)atomicAdd(&A.ctr->evaluated, (unsigned long long)__popc(mw));
-                    basew = __shfl_sync(0xffffffffu, basew, 0);
-                    if (ow) A.work[basew + __popc(mw & lane_lt)] = v;
-                }
-            }
-        } else if (lane == 0) A.prop_mask[tile] = 0;
-    };
-
-    DenseTile<W> cur, nxt;
-    cur.tile = -1; nxt.tile = -1;
-    if (n_groups > 0) phase_a(0, cur);
-    for (int g = 0; g < n_groups; g++) {
-        if (g + 1 < n_groups) phase_a(g + 1, nxt); else nxt.tile = -1;
-        phase_b(g, cur);
-        // hand the stage back: the 8 warps arrive, warp (g mod 8) waits for all of them and refills it with group g + S
-        __syncwarp();
-        const int s = g % S;
-        if (lane == 0) mbar_arrive(bar0 + 64 + 8 * s);
-        if (g + S < n_groups && warp == (g % kDenseWarps)) {
-            if (lane == 0) {
-                mbar_wait(bar0 + 64 + 8 * s, (g / S) & 1);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue_group(g + S);
-            }
-            __syncwarp();
-        }
-        cur = nxt;
-    }
-    warp_count_add(&A.ctr->boundary, n_bnd);
-    warp_count_add(&A.ctr->pad[0], n_fused);
-    warp_count_add(&A.ctr->tests, n_tests);
-    warp_count_add(&A.ctr->proposals, n_props);
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// Third generation: an instruction diet for the common tile.
+// Third generation (the second -- static tile assignment, "empty" mbarrier hand-back, two tiles in flight per warp by software
+// pipelining -- measured 950 us against 706 us and was removed): an instruction diet for the common tile.
 //   * static tile assignment (warp w owns slot w of every staged group), stage hand-back through an "empty" mbarrier;
 //   * candidates without a slot loop: on a triangulated surface a boundary vertex sees one or two foreign clusters,
 //     which are the minimum and the maximum of its neighbours' cluster ids (one of them may be its own).  Both

@@ -125,7 +125,7 @@ typedef struct acvd_params {
     int32_t log_energy;           /* keep a per-round global-energy trace (energy.txt analogue) */
     int32_t rounds_per_sync;      /* rounds launched back to back between host polls in the tail of the last phases, <=0 -> 4, max 8 */
     double sv_threshold;          /* <=0 -> 1e-3 (Common/vtkQuadricTools.h:36) */
-    int32_t bulk_rounds;          /* early phases: 0 -> bulk Lloyd-criterion rounds on (cap 1000), <0 -> off, >0 -> cap */
+    int32_t bulk_rounds;          /* early phases: 0 -> automatic (bulk Lloyd-criterion rounds for meshes of >= 500 k vertices, cap 1000), <0 -> off, >0 -> on with this cap */
     int32_t commit_passes;        /* select+commit passes per exact round; <=0 -> 2 (the same default on any number of GPUs), max 8 */
     int32_t sparse_rounds;        /* 0 -> rounds after a phase's opening round run in the persistent sparse-round kernel
                                      (dirty set enumerated from the modified clusters' member arrays); <0 -> tile-filter

@@ -15,7 +15,7 @@ if __name__ == "__main__":
         for loops in (1, 2, 3, 4, 6, 8, 12, 20, 40, 80):
             g = capi.Context(0)
             g.set_mesh(p, t); g.build_items("qem", 0.0, None); g.set_num_clusters(K); g.initial_sampling()
-            rep = g.minimize(unconstrained_init=1, max_loops=loops)
+            rep = g.minimize(unconstrained_init=1, max_loops=loops, bulk_rounds=1000)
             rows.append((loops, rep["rounds"], rep["bulk_rounds"], rep["tests"], rep["proposals"], rep["modifications"], rep["evaluated"],
                          int(np.bitwise_xor.reduce(g.clustering() * np.arange(1, p.shape[0] + 1, dtype=np.int64)))))
             g.close()

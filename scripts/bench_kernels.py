@@ -9,11 +9,9 @@ import sys
 sys.path.insert(0, ".")
 from acvd_b200 import capi, meshgen  # noqa: E402
 
-VARIANTS = {-1: "k_scan<W,true> (list)", 0: "S=3 B=4", 1: "S=2 B=4", 2: "S=4 B=4", 3: "S=2 B=5", 4: "S=3 B=5", 5: "S=2 B=6", 6: "S=3 B=3",
-            20: "gen3 S=3 B=4", 21: "gen3 S=3 B=4 pf1", 22: "gen3 S=3 B=4 pf2", 23: "gen3 S=2 B=4 pf2", 24: "gen3 S=4 B=4 pf2", 25: "gen3 static S=3 B=4 pf2", 26: "gen3 S=3 B=3 pf2",
-            30: "gen3 S=3 B=4 no-decision", 31: "gen3 S=3 B=4 no-gathers", 32: "gen3 S=3 B=6 no-gathers", 33: "gen3 S=3 B=6 no-decision",
-            40: "split S=3 B=6 vpl1", 41: "split S=2 B=8 vpl1", 42: "split S=2 B=4 vpl2", 43: "split S=3 B=4 vpl2", 44: "split S=2 B=5 vpl2", 45: "split S=2 B=3 vpl4", 46: "split S=2 B=4 vpl4", 47: "split S=3 B=3 vpl2",
-            10: "gen2 S=3 B=4", 11: "gen2 S=3 B=3", 12: "gen2 S=2 B=4", 13: "gen2 S=4 B=3", 14: "gen2 S=2 B=5", 15: "gen2 S=4 B=4"}
+VARIANTS = {-1: "k_scan<W,true> (list)", 0: "fused S=3 B=4", 1: "fused S=2 B=4",
+            20: "gen3 S=3 B=4", 22: "gen3 S=3 B=4 pf2", 25: "gen3 static S=3 B=4 pf2", 30: "gen3 S=3 B=4 no-decision", 31: "gen3 S=3 B=4 no-gathers",
+            40: "split S=3 B=6 vpl1", 42: "split S=2 B=4 vpl2 (shipped)", 44: "split S=2 B=5 vpl2", 46: "split S=2 B=4 vpl4"}
 
 if __name__ == "__main__":
     wl = sys.argv[1] if len(sys.argv) > 1 else "C4"

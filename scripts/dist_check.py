@@ -35,11 +35,12 @@ def main():
         g.initial_sampling()
         g.save_clustering()
         passes = int(os.environ.get("DIST_CHECK_PASSES", "0"))     # 0 = the library default (the same on any number of GPUs)
-        g.minimize(unconstrained_init=uncon, commit_passes=passes)     # warm-up (NCCL channels, allocations)
+        bulk = int(os.environ.get("DIST_CHECK_BULK", "1000"))      # bulk rounds forced on (automatic = off below 500 k vertices): the exchange of the bulk rounds is what is checked
+        g.minimize(unconstrained_init=uncon, commit_passes=passes, bulk_rounds=bulk)     # warm-up (NCCL channels, allocations)
         g.restore_clustering()
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
-        rep = g.minimize(unconstrained_init=uncon, commit_passes=passes)
+        rep = g.minimize(unconstrained_init=uncon, commit_passes=passes, bulk_rounds=bulk)
         torch.cuda.synchronize(); dist.barrier()
         dt = time.perf_counter() - t0
         cl = g.clustering()
@@ -55,10 +56,10 @@ def main():
             s.set_num_clusters(w["K"])
             s.initial_sampling()
             s.save_clustering()
-            s.minimize(unconstrained_init=uncon, commit_passes=passes)
+            s.minimize(unconstrained_init=uncon, commit_passes=passes, bulk_rounds=bulk)
             s.restore_clustering()
             t0 = time.perf_counter()
-            rep1 = s.minimize(unconstrained_init=uncon, commit_passes=passes)
+            rep1 = s.minimize(unconstrained_init=uncon, commit_passes=passes, bulk_rounds=bulk)
             dt1 = time.perf_counter() - t0
             cl1 = s.clustering()
             identical = bool(np.array_equal(cl, cl1))

@@ -224,12 +224,12 @@ def test_bulk_rounds_energy_monotone_and_same_fixed_point(oracle_mod, gpu_ctx_fa
     o, g = make_pair(oracle_mod, gpu_ctx_factory, p, t, metric, K, 1.5, ind)
     cl0 = o.initial_sampling()
     res = {}
-    for bulk in (0, -1):
+    for bulk in (1000, -1):          # forced on (the automatic setting turns them on from 500 k vertices) / off
         g.set_clustering(cl0)
         rep = g.minimize(unconstrained_init=uncon, log_energy=1, bulk_rounds=bulk)
         log = g.energy_log()
         nb = rep["bulk_rounds"]
-        assert (nb > 0) == (bulk == 0)
+        assert (nb > 0) == (bulk > 0)
         if nb:
             # energy never rises from one bulk round to the next; the only places it may rise are the phase
             # boundaries, where CleanClustering / FillHoles re-assign broken-off components
@@ -239,11 +239,11 @@ def test_bulk_rounds_energy_monotone_and_same_fixed_point(oracle_mod, gpu_ctx_fa
             assert np.all(np.diff(e)[rises] <= 1e-5 * np.abs(e[:-1][rises]))
         res[bulk] = rep["energy"]
         assert g.clean_clustering() == 0
-    assert abs(res[0] - res[-1]) <= 0.01 * abs(res[-1])
+    assert abs(res[1000] - res[-1]) <= 0.01 * abs(res[-1])
     o.set_params(unconstrained_init=uncon)
     o.minimize()
     o.recompute_statistics()
-    assert abs(res[0] - o.global_energy()) <= 0.01 * abs(o.global_energy())
+    assert abs(res[1000] - o.global_energy()) <= 0.01 * abs(o.global_energy())
 
 
 @pytest.mark.parametrize("metric,uncon", [("iso", 0), ("qem", 1)])
@@ -320,10 +320,9 @@ def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle,
     else:
         (p, t), ind, K, grad = spindle, None, 150, 0.0
     res = []
-    # variants: 0 = fused first generation; "1"/"0" = the list-based scan; 10, 11 = second generation (two tiles in flight);
-    # 20, 22, 25 = third (min/max candidates, prefetch, static assignment); 40+ = split form (classify + decide) with
-    # 1 / 2 / 4 tiles per ticket -- 42 is the shipped default
-    for no_dense, variant in (("", "0"), ("1", "0"), ("", "10"), ("", "11"), ("", "20"), ("", "22"), ("", "25"), ("", "40"), ("", "42"), ("", "46")):
+    # variants: 0 = fused first generation; "1"/"0" = the list-based scan; 20, 22, 25 = third generation (min/max candidates,
+    # prefetch, static assignment); 40+ = split form (classify + decide) with 1 / 2 / 4 tiles per ticket -- 42 is the shipped default
+    for no_dense, variant in (("", "0"), ("1", "0"), ("", "20"), ("", "22"), ("", "25"), ("", "40"), ("", "42"), ("", "46")):
         monkeypatch.setenv("ACVD_DENSE_VARIANT", variant)
         if no_dense:
             monkeypatch.setenv("ACVD_NO_DENSE_SCAN", "1")
@@ -334,7 +333,7 @@ def test_tma_staged_dense_scan_equals_list_scan(gpu_ctx_factory, torus, spindle,
         g.build_items("qem", grad, ind)
         g.set_num_clusters(K)
         g.initial_sampling()
-        rep = g.minimize(unconstrained_init=1)
+        rep = g.minimize(unconstrained_init=1, bulk_rounds=1000)      # forced on: these meshes are below the automatic threshold
         res.append((g.clustering().copy(), rep))
     c0, r0 = res[0]
     assert r0["bulk_rounds"] > 0 and r0["dense_scan_launches"] > 0 and res[1][1]["dense_scan_launches"] == 0
@@ -667,7 +666,7 @@ def test_context_reuse_across_meshes_of_different_scale(oracle_mod, gpu_ctx_fact
         g.build_items("iso")
         g.set_num_clusters(150)
         g.initial_sampling()
-        rep = g.minimize()
+        rep = g.minimize(bulk_rounds=1000)
         assert rep["bulk_rounds"] > 0 and rep["disconnected"] == 0
         o = oracle_mod.Oracle(ps, t)
         o.build_metric("iso")
