@@ -201,7 +201,8 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
         TraceScope ts(c, "set_mesh: csr + incidence");
         const int64_t n3 = 3 * (int64_t)F;
         DevBuf<int> cnt, cursor, he, deg;
-        cnt.alloc((size_t)V + 1); cursor.alloc(V); he.alloc((size_t)(2 * n3)); deg.alloc((size_t)V + 1);
+        DevBuf<int4> rec;
+        cnt.alloc((size_t)V + 1); cursor.alloc(V); he.alloc((size_t)(2 * n3)); deg.alloc((size_t)V + 1); rec.alloc((size_t)n3);
         c->vf_ptr.alloc((size_t)V + 1); c->vf_keys.alloc((size_t)n3); c->row_ptr.alloc((size_t)V + 1);
         ACVD_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         ACVD_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)V * sizeof(int), c->stream));
@@ -212,9 +213,9 @@ extern "C" int acvd_set_mesh(acvd_ctx* c, int32_t V, int32_t F, const float* xyz
         ACVD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, c->vf_ptr.p, V + 1, c->stream));
         void* t = cub_temp(c, tb);
         ACVD_CUDA(cub::DeviceScan::ExclusiveSum(t, tb, cnt.p, c->vf_ptr.p, V + 1, c->stream));
-        k_scatter_corners<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, c->vf_ptr.p, cursor.p, c->vf_keys.p, he.p);
+        k_scatter_corners<<<grid_for(F), kThreads, 0, c->stream>>>(F, c->tri.p, c->vf_ptr.p, cursor.p, rec.p);
         ACVD_LAUNCH_CHECK();
-        k_sort_rows<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->vf_ptr.p, c->vf_keys.p, he.p, deg.p);
+        k_sort_rows<<<grid_for(V), kThreads, 0, c->stream>>>(V, c->vf_ptr.p, rec.p, c->vf_keys.p, he.p, deg.p);
         ACVD_LAUNCH_CHECK();
         ACVD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, deg.p, c->row_ptr.p, V + 1, c->stream));
         t = cub_temp(c, tb);

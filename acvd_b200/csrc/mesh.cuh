@@ -28,8 +28,8 @@ __global__ void k_count_corners(int F, const int* __restrict__ tri, int* cnt) {
     }
 }
 
-__global__ void k_scatter_corners(int F, const int* __restrict__ tri, const int* __restrict__ off, int* cursor,
-                                  unsigned long long* vf_keys, int* he) {
+// every corner drops ONE 16-byte record (face, next vertex, previous vertex) into its vertex' segment: one store per corner
+__global__ void k_scatter_corners(int F, const int* __restrict__ tri, const int* __restrict__ off, int* cursor, int4* rec) {
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
         const int v[3] = {tri[3 * (int64_t)f], tri[3 * (int64_t)f + 1], tri[3 * (int64_t)f + 2]};
         if (v[0] == v[1]) continue;
@@ -37,25 +37,68 @@ __global__ void k_scatter_corners(int F, const int* __restrict__ tri, const int*
         for (int k = 0; k < 3; k++) {
             const int u = v[k], nxt = v[(k + 1) % 3], prv = v[(k + 2) % 3];
             const int64_t pos = (int64_t)off[u] + atomicAdd(cursor + u, 1);
-            vf_keys[pos] = ((unsigned long long)(unsigned)u << 32) | (unsigned)f;
-            he[2 * pos] = nxt != u ? nxt : kNoNeighbour;      // self loops are rejected (:1168-1172)
-            he[2 * pos + 1] = prv != u ? prv : kNoNeighbour;
+            rec[pos] = make_int4(f, nxt != u ? nxt : kNoNeighbour, prv != u ? prv : kNoNeighbour, 0);   // self loops are rejected (:1168-1172)
         }
     }
 }
 
-__global__ void k_sort_rows(int V, const int* __restrict__ off, unsigned long long* vf_keys, int* he, int* deg) {
+// Batcher's odd-even merge sort as a compile-time network (N a power of two): every index is static, so the keys stay in registers
+template <typename T, int N>
+__device__ __forceinline__ void sort_network(T (&a)[N]) {
+#pragma unroll
+    for (int p = 1; p < N; p *= 2)
+#pragma unroll
+        for (int k = p; k >= 1; k /= 2)
+#pragma unroll
+            for (int j = k % p; j <= N - 1 - k; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i < k; i++)
+                    if (i + j + k < N && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        const T lo = a[i + j] < a[i + j + k] ? a[i + j] : a[i + j + k];
+                        const T hi = a[i + j] < a[i + j + k] ? a[i + j + k] : a[i + j];
+                        a[i + j] = lo; a[i + j + k] = hi;
+                    }
+}
+
+// one thread per vertex: its records -> faces ascending (vf_keys, kept) and distinct neighbours ascending (he, for k_compact_rows)
+__global__ void k_sort_rows(int V, const int* __restrict__ off, const int4* __restrict__ rec, unsigned long long* vf_keys, int* he, int* deg) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         const int64_t b = off[v];
         const int m = off[v + 1] - off[v];
         unsigned long long* fk = vf_keys + b;
+        int* h = he + 2 * b;
+        const unsigned long long vhi = (unsigned long long)(unsigned)v << 32;
+        if (m <= 8) {
+            // the common row (up to 8 incident faces, 16 half-edge ends): sorted in registers by a network, one pass over memory
+            unsigned long long f[8];
+            int hh[16];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                int4 r = make_int4(0, kNoNeighbour, kNoNeighbour, 0);
+                if (i < m) r = __ldg(rec + b + i);
+                f[i] = i < m ? (vhi | (unsigned)r.x) : ~0ull;
+                hh[2 * i] = r.y; hh[2 * i + 1] = r.z;
+            }
+            sort_network<unsigned long long, 8>(f);
+            sort_network<int, 16>(hh);
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (i < m) fk[i] = f[i];
+            int d = 0, last = -1;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int x = hh[i];
+                if (x != kNoNeighbour && x != last) { h[d++] = x; last = x; }      // ascending: duplicates are adjacent
+            }
+            deg[v] = d;
+            continue;
+        }
+        for (int i = 0; i < m; i++) { const int4 r = rec[b + i]; fk[i] = vhi | (unsigned)r.x; h[2 * i] = r.y; h[2 * i + 1] = r.z; }
         for (int i = 1; i < m; i++) {                    // faces ascending
             const unsigned long long x = fk[i];
             int j = i - 1;
             while (j >= 0 && fk[j] > x) { fk[j + 1] = fk[j]; j--; }
             fk[j + 1] = x;
         }
-        int* h = he + 2 * b;
         for (int i = 1; i < 2 * m; i++) {                // neighbours ascending, kNoNeighbour last
             const int x = h[i];
             int j = i - 1;
