@@ -86,6 +86,7 @@ SYMBOLS = [
     ("acvd_get_cluster_stats", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ("acvd_global_energy", C.c_int, [_vp, C.POINTER(_d)]),
     ("acvd_get_energy_log", C.c_int, [_vp, _vp, _i32, C.POINTER(_i32)]),
+    ("acvd_get_energy_times", C.c_int, [_vp, _vp, _i32, C.POINTER(_i32)]),
     ("acvd_representative_points", C.c_int, [_vp, _i32, _vp, _vp, _i32, _d, _vp]),
     ("acvd_cluster_quadrics", C.c_int, [_vp, _i32, _vp]),
     ("acvd_boundary_flags", C.c_int, [_vp, _vp]),
@@ -327,6 +328,14 @@ class Context:
         self._ck(self.L.acvd_get_energy_log(self.h, None, 0, C.byref(n)))
         out = np.zeros(n.value)
         self._ck(self.L.acvd_get_energy_log(self.h, _p(out), n.value, C.byref(n)))
+        return out
+
+    def energy_times(self):
+        """seconds since the start of the last minimize() at which each entry of energy_log() was taken"""
+        n = C.c_int32()
+        self._ck(self.L.acvd_get_energy_times(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value)
+        self._ck(self.L.acvd_get_energy_times(self.h, _p(out), n.value, C.byref(n)))
         return out
 
     def representative_points(self, quadrics9, points3, max_sv=3, sv_threshold=1e-3):

@@ -1556,7 +1556,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
     auto t0 = std::chrono::steady_clock::now();
     acvd_report R;
     memset(&R, 0, sizeof R);
-    c->energy_log.clear();
+    c->energy_log.clear(); c->energy_time.clear();
 
     // SetConstrainedClustering(0) when UnconstrainedInitialization (:683-688); only QEM honours it
     int constrained = (c->metric == M_QEM && p.unconstrained_init) ? 0 : 1;
@@ -1632,6 +1632,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                     if (p.log_energy) {   // exact energy of the current clustering (test/trace path only)
                         recompute_statistics(c, constrained, qlevel, thr);
                         c->energy_log.push_back(global_energy(c));
+                        c->energy_time.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
                     }
                     if (trace_on())
                         fprintf(stderr, "[acvd trace] bulk  %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
@@ -1647,7 +1648,7 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                         if (e > e_prev) {
                             bulk_rollback(c);
                             R.modifications -= (int64_t)r.mods; R.bulk_rollbacks++;
-                            if (p.log_energy && !c->energy_log.empty()) c->energy_log.pop_back();
+                            if (p.log_energy && !c->energy_log.empty()) { c->energy_log.pop_back(); c->energy_time.pop_back(); }
                             break;
                         }
                         if (dry) break;
@@ -1679,7 +1680,10 @@ extern "C" int acvd_minimize(acvd_ctx* c, const acvd_params* pin, acvd_report* r
                 if (c->last_sparse_cluster) R.sparse_cluster_rounds++;
                 R.scan_bytes += sparse_scan_bytes(c, q);
             } else R.scan_bytes += scan_bytes(c, q);
-            if (p.log_energy) c->energy_log.push_back(global_energy(c));
+            if (p.log_energy) {
+                c->energy_log.push_back(global_energy(c));
+                c->energy_time.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+            }
             if (trace_on())
                 fprintf(stderr, "[acvd trace] %s %5lld conv %d tiles %8llu boundary %9llu evaluated %9llu tests %9llu proposals %9llu mods %8llu  scan %.0f eval %.0f commit %.0f us\n",
                         q.sparse ? "sprnd" : "round", (long long)loops, nconv, q.active_tiles, q.boundary, q.evaluated, q.tests, q.proposals, q.mods,
@@ -1795,6 +1799,13 @@ extern "C" int acvd_get_energy_log(acvd_ctx* c, double* out, int32_t cap, int32_
     if (!c) return fail(nullptr, ACVD_EINVAL, "null context");
     if (n) *n = (int32_t)c->energy_log.size();
     if (out) for (int i = 0; i < cap && i < (int)c->energy_log.size(); i++) out[i] = c->energy_log[i];
+    return ACVD_OK;
+}
+
+extern "C" int acvd_get_energy_times(acvd_ctx* c, double* out, int32_t cap, int32_t* n) {
+    if (!c) return fail(nullptr, ACVD_EINVAL, "null context");
+    if (n) *n = (int32_t)c->energy_time.size();
+    if (out) for (int i = 0; i < cap && i < (int)c->energy_time.size(); i++) out[i] = c->energy_time[i];
     return ACVD_OK;
 }
 

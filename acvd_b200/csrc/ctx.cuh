@@ -100,6 +100,7 @@ struct acvd_ctx {
     DevBuf<unsigned long long> winner, scalars;   // scalars: small device counters
     unsigned long long* h_scalars = nullptr;      // pinned, 8 entries + one active-tile count per round slot
     std::vector<double> energy_log;
+    std::vector<double> energy_time;   // seconds since the start of acvd_minimize at which each entry of energy_log was taken
     int stats_constrained = 1, stats_qlevel = 3;
     // multi-GPU (dist.cuh)
     ncclComm_t comm = nullptr;

@@ -134,14 +134,15 @@ void vtkDiscreteRemeshingB200::MinimizeEnergy(int connexity) {
     if (!Check(acvd_minimize(Ctx, &p, &Report), "acvd_minimize")) return;
     if (WriteEnergyLog) {
         // energy.txt: "loop seconds energy" per loop + final energy (vtkUniformClustering.h:677-699, 1384-1395);
-        // a loop here is a reassignment round and the time column is the round's share of the total
+        // a loop here is a reassignment round, stamped when its energy was taken (acvd_get_energy_times)
         int32_t n = 0;
         acvd_get_energy_log(Ctx, nullptr, 0, &n);
-        std::vector<double> log((size_t)n);
+        std::vector<double> log((size_t)n), when((size_t)n);
         acvd_get_energy_log(Ctx, log.data(), n, &n);
+        acvd_get_energy_times(Ctx, when.data(), n, &n);
         std::ofstream f(OutputDirectory + "energy.txt", std::ofstream::out | std::ofstream::trunc);
         for (int i = 0; i < n; i++)
-            f << i << " " << Report.ms_total * 1e-3 * (i + 1) / std::max(1, n) << " " << std::setprecision(15) << log[(size_t)i] << std::setprecision(6) << endl;
+            f << i << " " << when[(size_t)i] << " " << std::setprecision(15) << log[(size_t)i] << std::setprecision(6) << endl;
         f << "Final Energy :" << std::setprecision(15) << Report.energy << endl;
     }
     FetchClusters();

@@ -187,6 +187,9 @@ int acvd_get_cluster_stats(acvd_ctx* ctx, double* sums, double* centroid /*3K*/,
                            int32_t* sizes /*K*/);
 int acvd_global_energy(acvd_ctx* ctx, double* energy);
 int acvd_get_energy_log(acvd_ctx* ctx, double* out, int32_t cap, int32_t* n);
+/* seconds since the start of the acvd_minimize call at which each entry of the energy log was taken: the time column of
+ * energy.txt (the reference's timer, Common/vtkUniformClustering.h:690-706, stamps every loop) */
+int acvd_get_energy_times(acvd_ctx* ctx, double* out, int32_t cap, int32_t* n);
 
 /* vtkQuadricTools::ComputeRepresentativePoint (Common/vtkQuadricTools.cxx:168-177), batched:
  * n quadrics (9 doubles each) and points (3 doubles each, updated in place), rank deficiency out. */

@@ -180,6 +180,8 @@ def test_minimize_energy_within_one_percent(oracle_mod, gpu_ctx_factory, sphere,
     assert g.clean_clustering() == 0          # every cluster connected
     log = g.energy_log()
     assert rep["modifications"] > 0 and rep["rounds"] == len(log)
+    when = g.energy_times()
+    assert len(when) == len(log) and np.all(np.diff(when) >= 0) and when[-1] <= 1e-3 * rep["ms_total"] + 1e-3
     # energy: raw (energy.txt parity number) and translation-invariant sum w |p - c|^2
     it = o.items()
     w = it[:, 3]
