@@ -360,9 +360,9 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
     ReassignArgs A = make_args(c, cfg, 0, force_all);
     A.bulk = 1; A.bulk_stage = stage; A.bulk_count_leave = 0;
     BulkArgs B = make_bulk_args(c);
-    ACVD_CUDA(cudaMemsetAsync(c->ctr.p, 0, sizeof(RoundCounters), c->stream));
-    ACVD_CUDA(cudaMemsetAsync(c->round_scalars.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, nullptr, nullptr, 0, c->csize.p, c->cmeta.p);
+    // (the round's counters are opened by k_modbits: one launch instead of three)
+    k_modbits<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->mod_round.p, c->round - 1, force_all, c->modbits.p, c->ctr.p,
+                                                          c->round_scalars.p, 2, c->csize.p, c->cmeta.p);
     ACVD_LAUNCH_CHECK();
     int t0, t1;
     dist_tile_range(c, t0, t1);
@@ -405,6 +405,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
         k_bulk_refresh<<<grid_for(c->K), kThreads, 0, c->stream>>>(c->K, c->csize.p, B);
         ACVD_LAUNCH_CHECK();
         ACVD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        if (stage == 1) bulk_energy_enqueue(c);          // the energy guard's sum travels with the counters
         ACVD_CUDA(cudaMemcpy2DAsync(c->h_hdr, 64, c->moves_all.p, seg, 64, (size_t)W, cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(RoundCounters), cudaMemcpyDeviceToHost, c->stream));
         ACVD_CUDA(cudaStreamSynchronize(c->stream));
@@ -415,6 +416,7 @@ static RoundResult run_bulk_round_dist(acvd_ctx* c, int force_all, int stage) {
             r.proposals += h[1]; r.tests += h[2]; r.evaluated += h[3]; r.boundary += h[4]; r.active_tiles += h[5];
         }
         c->bulk_cap_next = std::max<long long>(4096, mx + mx / 2 + 1024);
+        if (mx > cap) c->bulk_energy_pending = false;       // the round is repeated below: its energy is summed again
         if (mx <= cap) {
             exchanged = true;
             c->last_bulk_seg = true; c->last_bulk_total = total; c->last_seg_bytes = (long long)seg; c->last_seg_cap = cap;
