@@ -353,6 +353,11 @@ struct WarpPush {
 constexpr int kEnumChunks = 4;          // 32-member chunks of one modified cluster handled by different warps
 
 // (modin: written by the previous round of the same launch, so no read-only path)
+// One 32-member batch of a modified cluster: the stage-by-stage gathers are written for TWO batches side by side (the two
+// tasks a warp takes per iteration), so that the eight dependent levels of a batch (cluster id -> offsets -> member ->
+// row -> neighbours -> their clusters -> their stamps -> claims) are paid once per pair: the step is bound by that chain.
+struct EnumBatch { int c, b, n, i0; bool on; };
+
 static __device__ __noinline__ void enumerate_modified(const ReassignArgs& A, const int* modin, int n_modin, int* s_buf) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -360,36 +365,49 @@ static __device__ __noinline__ void enumerate_modified(const ReassignArgs& A, co
     const int round = A.round;
     unsigned n_members = 0;
     const int n_tasks = n_modin * kEnumChunks;
-    for (int task = warp; task < n_tasks; task += n_warps) {
-        const int c = modin[task / kEnumChunks];
-        const int b = A.mem.off[c], n = A.csize[c];
-        for (int i0 = (task % kEnumChunks) * 32; i0 < n; i0 += kEnumChunks * 32) {
-            const int i = i0 + lane;
-            const bool live = i < n;
-            const int v = live ? A.mem.memb[b + i] : 0;
-            const int beg = live ? A.row_ptr[v] : 0, deg = live ? A.row_ptr[v + 1] - beg : 0;
-            // the gathers of one member batch are issued stage by stage, all slots of a stage in flight together
-            int nb[kRingW], cu[kRingW], st[kRingW];
+
+    // gathers of two batches, level by level; the claims (atomicExch on the stamps) and the list appends one batch after the other
+    auto run_pair = [&](const EnumBatch (&B)[2]) {
+        int v[2], beg[2], deg[2];
+        bool live[2];
 #pragma unroll
-            for (int k = 0; k < kRingW; k++) nb[k] = k < deg ? A.col[beg + k] : -1;
+        for (int t = 0; t < 2; t++) {
+            live[t] = B[t].on && B[t].i0 + lane < B[t].n;
+            v[t] = live[t] ? A.mem.memb[B[t].b + B[t].i0 + lane] : 0;
+        }
 #pragma unroll
-            for (int k = 0; k < kRingW; k++) cu[k] = nb[k] >= 0 ? A.cid[nb[k]] : c;
+        for (int t = 0; t < 2; t++) { beg[t] = live[t] ? A.row_ptr[v[t]] : 0; deg[t] = live[t] ? A.row_ptr[v[t] + 1] - beg[t] : 0; }
+        int nb[2][kRingW], cu[2][kRingW], st[2][kRingW];
 #pragma unroll
-            for (int k = 0; k < kRingW; k++) st[k] = cu[k] != c ? A.stamp[nb[k]] : round;
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+            for (int k = 0; k < kRingW; k++) nb[t][k] = k < deg[t] ? A.col[beg[t] + k] : -1;
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+            for (int k = 0; k < kRingW; k++) cu[t][k] = nb[t][k] >= 0 ? A.cid[nb[t][k]] : B[t].c;
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+            for (int k = 0; k < kRingW; k++) st[t][k] = cu[t][k] != B[t].c ? A.stamp[nb[t][k]] : round;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            if (!B[t].on) continue;                      // (warp-uniform)
+            const int c = B[t].c;
             bool bnd = false;
 #pragma unroll
             for (int k = 0; k < kRingW; k++) {
-                const bool foreign = cu[k] != c;
+                const bool foreign = cu[t][k] != c;
                 bnd |= foreign;
-                const bool add = foreign && st[k] != round && atomicExch(A.stamp + nb[k], round) != round;
-                wp.push(add, nb[k], lane);
+                const bool add = foreign && st[t][k] != round && atomicExch(A.stamp + nb[t][k], round) != round;
+                wp.push(add, nb[t][k], lane);
             }
-            const int extra = __reduce_max_sync(0xffffffffu, deg) - kRingW;     // rows longer than kRingW: slot by slot
+            const int extra = __reduce_max_sync(0xffffffffu, deg[t]) - kRingW;     // rows longer than kRingW: slot by slot
             for (int k = 0; k < extra; k++) {
                 bool add = false;
                 int u = 0;
-                if (kRingW + k < deg) {
-                    u = A.col[beg + kRingW + k];
+                if (kRingW + k < deg[t]) {
+                    u = A.col[beg[t] + kRingW + k];
                     if (A.cid[u] != c) {
                         bnd = true;
                         add = A.stamp[u] != round && atomicExch(A.stamp + u, round) != round;
@@ -397,12 +415,35 @@ static __device__ __noinline__ void enumerate_modified(const ReassignArgs& A, co
                 }
                 wp.push(add, u, lane);
             }
-            const bool addv = bnd && atomicExch(A.stamp + v, round) != round;
-            wp.push(addv, v, lane);
+            const bool addv = bnd && atomicExch(A.stamp + v[t], round) != round;
+            wp.push(addv, v[t], lane);
             // a member that is no boundary vertex any more (its last foreign neighbour joined the cluster) drops the
             // proposal it may still hold, as it does on the tile-filter path: it is not carried over
-            if (live && !bnd) A.stamp[v] = round;
-            n_members += live ? 1u : 0u;
+            if (live[t] && !bnd) A.stamp[v[t]] = round;
+            n_members += live[t] ? 1u : 0u;
+        }
+    };
+
+    for (int task0 = warp; task0 < n_tasks; task0 += 2 * n_warps) {
+        EnumBatch B[2];
+        int ct[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int task = task0 + t * n_warps;
+            B[t].on = task < n_tasks;
+            ct[t] = B[t].on ? modin[task / kEnumChunks] : 0;
+            B[t].i0 = B[t].on ? (task % kEnumChunks) * 32 : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) { B[t].c = ct[t]; B[t].b = A.mem.off[ct[t]]; B[t].n = B[t].on ? A.csize[ct[t]] : 0; }
+        run_pair(B);
+        // clusters with more than kEnumChunks x 32 members (rare): the further batches of the two tasks
+        while (true) {
+            bool more = false;
+#pragma unroll
+            for (int t = 0; t < 2; t++) { B[t].i0 += kEnumChunks * 32; B[t].on = B[t].on && B[t].i0 < B[t].n; more |= B[t].on; }
+            if (!more) break;
+            run_pair(B);
         }
     }
     wp.flush(lane);
